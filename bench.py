@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- kNN-graph contigs/sec on the headline workload of BASELINE.json:
+N = 1,000,000 synthetic contigs, embedding width 100 (float32), k = 200
+(SemiBin/cluster.py:94-99, max_edges default 200), exact neighbour sets.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N] [--k K]
+
+A "step" is one complete kNN-graph build over all N contigs: FP16 staging,
+tcgen05 threshold + filter passes over all N x N pairs, FP64 rerank with the
+exactness certificate, and (N > 1 GPUs) the NCCL all-gather of the row blocks.
+`value` is timed with the embedding already resident in HBM; `e2e` goes through
+the public host-buffer call (pinned host embedding in, pinned host (dist, idx)
+out, copies inside the timed region).
+N > 1: one process per GPU (torchrun), query rows sharded, references
+replicated, total work fixed -> "scaling": "strong".
+--impl reference times the reference's own path (scikit-learn brute-force
+kneighbors, the code SemiBin calls) on the host cores on a bounded row sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_DEFAULT = 1_000_000
+K_DEFAULT = 200
+D_EMB = 100
+SEED = 20242
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return dict(tflops=float(j.get('bf16_tflops_sustained', j['bf16_tflops'])), hbm=float(j['hbm_gbs']),
+                        source='MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)')
+        except Exception:
+            pass
+    return dict(tflops=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)')
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = False
+        self.samples = []
+        self.max_mhz = None
+        self.reasons = set()
+        self.err = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
+                getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
+                getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
+                getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
+            }
+            while not self.stop_flag:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((mhz, util))
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.05)
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def summary(self):
+        loaded = [m for m, u in self.samples if u >= 50] or [m for m, _ in self.samples]
+        med = float(np.median(loaded)) if loaded else None
+        out = {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        if self.err:
+            out['error'] = self.err
+        return out
+
+
+def synth_embeddings(n):
+    from semibin_b200 import synth
+    return synth.embeddings(n, seed=SEED)
+
+
+def reference_knn_block(X, k, rows):
+    """The reference's own code path for a block of query rows: sklearn brute
+    force (ArgKmin32), the call SemiBin/cluster.py:94-99 makes."""
+    from oracle import knn as ok
+    return ok.knn_sklearn(X, k, q_begin=rows[0], q_end=rows[1])
+
+
+def run_reference(args):
+    rank = env_int('RANK', 0)
+    if rank != 0:
+        return 0
+    n, k = args.n, args.k
+    X = synth_embeddings(n)
+    cores = os.cpu_count()
+    total_steps = args.steps + args.warmup
+    # bounded sample: ~8e9 pairs per step at the default N (about 10-30 s on 8-32 cores)
+    block = max(256, min(n, int(8.2e9 / n)))
+    if total_steps > 8:
+        block = max(256, block * 8 // total_steps)
+    lo = (n // 2 // block) * block
+    for _ in range(args.warmup):
+        reference_knn_block(X, k, (lo, lo + block))
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        reference_knn_block(X, k, (lo, lo + block))
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = block / dt
+    sample = f'{block} query rows x all {n} references per step (sklearn NearestNeighbors brute, k+1={k + 1}), contigs/s = rows/s'
+    line = {
+        'impl': 'reference', 'metric': 'kNN-graph contigs/sec', 'value': value, 'unit': 'contigs/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
+                   'n': n, 'd': D_EMB, 'k': k},
+        'cpu_baseline': {'value': value, 'unit': 'contigs/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'contigs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from semibin_b200 import _lib
+    from semibin_b200.neighbors import knn
+    from semibin_b200 import dist as sdist
+
+    rank = env_int('RANK', 0)
+    world = env_int('WORLD_SIZE', 1)
+    local_rank = env_int('LOCAL_RANK', 0)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    _lib.require_cuda()
+    n, k = args.n, args.k
+    X_host = torch.from_numpy(synth_embeddings(n)).pin_memory()
+    X = X_host.cuda()
+    lo, hi = sdist.row_block(n, rank, world)
+    n_loc = hi - lo
+    out_d_host = torch.empty((n_loc, k), dtype=torch.float32).pin_memory()
+    out_i_host = torch.empty((n_loc, k), dtype=torch.int32).pin_memory()
+
+    def step(collect=None):
+        d, i, st = knn(X, k, q_begin=lo, q_end=hi, algo=args.algo, return_stats=True)
+        if world > 1:
+            d = sdist.all_gather_rows(d, n)
+            i = sdist.all_gather_rows(i, n)
+        if collect is not None:
+            collect.append(st)
+        return d, i
+
+    def step_e2e():
+        Xd = X_host.cuda(non_blocking=True)                       # H2D of this step's input
+        d, i = knn(Xd, k, q_begin=lo, q_end=hi, algo=args.algo)
+        out_d_host.copy_(d, non_blocking=True)                    # D2H of this step's result
+        out_i_host.copy_(i, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    stats = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        d, i = step(stats)
+    ev1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # end-to-end through the host-buffer call
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item())
+    sampler.join(timeout=2)
+
+    # dominant kernel: tcgen05 filter pass (per launch: one launch per step per rank)
+    peaks = measured_peaks()
+    filt_ms = float(np.mean([s['ms_filter'] for s in stats])) if stats else 0.0
+    n_filter_launch = stats[0]['n_chunks'] if stats else 1
+    flops = 2.0 * n_loc * n * D_EMB                               # algorithmic: true D, no padding credit
+    roofline = None
+    if filt_ms > 0:
+        ach = flops / n_filter_launch / (filt_ms / n_filter_launch * 1e-3) / 1e12
+        roofline = {'bound': 'tensor', 'kernel': 'tc_kernel<FILTER>', 'achieved': ach, 'peak': peaks['tflops'],
+                    'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+                    'peak_source': peaks['source'], 'ms_per_launch': filt_ms / n_filter_launch,
+                    'algorithmic_flops_per_launch': flops / n_filter_launch}
+    stage_ms = {key: float(np.mean([s[key] for s in stats])) for key in
+                ('ms_prepare', 'ms_sample', 'ms_filter', 'ms_rerank', 'ms_fallback', 'ms_exact_filter')} if stats else {}
+
+    if rank == 0:
+        line = {
+            'metric': 'kNN-graph contigs/sec', 'value': n / (ms_step * 1e-3), 'unit': 'contigs/s',
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+            'dtype': 'f16 tensor-core filter + f64 rerank (exact result)', 'data': 'synthetic',
+            'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
+                       'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo, 'parallelism': f'row-block x{world}, references replicated',
+                       'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
+            'clocks': sampler.summary(),
+            'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
+                    'h2d_bytes_per_step': int(X_host.numel() * 4),
+                    'd2h_bytes_per_step': int(out_d_host.numel() * 4 + out_i_host.numel() * 4),
+                    'api': 'semibin_b200.neighbors.knn on a pinned host embedding, (dist f32, idx i32) row block copied back to pinned host memory'},
+            'gpu_launches': int(sum(s['n_launches'] for s in stats)),
+            'roofline': roofline,
+            'stages_ms': stage_ms,
+            'knn_stats': {kk: stats[-1][kk] for kk in ('algo_used', 'n_chunks', 'n_fallback_rows', 'n_candidates',
+                                                       'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            Xn = X_host.numpy()
+            block = max(256, min(n, int(8.2e9 / n)))
+            lo_b = (n // 2 // block) * block
+            t0 = time.perf_counter()
+            rd, ri = reference_knn_block(Xn, k, (lo_b, lo_b + block))
+            dt = time.perf_counter() - t0
+            # the baseline sample doubles as a parity spot check of the last step's result
+            from oracle import compare
+            res = compare.compare_knn(rd, ri, d[lo_b:lo_b + block].cpu().numpy().astype(np.float64),
+                                      i[lo_b:lo_b + block].cpu().numpy().astype(np.int64), rtol=1e-5)
+            line['cpu_baseline'] = {'value': block / dt, 'unit': 'contigs/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                                    'sample': f'{block} query rows x all {n} references, live scikit-learn brute kneighbors (the call SemiBin makes), one run',
+                                    'parity_rows_bad': res['n_rows_bad'], 'parity_rows_tied': res['n_rows_tied']}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--n', type=int, default=N_DEFAULT)
+    ap.add_argument('--k', type=int, default=K_DEFAULT)
+    ap.add_argument('--algo', default='auto')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

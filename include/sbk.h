@@ -1,0 +1,172 @@
+/* sbk.h -- C-ABI of libsbk.so: the B200 (sm_100a) kernels behind SemiBin's
+ * clustering front end.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Every entry point replaces one call site of the reference (paths relative to
+ * the SemiBin source tree; sklearn/ paths relative to site-packages of the
+ * scikit-learn 1.9.0 wheel the reference pins, pixi.lock:4152-4153):
+ *
+ *   sbk_knn                 sklearn.neighbors.kneighbors_graph(X, k, mode='distance', p=2)
+ *                             SemiBin/cluster.py:94-99 (float32 embedding), :100-105 (float64
+ *                             features), SemiBin/long_read_cluster.py:108-113
+ *                             -> sklearn/neighbors/_base.py:756-1041, ArgKmin32/64
+ *   sbk_edges_stage1        SemiBin/cluster.py:109-122  (kNN(emb) ∩ kNN(features), 1-min(d,1),
+ *                             row max, per-threshold counts for the max_node search)
+ *   sbk_edges_stage2        SemiBin/cluster.py:127-151 + cal_kl :13-60 evaluated only at
+ *                             surviving edges (threshold prune, KL factor, <=1e-6 cut,
+ *                             upper triangle, row-major compaction)
+ *   sbk_radius_sweep        sklearn.cluster.dbscan(..., metric='precomputed') neighbourhood
+ *                             + core test, SemiBin/long_read_cluster.py:115-120
+ *                             -> sklearn/cluster/_dbscan.py:430-463
+ *   sbk_dbscan_labels       sklearn/cluster/_dbscan_inner.pyx (label expansion)
+ *
+ * Ownership: the caller allocates every buffer (inputs, outputs, workspace) on
+ * the current CUDA device and keeps it alive until the stream is synchronised.
+ * The library allocates nothing persistent.
+ * Errors: functions return 0 on success or a negative sbk_status; the message
+ * is available from sbk_last_error() (thread local).  Nothing throws across the
+ * ABI.  There is no CPU fallback: without a CUDA device every compute entry
+ * point returns SBK_ERR_CUDA.
+ * Threading: re-entrant per (device, stream); the only global state is the
+ * thread-local error slot.
+ */
+#ifndef SBK_H_
+#define SBK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBK_VERSION 100          /* 0.1.0 */
+
+typedef enum sbk_status {
+  SBK_OK = 0,
+  SBK_ERR_INVALID = -1,          /* bad argument (k >= n, unsupported width, ...) */
+  SBK_ERR_WORKSPACE = -2,        /* workspace too small */
+  SBK_ERR_CUDA = -3,             /* CUDA runtime error / no device */
+  SBK_ERR_INTERNAL = -4          /* exactness certificate could not be established */
+} sbk_status;
+
+typedef enum sbk_dtype { SBK_F32 = 0, SBK_F64 = 1 } sbk_dtype;
+
+typedef enum sbk_knn_algo {
+  SBK_KNN_AUTO = 0,              /* tensor-core filter for large n, exact filter otherwise */
+  SBK_KNN_EXACT = 1,             /* FP64 CUDA-core filter (also the certificate fallback) */
+  SBK_KNN_TENSOR = 2             /* tcgen05 FP16 filter + FP64 rerank with exactness certificate */
+} sbk_knn_algo;
+
+/* Filled (when non-NULL) after the call's work is complete; passing a non-NULL
+ * pointer makes sbk_knn synchronise the stream before returning. */
+typedef struct sbk_knn_stats {
+  int32_t algo_used;             /* sbk_knn_algo actually run */
+  int32_t n_chunks;              /* query chunks processed */
+  int64_t n_fallback_rows;       /* rows whose certificate failed -> exact filter */
+  int64_t n_candidates;          /* total candidates reranked in FP64 */
+  int32_t sample_size;           /* reference sample used for thresholds (tensor path) */
+  int32_t cand_capacity;         /* per-row candidate slots (tensor path) */
+  int32_t order_stat;            /* which group-min order statistic set the threshold */
+  int32_t kpad;                  /* padded K of the FP16 operands */
+  int32_t n_launches;            /* kernels launched by this call */
+  int32_t reserved;
+  /* device time per stage, CUDA events on `cuda_stream`, summed over chunks (ms) */
+  float ms_prepare;              /* centre/scale/FP16 staging */
+  float ms_sample;               /* tcgen05 threshold pass over the reference sample */
+  float ms_filter;               /* tcgen05 filter pass over all references (dominant kernel) */
+  float ms_rerank;               /* FP64 rerank + certificate */
+  float ms_fallback;             /* exact filter + rerank of uncertified rows */
+  float ms_exact_filter;         /* exact path: FP64 filter */
+} sbk_knn_stats;
+
+int sbk_version(void);
+const char* sbk_last_error(void);
+/* Number of CUDA devices visible (0 when none / no driver). */
+int sbk_device_count(void);
+
+/* Workspace (bytes) sbk_knn needs for a block of n_query rows. */
+size_t sbk_knn_workspace_bytes(int dtype, int64_t n_ref, int32_t d, int64_t n_query, int32_t k,
+                               int algo);
+
+/* Exact Euclidean k nearest neighbours of rows [q_begin, q_end) of X among all
+ * n_ref rows of X, self excluded (by index; if self is not among the k+1
+ * nearest because of >k exact duplicates the first entry is dropped), ordered
+ * by (distance, index).  X is row-major [n_ref, ld] on the device.
+ *   out_dist : float[(q_end-q_begin)*k]  for SBK_F32 input, value
+ *              f32(sqrt(f64(f32(d2))))  (sklearn _argkmin.pyx.tp:285-295)
+ *              double[...]              for SBK_F64 input, value sqrt(d2)
+ *   out_idx  : int32[(q_end-q_begin)*k]
+ * d2 is the FP64 direct-difference squared distance. */
+int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+            int64_t q_begin, int64_t q_end, int32_t k,
+            void* out_dist, int32_t* out_idx,
+            void* workspace, size_t ws_bytes, int algo,
+            sbk_knn_stats* stats, void* cuda_stream);
+/* sbk_knn synchronises `cuda_stream` before it returns (it reads back the
+ * certificate-failure count to size the fallback launch). */
+
+/* Number of thresholds of the max_node search (cluster.py:118-125). */
+#define SBK_MAX_THRESHOLDS 32
+
+/* Stage 1 of the short-read edge list for rows [row_begin, row_begin+n_rows):
+ *   w[r*k+c] = 1 - min(emb_dist, 1) if emb_idx[r*k+c] is also in kmer_idx row r
+ *              with kmer_dist != 0 and emb_dist != 0, else 0     (cluster.py:109-116)
+ *   rowmax[r] = max_c w[r*k+c]                                     (cluster.py:119)
+ *   counts[m] += #{r : rowmax[r] > thresholds[m]}  (int64, caller zeroes)   (:122)
+ * kmer_dist may be NULL (then every feature-graph entry counts as non-zero). */
+int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
+                     const double* kmer_dist, const int32_t* kmer_idx,
+                     int64_t n_rows, int32_t k,
+                     const double* thresholds, int32_t n_thresholds,
+                     double* w, double* rowmax, long long* counts, void* cuda_stream);
+
+size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k);
+
+/* Stage 2: drop w <= threshold, multiply by the KL factor (float32 op order of
+ * cluster.py:129-141 / cal_kl numpy branch) unless is_combined, drop <= 1e-6,
+ * keep column > row, emit row-major sorted.  depth is float[n_total, 2*n_sample]
+ * interleaved [mean_s, var_s] for ALL contigs (columns are global indices).
+ *   out_x/out_y : int32[capacity], out_v : double[capacity]
+ *   n_edges     : device int64, number of edges produced (if > capacity only
+ *                 the first `capacity` are written). */
+int sbk_edges_stage2(const double* w, const int32_t* emb_idx,
+                     int64_t row_begin, int64_t n_rows, int32_t k, double threshold,
+                     const float* depth, int32_t n_sample, int is_combined,
+                     int32_t* out_x, int32_t* out_y, double* out_v, int64_t capacity,
+                     long long* n_edges, void* workspace, size_t ws_bytes, void* cuda_stream);
+
+/* eps sweep over a distance-sorted kNN graph, rows [row_begin,row_begin+n_rows):
+ *   prefix_len[e*n_rows+r] = #{c : dist[r*k+c] <= eps[e]}   (double compare, eps python floats)
+ *   core[e*n_rows+r] = weight[row] + sum_{c<prefix} weight[idx] >= min_samples
+ * weight may be NULL (all ones).  dist/idx hold only the n_rows local rows;
+ * idx values and weight are global.  eps is a HOST array (n_eps <= 16); every
+ * other pointer is device memory. */
+int sbk_radius_sweep(const float* dist, const int32_t* idx, int64_t row_begin, int64_t n_rows,
+                     int32_t k, const double* eps, int32_t n_eps,
+                     const double* weight, double min_samples,
+                     int32_t* prefix_len, uint8_t* core, void* cuda_stream);
+
+size_t sbk_dbscan_labels_workspace_bytes(int64_t n, int32_t n_eps);
+
+/* DBSCAN labels for n_eps neighbourhood graphs at once (all n rows resident):
+ * labels[e*n+i] = rank of min{u core : u reaches i through core points} among
+ * the distinct seeds, or -1 (noise) -- identical to sklearn's dbscan_inner. */
+int sbk_dbscan_labels(const int32_t* idx, int64_t n, int32_t k,
+                      const int32_t* prefix_len, const uint8_t* core, int32_t n_eps,
+                      long long* labels, void* workspace, size_t ws_bytes, void* cuda_stream);
+
+/* Debug / test hook: raw tcgen05 tile product.  Computes, with the same FP16
+ * operand staging and MMA pipeline as the tensor filter, the matrix
+ *   s[i,j] = ||y_j - c||^2*S^2 - 2*S^2*<x_i - c, y_j - c>   (i < n_q, j < n_ref <= 65536)
+ * into out[n_q, ceil(n_ref/256)*256] (float) together with the per-row error
+ * bound E[n_q] and the exact scaled row norms nrm[n_q] followed by the scale S
+ * (nrm has n_q+1 doubles), so tests can verify |s - (S^2 d2 - nrm_i)| <= E_i. */
+int sbk_debug_tc_scores(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                        int64_t n_q, float* out, double* E, double* nrm,
+                        void* workspace, size_t ws_bytes, void* cuda_stream);
+size_t sbk_debug_tc_workspace_bytes(int64_t n_ref, int32_t d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBK_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libsbk.so (C-ABI declared in include/sbk.h).
+
+The product path has NO CPU fallback: a missing library or a missing CUDA
+device raises.  torch is used only to own device memory and streams.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libsbk.so')
+
+SBK_F32, SBK_F64 = 0, 1
+KNN_AUTO, KNN_EXACT, KNN_TENSOR = 0, 1, 2
+ALGOS = {'auto': KNN_AUTO, 'exact': KNN_EXACT, 'tensor': KNN_TENSOR}
+MAX_THRESHOLDS = 32
+
+
+class KnnStats(C.Structure):
+    _fields_ = [('algo_used', C.c_int32), ('n_chunks', C.c_int32),
+                ('n_fallback_rows', C.c_int64), ('n_candidates', C.c_int64),
+                ('sample_size', C.c_int32), ('cand_capacity', C.c_int32),
+                ('order_stat', C.c_int32), ('kpad', C.c_int32),
+                ('n_launches', C.c_int32), ('reserved', C.c_int32),
+                ('ms_prepare', C.c_float), ('ms_sample', C.c_float), ('ms_filter', C.c_float),
+                ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class SbkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); every symbol include/sbk.h declares
+SIGNATURES = {
+    'sbk_version': (C.c_int, []),
+    'sbk_last_error': (C.c_char_p, []),
+    'sbk_device_count': (C.c_int, []),
+    'sbk_knn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int]),
+    'sbk_knn': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(KnnStats), C.c_void_p]),
+    'sbk_edges_stage1': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sbk_edges_stage2_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
+    'sbk_edges_stage2': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double,
+                                   C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sbk_radius_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
+                                   C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_double,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    'sbk_dbscan_labels_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
+    'sbk_dbscan_labels': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sbk_debug_tc_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
+    'sbk_debug_tc_scores': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+
+def load():
+    """Load libsbk.so (building is done by __graft_entry__.build / _build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SbkError(f'{LIB_PATH} not found: build it with `python -m semibin_b200._build` '
+                       '(there is no CPU fallback)')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().sbk_last_error().decode('utf-8', 'replace')
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == -1:
+        raise ValueError(msg)
+    raise SbkError(f'libsbk error {rc}: {msg}')
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available() or load().sbk_device_count() < 1:
+        raise SbkError('semibin_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

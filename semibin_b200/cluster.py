@@ -1,0 +1,166 @@
+"""Short-read clustering front end: drop-in for SemiBin/cluster.py:64-168
+(`run_embed_infomap`) with the graph build on the GPU.
+
+    run_embed_infomap(logger, model, data, *, device, max_edges, max_node,
+                      is_combined, n_sample, contig_dict, num_process, random_seed)
+        -> (embedding float32 [N,100], contig_labels int [N])        cluster.py:64-66,168
+    build_edge_list(embedding, features, depth, *, max_edges, max_node,
+                    is_combined, n_sample) -> (X int32[E], Y int32[E], V float64[E])
+        the exact (edges, edge_weights) hand-off of cluster.py:144-151, row-major
+        sorted, Y > X, without materialising Python tuples.
+
+The embedding MLP forward stays in the reference model (north_star); the two
+kNN graphs, their intersection, the 1-min(d,1) transform, the max_node
+threshold, the KL/abundance factor (cal_kl evaluated at edges only) and the
+edge compaction run in libsbk (include/sbk.h).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from .neighbors import knn, _as_device_matrix, _workspace
+
+
+def threshold_sequence():
+    """Values `threshold` takes in cluster.py:118-125 (repeated += 0.05 in
+    float64 -- the drift is part of the reference semantics)."""
+    out = []
+    t = 0
+    while t < 1:
+        t += 0.05
+        out.append(t)
+    return out
+
+
+def pick_threshold(counts, num_contigs, max_node):
+    """cluster.py:118-126 given counts[m] = #(rowmax > threshold_m).  numpy
+    scalar types are kept so that round() is numpy's, as in the reference."""
+    threshold = 0
+    m = 0
+    while threshold < 1:
+        threshold += 0.05
+        n_above = np.int64(counts[m])
+        m += 1
+        if round(n_above / num_contigs, 2) < max_node:
+            break
+    threshold -= 0.05
+    return threshold
+
+
+def edges_stage1(emb_d, emb_i, kmer_d, kmer_i, thresholds):
+    """Device tensors in; returns (w [n,k] f64, rowmax [n] f64, counts int64[len(thresholds)])."""
+    import torch
+    lib = _lib.load()
+    n, k = emb_i.shape
+    dev = emb_i.device
+    thr = torch.tensor(thresholds, dtype=torch.float64, device=dev)
+    w = torch.empty((n, k), dtype=torch.float64, device=dev)
+    rowmax = torch.empty((n,), dtype=torch.float64, device=dev)
+    counts = torch.zeros((_lib.MAX_THRESHOLDS,), dtype=torch.int64, device=dev)
+    kd = kmer_d
+    if kd is not None and kd.dtype != torch.float64:
+        kd = kd.double()
+    rc = lib.sbk_edges_stage1(_lib.ptr(emb_d), _lib.ptr(emb_i), _lib.ptr(kd), _lib.ptr(kmer_i), n, k,
+                              _lib.ptr(thr), len(thresholds), _lib.ptr(w), _lib.ptr(rowmax), _lib.ptr(counts),
+                              _lib.stream_ptr())
+    _lib.check(rc)
+    return w, rowmax, counts[:len(thresholds)]
+
+
+def edges_stage2(w, emb_i, row_begin, threshold, depth, n_sample, is_combined, capacity=None):
+    """Returns device tensors (X int32, Y int32, V float64) for the local rows."""
+    import torch
+    lib = _lib.load()
+    n, k = emb_i.shape
+    dev = emb_i.device
+    if capacity is None:
+        capacity = n * k
+    ws_bytes = lib.sbk_edges_stage2_workspace_bytes(n, k)
+    ws = _workspace(ws_bytes, dev)
+    ox = torch.empty((capacity,), dtype=torch.int32, device=dev)
+    oy = torch.empty((capacity,), dtype=torch.int32, device=dev)
+    ov = torch.empty((capacity,), dtype=torch.float64, device=dev)
+    ne = torch.zeros((1,), dtype=torch.int64, device=dev)
+    rc = lib.sbk_edges_stage2(_lib.ptr(w), _lib.ptr(emb_i), row_begin, n, k, float(threshold),
+                              _lib.ptr(depth), int(n_sample), int(bool(is_combined)),
+                              _lib.ptr(ox), _lib.ptr(oy), _lib.ptr(ov), capacity, _lib.ptr(ne),
+                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc)
+    e = int(ne.item())
+    if e > capacity:
+        raise _lib.SbkError(f'edge list capacity {capacity} < {e}')
+    return ox[:e], oy[:e], ov[:e]
+
+
+def build_edge_list(embedding, features, depth, *, max_edges, max_node, is_combined, n_sample,
+                    algo='auto', return_graphs=False):
+    """Fused GPU path for cluster.py:94-151.
+
+    embedding : [N,100] float32      (model.embedding output, cluster.py:93)
+    features  : [N,136] float64, or [N,136+S] when is_combined (already normalised
+                as in cluster.py:81-86)
+    depth     : [N,2S] float32 interleaved [mean_s,var_s] (cluster.py:88); unused
+                when is_combined
+    Returns host numpy arrays (X int32[E], Y int32[E], V float64[E])."""
+    import torch
+    _lib.require_cuda()
+    emb = _as_device_matrix(embedding)
+    feat = _as_device_matrix(features)
+    if emb.dtype != torch.float32:
+        emb = emb.float()
+    N = emb.shape[0]
+    k = min(int(max_edges), N - 1)                       # cluster.py:96
+    a_d, a_i = knn(emb, k, algo=algo)                    # :94-99
+    b_d, b_i = knn(feat, k, algo=algo)                   # :100-105
+    ths = threshold_sequence()
+    w, rowmax, counts = edges_stage1(a_d, a_i, b_d, b_i, ths)      # :109-122
+    threshold = pick_threshold(counts.cpu().numpy(), N, max_node)  # :118-126
+    dep = None
+    if not is_combined:
+        dep = torch.as_tensor(np.ascontiguousarray(depth, dtype=np.float32)).cuda() \
+            if not isinstance(depth, torch.Tensor) else depth.float().contiguous().cuda()
+        if dep.shape != (N, 2 * n_sample):
+            raise ValueError(f'depth must be [N, 2*n_sample] = {(N, 2 * n_sample)}, got {tuple(dep.shape)}')
+    X, Y, V = edges_stage2(w, a_i, 0, threshold, dep, n_sample, is_combined)   # :127-151
+    out = (X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy())
+    if return_graphs:
+        return out, dict(emb=(a_d, a_i), kmer=(b_d, b_i), threshold=threshold)
+    return out
+
+
+def run_embed_infomap(logger, model, data, *, device, max_edges, max_node, is_combined, n_sample,
+                      contig_dict, num_process: int, random_seed):
+    """Drop-in for SemiBin.cluster.run_embed_infomap (same arguments, same
+    returns).  Infomap itself stays in igraph (consumer of the hand-off)."""
+    import torch
+    from igraph import Graph                                     # cluster.py:72 (consumer, out of scope)
+    NR_INFOMAP_TRIALS = 10                                       # cluster.py:11
+
+    train_data_input = data.values[:, 0:136] if not is_combined else data.values   # :79
+    if is_combined:
+        n = train_data_input.shape[1] - 136                      # utils.py:630-636 norm_abundance
+        if n >= 20 or (n >= 5 and np.mean(np.sum(train_data_input[:, 136:], axis=1)) > 2):
+            norm = np.sum(train_data_input, axis=0)              # cluster.py:83-86
+            train_data_input = train_data_input / norm
+            train_data_input = train_data_input / np.abs(train_data_input).sum(axis=1, keepdims=True)
+    depth = data.values[:, 136:len(data.values[0])].astype(np.float32)              # :88
+    num_contigs = train_data_input.shape[0]
+    with torch.no_grad():
+        model.eval()
+        x = torch.from_numpy(np.ascontiguousarray(train_data_input)).to(device)
+        emb_t = model.embedding(x.float()).detach()              # :90-93 (reference model)
+        embedding = emb_t.cpu().numpy()
+    X, Y, V = build_edge_list(emb_t if emb_t.is_cuda else embedding, train_data_input, depth,
+                              max_edges=max_edges, max_node=max_node, is_combined=is_combined,
+                              n_sample=n_sample)
+    logger.debug(f'Number of edges in clustering graph: {len(X)}')
+    g = Graph()
+    g.add_vertices(np.arange(num_contigs))
+    g.add_edges(list(zip(X.tolist(), Y.tolist())))
+    length_weight = np.array([len(contig_dict[name]) for name in data.index])
+    logger.debug(f'Running infomap with {num_process} processes...')
+    result = g.community_infomap(edge_weights=V, vertex_weights=length_weight, trials=NR_INFOMAP_TRIALS)
+    contig_labels = np.zeros(shape=num_contigs, dtype=int)
+    for i, r in enumerate(result):
+        contig_labels[r] = i
+    return embedding, contig_labels

@@ -1,0 +1,235 @@
+// edges.cu -- short-read edge list after the two kNN graphs
+// (SemiBin/cluster.py:109-151 and cal_kl :13-60 evaluated at edges only).
+// All kernels are HBM-bound streaming passes over the N x k neighbour rows.
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace sbk {
+
+static constexpr int E_THREADS = 128;
+static constexpr int E_MAXK = 1024;
+
+// Stage 1: one CTA per row.  w = 1 - min(d_emb, 1) where the column is in both
+// graphs and neither distance is an explicit zero (eliminate_zeros,
+// cluster.py:109,112); row max (cluster.py:119).
+__global__ void __launch_bounds__(E_THREADS)
+edges_stage1_kernel(const float* __restrict__ emb_dist, const int32_t* __restrict__ emb_idx,
+                    const double* __restrict__ kmer_dist, const int32_t* __restrict__ kmer_idx,
+                    int k, double* __restrict__ w, double* __restrict__ rowmax) {
+  __shared__ int32_t bidx[E_MAXK];
+  __shared__ double red[E_THREADS / 32];
+  const long long r = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int c = tid; c < k; c += E_THREADS) {
+    int32_t j = kmer_idx[r * k + c];
+    if (kmer_dist && kmer_dist[r * k + c] == 0.0) j = -1;       // explicit zero -> eliminated
+    bidx[c] = j;
+  }
+  __syncthreads();
+  double mx = 0.0;                                              // implicit zeros count
+  for (int c = tid; c < k; c += E_THREADS) {
+    const int32_t j = emb_idx[r * k + c];
+    const double d = (double)emb_dist[r * k + c];
+    bool found = false;
+    for (int t = 0; t < k; ++t) found |= (bidx[t] == j);
+    double ww = 0.0;
+    if (found && d != 0.0) ww = 1.0 - fmin(d, 1.0);
+    w[r * k + c] = ww;
+    mx = fmax(mx, ww);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < E_THREADS / 32; ++i) mx = fmax(mx, red[i]);
+    rowmax[r] = mx;
+  }
+}
+
+// counts[m] += #{r : rowmax[r] > thresholds[m]}   (cluster.py:122)
+__global__ void __launch_bounds__(256)
+threshold_count_kernel(const double* __restrict__ rowmax, long long n,
+                       const double* __restrict__ thresholds, int n_thr,
+                       unsigned long long* __restrict__ counts) {
+  __shared__ double thr[SBK_MAX_THRESHOLDS];
+  __shared__ unsigned int blk[SBK_MAX_THRESHOLDS];
+  if (threadIdx.x < SBK_MAX_THRESHOLDS) {
+    thr[threadIdx.x] = threadIdx.x < n_thr ? thresholds[threadIdx.x] : 0.0;
+    blk[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  unsigned int local[SBK_MAX_THRESHOLDS];
+#pragma unroll
+  for (int m = 0; m < SBK_MAX_THRESHOLDS; ++m) local[m] = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = rowmax[i];
+#pragma unroll
+    for (int m = 0; m < SBK_MAX_THRESHOLDS; ++m) local[m] += (m < n_thr && v > thr[m]) ? 1u : 0u;
+  }
+#pragma unroll
+  for (int m = 0; m < SBK_MAX_THRESHOLDS; ++m) {
+    unsigned int v = local[m];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&blk[m], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_thr && blk[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)blk[threadIdx.x]);
+}
+
+// float32 KL term of cal_kl (cluster.py:13-60, numpy evaluator :49-60), row i / col j:
+//   (log v_j - log v_i)/2 + ((m_j - m_i)^2 + v_i) / (2 v_j) - 0.5, clipped to [1e-6, 1-1e-6]
+// every operation individually rounded to float32 (no FMA contraction).  The
+// float32 log is taken as the correctly rounded value of the float64 log.
+__device__ __forceinline__ float kl_term(float mi, float vi, float mj, float vj) {
+  mi = fmaxf(mi, 1e-6f); mj = fmaxf(mj, 1e-6f);
+  vi = fmaxf(vi, 1.0f);  vj = fmaxf(vj, 1.0f);
+  const float lvi = (float)log((double)vi), lvj = (float)log((double)vj);
+  float v_div = __fsub_rn(lvj, lvi);
+  v_div = __fdiv_rn(v_div, 2.0f);
+  float m_dif = __fsub_rn(mj, mi);
+  m_dif = __fmul_rn(m_dif, m_dif);
+  m_dif = __fadd_rn(m_dif, vi);
+  m_dif = __fdiv_rn(m_dif, __fmul_rn(2.0f, vj));
+  v_div = __fadd_rn(v_div, m_dif);
+  v_div = __fsub_rn(v_div, 0.5f);
+  const float lo = 1e-6f, hi = (float)(1.0 - 1e-6);
+  return fminf(fmaxf(v_div, lo), hi);
+}
+
+// Stage 2a: one CTA per row: threshold prune, KL factor, <=1e-6 cut, upper
+// triangle, sort by column; result staged row-strided + per-row count.
+__global__ void __launch_bounds__(E_THREADS)
+edges_stage2_kernel(const double* __restrict__ w, const int32_t* __restrict__ emb_idx,
+                    long long row_begin, int k, double threshold,
+                    const float* __restrict__ depth, int n_sample, int is_combined,
+                    int32_t* __restrict__ stage_y, double* __restrict__ stage_v,
+                    int32_t* __restrict__ row_cnt) {
+  __shared__ double skey[E_MAXK];
+  __shared__ uint32_t sid[E_MAXK];
+  __shared__ double sval[E_MAXK];
+  __shared__ int s_n;
+  const long long r = blockIdx.x;
+  const long long gi = row_begin + r;
+  const int tid = threadIdx.x;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  for (int c = tid; c < k; c += E_THREADS) {
+    double ww = w[r * k + c];
+    const int32_t j = emb_idx[r * k + c];
+    bool keep = (ww != 0.0) && !(ww <= threshold);           // cluster.py:127-128
+    if (keep && !is_combined) {
+      const float* di = depth + gi * 2 * n_sample;
+      const float* dj = depth + (long long)j * 2 * n_sample;
+      float acc = 0.f;
+      for (int s = 0; s < n_sample; ++s) {
+        const float kl = kl_term(di[2 * s], di[2 * s + 1], dj[2 * s], dj[2 * s + 1]);
+        acc = (s == 0) ? -kl : __fsub_rn(acc, kl);            // kl *= -1 ; kl_matrix -= kl
+      }
+      acc = __fadd_rn(acc, (float)n_sample);                   // += n_sample
+      acc = __fdiv_rn(acc, (float)n_sample);                   // /= n_sample
+      ww = ww * (double)acc;                                   // cluster.py:141 (f64 * f32)
+    }
+    keep = keep && !(ww <= 1e-6) && ((long long)j > gi);       // :143, :146-148
+    if (keep) {
+      int p = atomicAdd(&s_n, 1);
+      skey[p] = (double)j; sid[p] = (uint32_t)p; sval[p] = ww;
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (tid == 0) row_cnt[r] = n;
+  if (n == 0) return;
+  int P = (int)pow2ceil((uint32_t)n);
+  if (P < 2) P = 2;
+  for (int t = n + tid; t < P; t += E_THREADS) { skey[t] = __longlong_as_double(0x7ff0000000000000LL); sid[t] = 0xffffffffu; }
+  block_bitonic_sort<E_THREADS>(skey, sid, P, tid);
+  for (int t = tid; t < n; t += E_THREADS) {
+    stage_y[r * k + t] = (int32_t)skey[t];
+    stage_v[r * k + t] = sval[sid[t]];
+  }
+}
+
+// Stage 2b: compaction to the row-major edge list.
+__global__ void __launch_bounds__(E_THREADS)
+edges_compact_kernel(const int32_t* __restrict__ stage_y, const double* __restrict__ stage_v,
+                     const int32_t* __restrict__ row_cnt, const long long* __restrict__ row_off,
+                     long long row_begin, long long n_rows, int k, long long capacity,
+                     int32_t* __restrict__ out_x, int32_t* __restrict__ out_y, double* __restrict__ out_v,
+                     long long* __restrict__ n_edges) {
+  const long long r = blockIdx.x;
+  const int n = row_cnt[r];
+  const long long o = row_off[r];
+  for (int t = threadIdx.x; t < n; t += E_THREADS) {
+    if (o + t < capacity) {
+      out_x[o + t] = (int32_t)(row_begin + r);
+      out_y[o + t] = stage_y[r * k + t];
+      out_v[o + t] = stage_v[r * k + t];
+    }
+  }
+  if (r == 0 && threadIdx.x == 0) *n_edges = row_off[n_rows];
+}
+
+}  // namespace sbk
+
+using namespace sbk;
+
+extern "C" int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
+                                const double* kmer_dist, const int32_t* kmer_idx,
+                                int64_t n_rows, int32_t k,
+                                const double* thresholds, int32_t n_thresholds,
+                                double* w, double* rowmax, long long* counts, void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (k < 1 || k > E_MAXK) { set_error("edges: k=%d outside [1,%d]", k, E_MAXK); return SBK_ERR_INVALID; }
+  if (n_thresholds < 0 || n_thresholds > SBK_MAX_THRESHOLDS) { set_error("edges: n_thresholds=%d", n_thresholds); return SBK_ERR_INVALID; }
+  if (n_rows <= 0) return SBK_OK;
+  edges_stage1_kernel<<<(unsigned)n_rows, E_THREADS, 0, stream>>>(emb_dist, emb_idx, kmer_dist, kmer_idx, k, w, rowmax);
+  SBK_LAUNCH_CHECK();
+  if (n_thresholds > 0) {
+    int blocks = (int)((n_rows + 256 * 16 - 1) / (256 * 16));
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    threshold_count_kernel<<<blocks, 256, 0, stream>>>(rowmax, n_rows, thresholds, n_thresholds,
+                                                       (unsigned long long*)counts);
+    SBK_LAUNCH_CHECK();
+  }
+  return SBK_OK;
+}
+
+extern "C" size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k) {
+  Arena a(nullptr, 0);
+  a.take<int32_t>((size_t)n_rows * k);
+  a.take<double>((size_t)n_rows * k);
+  a.take<int32_t>((size_t)n_rows + 1);
+  a.take<long long>((size_t)n_rows + 1);
+  a.take<long long>(scan_workspace_elems(n_rows));
+  return a.off + 256;
+}
+
+extern "C" int sbk_edges_stage2(const double* w, const int32_t* emb_idx,
+                                int64_t row_begin, int64_t n_rows, int32_t k, double threshold,
+                                const float* depth, int32_t n_sample, int is_combined,
+                                int32_t* out_x, int32_t* out_y, double* out_v, int64_t capacity,
+                                long long* n_edges, void* workspace, size_t ws_bytes, void* cuda_stream) {
+  cudaStream_t stream = (cudaStream_t)cuda_stream;
+  if (k < 1 || k > E_MAXK) { set_error("edges: k=%d outside [1,%d]", k, E_MAXK); return SBK_ERR_INVALID; }
+  if (!is_combined && (n_sample < 1 || depth == nullptr)) { set_error("edges: KL weighting needs depth and n_sample >= 1"); return SBK_ERR_INVALID; }
+  Arena a(workspace, ws_bytes);
+  int32_t* stage_y = a.take<int32_t>((size_t)n_rows * k);
+  double* stage_v = a.take<double>((size_t)n_rows * k);
+  int32_t* row_cnt = a.take<int32_t>((size_t)n_rows + 1);
+  long long* row_off = a.take<long long>((size_t)n_rows + 1);
+  long long* bsum = a.take<long long>(scan_workspace_elems(n_rows));
+  if (!a.ok()) { set_error("edges stage2: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
+  if (n_rows <= 0) { SBK_CUDA_CHECK(cudaMemsetAsync(n_edges, 0, sizeof(long long), stream)); return SBK_OK; }
+  edges_stage2_kernel<<<(unsigned)n_rows, E_THREADS, 0, stream>>>(w, emb_idx, row_begin, k, threshold, depth, n_sample,
+                                                                 is_combined, stage_y, stage_v, row_cnt);
+  SBK_LAUNCH_CHECK();
+  int rc = exclusive_scan(row_cnt, n_rows, row_off, bsum, stream);
+  if (rc) return rc;
+  edges_compact_kernel<<<(unsigned)n_rows, E_THREADS, 0, stream>>>(stage_y, stage_v, row_cnt, row_off, row_begin, n_rows, k,
+                                                                  capacity, out_x, out_y, out_v, n_edges);
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}

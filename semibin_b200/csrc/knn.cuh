@@ -1,0 +1,61 @@
+// knn.cuh -- internal launch interfaces of the kNN pipeline stages.
+#pragma once
+#include "common.cuh"
+
+namespace sbk {
+
+// ---- exact (FP64 CUDA-core) filter + rerank: knn_exact.cu ----
+int exact_filter_cap(int k1);
+size_t exact_filter_smem(int d, int k1);
+int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long long ld,
+                        const int32_t* rows, long long q_begin, long long n_q, int n_split, int k1,
+                        uint32_t* cand_idx, long long cand_stride, int32_t* cand_count,
+                        cudaStream_t stream);
+int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
+                  const int32_t* rows, long long q_begin, long long n_slots,
+                  const uint32_t* cand_idx, long long cand_stride, const int32_t* cand_count,
+                  const double* bound, int k,
+                  void* out_dist, int32_t* out_idx, long long out_row0,
+                  int32_t* fail_rows, int* n_fail, unsigned long long* cand_total,
+                  cudaStream_t stream);
+
+// ---- tensor-core (tcgen05) filter: knn_tc.cu ----
+struct TcPlan {
+  int kpad;            // padded K (multiple of 16) = d + 3 norm columns rounded up
+  int ksteps;          // kpad / 16
+  long long n_tiles;   // reference tiles of TC_BN rows
+  int sample_size;     // rows in the threshold sample (multiple of TC_BN)
+  int order_stat;      // r: threshold = r-th smallest group minimum
+  int n_groups;        // G
+  int cand_cap;        // candidate slots per query row
+  size_t stage_bytes;  // bytes of one staged reference tile
+};
+static constexpr int TC_BM = 128;   // query rows per CTA
+static constexpr int TC_BN = 256;   // reference rows per MMA tile
+
+struct TcScalars;
+struct TcState {
+  __half* a_tiles; __half* b_tiles; __half* s_tiles;
+  double* centre; double* colsum; double* scale; double* nrm;
+  float* dq; float* zq; TcScalars* sc; int32_t* sample_rows; float* thr;
+  unsigned long long* maxabs;
+  int nstage; long long n_ref; int d;
+};
+
+TcPlan tc_make_plan(long long n_ref, int d, int k);
+long long tc_chunk_rows(const TcPlan& p, long long n_ref);
+size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query);
+// Stage operands, centre/scale, sample; `chunk` = max query rows per tc_filter_chunk call.
+int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, const TcPlan& p,
+               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream);
+// Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
+// and certificate bounds bound[slot].
+int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
+                    cudaStream_t stream);
+// Filter pass over all references: fills cand_idx[slot*cand_cap..], cand_count[slot].
+int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
+                    uint32_t* cand_idx, int32_t* cand_count, cudaStream_t stream);
+int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
+int tc_row_errors(TcState* st, const TcPlan& p, long long n, double* E, double* nrm_out, cudaStream_t stream);
+
+}  // namespace sbk

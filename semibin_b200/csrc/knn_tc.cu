@@ -1,0 +1,676 @@
+// knn_tc.cu -- tcgen05 (5th-gen tensor core) candidate filter of the kNN graph.
+//
+// Replaces the 256x256-chunk dgemm + heap loop of sklearn's EuclideanArgKmin
+// (_middle_term_computer.pyx.tp:401-442, _argkmin.pyx.tp:490-510) reached from
+// SemiBin/cluster.py:94-105 and long_read_cluster.py:108-113.
+//
+// Data flow (all per GPU, references replicated):
+//   tc_stage_kernel   X (f32/f64) -> centred, power-of-two scaled FP16 operands in
+//                     core-matrix tiled layout + per-row norms / rounding-error norms
+//   tc_kernel<SAMPLE> every query tile x a pseudo-random reference sample:
+//                     per-row group minima -> order-statistic threshold thr_i and
+//                     the certificate bound_i
+//   tc_kernel<FILTER> every query tile x ALL reference tiles: emit column j as a
+//                     candidate iff s_ij <= thr_i
+// where   s_ij = ||z_j||^2 - 2 <zh_i, zh_j>   is produced DIRECTLY by the MMA: the
+// three spare K columns carry an FP16 hi/mid/lo split of ||z_j||^2 against ones.
+// ||z_i||^2 is constant per row and irrelevant for the ranking.
+//
+// Exactness: |s_ij - (S^2 d2_ij - ||z_i||^2)| <= E_i (bound derived from the
+// actual FP16 rounding residuals, see tc_stage_kernel / tc_finish_thresholds).
+// Every reference that is NOT emitted has d2 > bound_i; the FP64 rerank
+// (knn_exact.cu) certifies  d2_(k+1) < bound_i  per row or sends the row to the
+// exact filter.  The neighbour sets are therefore exact, never approximate.
+//
+// Kernel anatomy (one CTA per 128-query tile, 1 CTA / SM, 12 warps):
+//   warp 0     : bulk-async (TMA engine, UBLKCP) producer: A tile once, then a
+//                ring of reference tiles, mbarrier complete_tx
+//   warp 1     : single-thread tcgen05.mma issuer, M=128 N=256 K=16, FP16 in /
+//                FP32 accumulate in TMEM, two accumulator stages (2 x 256 cols)
+//   warp 2     : TMEM allocator
+//   warps 4-11 : epilogue: tcgen05.ld 32x32b.x32, FMNMX3 min-tree against the
+//                per-row threshold, rare-path append to the candidate list
+#include "common.cuh"
+#include "knn.cuh"
+#include <math.h>
+#include <algorithm>
+#include <string.h>
+
+namespace sbk {
+
+static constexpr int TC_THREADS = 384;
+static constexpr int TC_EPI_WARP0 = 4;
+static constexpr int TC_EPI_WARPS = 8;
+static constexpr int TC_NGROUP = 64;            // group minima per row (2 halves x 32 columns)
+static constexpr int TC_MAX_KPAD = 176;
+static constexpr uint32_t TC_IDESC =            // kind::f16: A,B = F16 (0), D = F32 (1<<4), K-major,
+    (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N>>3 @17, M>>4 @24
+
+enum TcMode { TC_SAMPLE = 0, TC_FILTER = 1, TC_DUMP = 2 };
+
+// device scalars produced by staging (non-negative doubles stored as ordered bits)
+struct TcScalars {
+  unsigned long long zmax2_bits;   // max_j ||z_j||^2
+  unsigned long long dmax2_bits;   // max_j ||delta_j||^2
+  unsigned long long rmax_bits;    // max_j |nrep_j - n_j|
+  unsigned long long zhmax2_bits;  // max_j ||zh_j||^2
+};
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {        // ~4 s
+      printf("sbk: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle ("interleave") shared-memory matrix descriptor:
+//   core matrix = 8 rows x 16 B stored contiguously (128 B)
+//   LBO = byte stride between core matrices adjacent in K
+//   SBO = byte stride between core matrices adjacent in M/N
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;                               // descriptor version (sm_100)
+  return d;                                      // layout_type = 0 (SWIZZLE_NONE), base_offset = 0
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// staging
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+tc_colstat_kernel(const T* __restrict__ X, long long n, int d, long long ld,
+                  double* __restrict__ colsum, unsigned long long* __restrict__ maxabs_bits) {
+  // block handles 1024 rows; thread t accumulates columns t, t+256, ...
+  const long long r0 = (long long)blockIdx.x * 1024;
+  const long long r1 = min(n, r0 + 1024);
+  double mx = 0.0;
+  for (int c = threadIdx.x; c < d; c += 256) {
+    double s = 0.0;
+    for (long long r = r0; r < r1; ++r) { double v = (double)X[r * ld + c]; s += v; mx = fmax(mx, fabs(v)); }
+    atomicAdd(&colsum[c], s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(mx));
+}
+
+__global__ void tc_centre_kernel(const double* __restrict__ colsum, const unsigned long long* __restrict__ maxabs_bits,
+                                 long long n, int d, double* __restrict__ centre, double* __restrict__ scale) {
+  // single block
+  __shared__ double cmax;
+  if (threadIdx.x == 0) cmax = 0.0;
+  __syncthreads();
+  double m = 0.0;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double cv = colsum[c] / (double)n;
+    cv = (double)(float)cv;                       // keep the centre float-representable
+    centre[c] = cv;
+    m = fmax(m, fabs(cv));
+  }
+  atomicMax((unsigned long long*)&cmax, (unsigned long long)__double_as_longlong(m));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double bound = __longlong_as_double((long long)*maxabs_bits) + cmax;   // >= max |x - c|
+    if (!(bound > 0.0)) bound = 1.0;
+    // power of two S with S * bound in [4, 8): FP16 elements stay far from overflow and
+    // ||z||^2 <= 64 d < 65504 for d <= 1023
+    int e;
+    frexp(bound, &e);                             // bound = f * 2^e, f in [0.5,1)
+    scale[0] = ldexp(1.0, 3 - e);                 // S * bound = f * 8 in [4, 8)
+  }
+}
+
+// One thread per staged row.  `src_rows` (optional) gathers a sample.
+//   b_tiles : reference-side operand, tiles of TC_BN rows:  -2*zh | n_hi n_mid n_lo | 0
+//   a_tiles : query-side operand, tiles of TC_BM rows:        zh  |  1    1     1   | 0   (NULL for samples)
+// tile layout (FP16 elements): [kpad/8 chunks][R rows][8]  -> core matrices of 8 rows x 16 B
+template <typename T>
+__global__ void __launch_bounds__(128)
+tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
+                const int32_t* __restrict__ src_rows, long long n_staged,
+                const double* __restrict__ centre, const double* __restrict__ scale, int kpad,
+                __half* __restrict__ b_tiles, __half* __restrict__ a_tiles,
+                double* __restrict__ nrm, float* __restrict__ dq, float* __restrict__ zq,
+                TcScalars* __restrict__ sc) {
+  const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (row >= n_staged) return;
+  const long long bt = row / TC_BN, br = row % TC_BN;
+  __half* bdst = b_tiles + bt * (long long)TC_BN * kpad + br * 8;
+  __half* adst = nullptr;
+  if (a_tiles) { const long long at = row / TC_BM, ar = row % TC_BM; adst = a_tiles + at * (long long)TC_BM * kpad + ar * 8; }
+  const long long src = src_rows ? (long long)src_rows[row] : row;
+  const bool real = src_rows ? true : (row < n);
+  const double S = scale[0];
+  double n2 = 0.0, d2 = 0.0, zh2 = 0.0;
+  const int nchunk = kpad / 8;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    __align__(16) __half hb[8];
+    __align__(16) __half ha[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = ch * 8 + e;
+      float zf = 0.f;
+      if (real && c < d) {
+        const double z = S * ((double)X[src * ld + c] - centre[c]);
+        const __half h = __double2half(z);
+        zf = __half2float(h);
+        const double dl = z - (double)zf;
+        n2 += z * z; d2 += dl * dl; zh2 += (double)zf * (double)zf;
+      }
+      ha[e] = __float2half_rn(zf);
+      hb[e] = __float2half_rn(-2.0f * zf);
+    }
+    // norm columns d, d+1, d+2 (filled after the loop for the chunks that hold them)
+    *reinterpret_cast<uint4*>(bdst + (long long)ch * TC_BN * 8) = *reinterpret_cast<uint4*>(hb);
+    if (adst) *reinterpret_cast<uint4*>(adst + (long long)ch * TC_BM * 8) = *reinterpret_cast<uint4*>(ha);
+  }
+  // FP16 hi/mid/lo split of ||z||^2 (padding rows: a huge value so they never pass a threshold)
+  double nn = real ? n2 : 60000.0;
+  const __half h0 = __double2half(nn);
+  const double r0 = nn - (double)__half2float(h0);
+  const __half h1 = __double2half(r0);
+  const double r1 = r0 - (double)__half2float(h1);
+  const __half h2 = __double2half(r1);
+  const double rep = r1 - (double)__half2float(h2);
+  const __half hn[3] = {h0, h1, h2};
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int c = d + e;
+    bdst[(long long)(c >> 3) * TC_BN * 8 + (c & 7)] = hn[e];
+    if (adst) adst[(long long)(c >> 3) * TC_BM * 8 + (c & 7)] = __float2half_rn(real ? 1.0f : 0.0f);
+  }
+  if (real && !src_rows) {
+    nrm[row] = n2;
+    dq[row] = __double2float_ru(sqrt(d2));
+    zq[row] = __double2float_ru(sqrt(zh2));
+    atomicMax(&sc->zmax2_bits, (unsigned long long)__double_as_longlong(n2));
+    atomicMax(&sc->dmax2_bits, (unsigned long long)__double_as_longlong(d2));
+    atomicMax(&sc->rmax_bits, (unsigned long long)__double_as_longlong(fabs(rep)));
+    atomicMax(&sc->zhmax2_bits, (unsigned long long)__double_as_longlong(zh2));
+  }
+}
+
+__global__ void tc_sample_rows_kernel(int32_t* __restrict__ rows, int m, long long n, long long mult, long long off) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) rows[i] = (int32_t)(((long long)i * mult + off) % n);   // mult coprime to n -> no repeats for m <= n
+}
+
+// Per-row error bound of the tensor-core score (scaled domain), see file header.
+__device__ __forceinline__ double tc_row_error(float dqi, float zqi, const TcScalars* sc, int kpad) {
+  const double zmax = sqrt(__longlong_as_double((long long)sc->zmax2_bits));
+  const double dmax = sqrt(__longlong_as_double((long long)sc->dmax2_bits));
+  const double zhmax = sqrt(__longlong_as_double((long long)sc->zhmax2_bits));
+  const double rmax = __longlong_as_double((long long)sc->rmax_bits);
+  const double nmax = zmax * zmax;
+  const double rounding = 2.0 * ((double)dqi * zmax + (double)zqi * dmax);
+  // FP32 accumulation inside the tensor core: assume no better than truncation at
+  // every one of the kpad additions (2^-23 relative each) of the absolute sum
+  const double acc = (double)kpad * 1.1920928955078125e-07 * (nmax + 2.0 * (double)zqi * zhmax);
+  return (rmax + rounding + acc) * 1.0001 + 1e-30;
+}
+
+// ---------------------------------------------------------------------------
+// the tcgen05 kernel
+// ---------------------------------------------------------------------------
+struct TcArgs {
+  const __half* a_tiles;      // query operand tiles (TC_BM rows each), all n rows
+  const __half* b_tiles;      // reference operand tiles (TC_BN rows each): full set or sample
+  long long n_btiles;
+  long long tile_m0;          // first query tile of this launch (global tile index)
+  long long row_lo, row_hi;   // valid global query rows [row_lo,row_hi); slot = row - row_lo
+  int kpad, nstage;
+  // SAMPLE
+  int order_stat;             // r (1-based)
+  const float* dq; const float* zq; const double* nrm; const TcScalars* sc; const double* scale;
+  float* thr;                 // [slots]
+  double* bound;              // [slots]
+  // FILTER
+  uint32_t* cand_idx; int32_t* cand_count; int cand_cap;
+  // DUMP
+  float* dump; long long dump_ld;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_kernel(const TcArgs p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int kpad = p.kpad;
+  const uint32_t a_bytes = (uint32_t)TC_BM * kpad * 2;
+  const uint32_t b_bytes = (uint32_t)TC_BN * kpad * 2;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + a_bytes;
+  unsigned char* tail = sB + (size_t)p.nstage * b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [nstage]
+  uint64_t* empty_bar = full_bar + 4;                              // [nstage]
+  uint64_t* tfull_bar = empty_bar + 4;                             // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
+  uint64_t* a_bar = tempty_bar + 2;                                // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
+  int* row_cnt = reinterpret_cast<int*>(tmem_slot + 2);            // [TC_BM]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long tile_m = p.tile_m0 + blockIdx.x;
+  const long long n_tiles = p.n_btiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], TC_EPI_WARPS); }
+    mbar_init(a_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < TC_BM) row_cnt[threadIdx.x] = 0;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      mbar_expect_tx(a_bar, a_bytes);
+      bulk_g2s(sA, p.a_tiles + tile_m * (long long)TC_BM * kpad, a_bytes, a_bar);
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = 0; t < n_tiles; ++t) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], b_bytes);
+        bulk_g2s(sB + (size_t)stage * b_bytes, p.b_tiles + t * (long long)TC_BN * kpad, b_bytes, &full_bar[stage]);
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      mbar_wait(a_bar, 0);
+      const uint32_t a_addr = smem_u32(sA);
+      const int ksteps = kpad / 16;
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = 0; t < n_tiles; ++t) {
+        const int as = (int)(t & 1);
+        mbar_wait(&tempty_bar[as], (uint32_t)(((t >> 1) & 1) ^ 1));
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_bytes);
+        const uint32_t d_addr = tmem_base + (uint32_t)as * TC_BN;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          // one k-step = 16 FP16 = two 16-byte chunks; chunk stride = rows * 16 B
+          const uint64_t ad = tc_smem_desc(a_addr + (uint32_t)ks * 2 * TC_BM * 16, TC_BM * 16, 128);
+          const uint64_t bd = tc_smem_desc(b_addr + (uint32_t)ks * 2 * TC_BN * 16, TC_BN * 16, 128);
+          tc_mma_f16(d_addr, ad, bd, TC_IDESC, ks > 0 ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[stage]);            // smem stage reusable once these MMAs retire
+        tc_commit(&tfull_bar[as]);               // accumulator ready for the epilogue
+        if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= TC_EPI_WARP0) {
+    // ===== epilogue =====
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    const int half = (warp - TC_EPI_WARP0) >> 2; // column half of the 256-wide tile
+    const int r_in_tile = q * 32 + lane;
+    const long long grow = tile_m * TC_BM + r_in_tile;
+    const bool row_ok = grow >= p.row_lo && grow < p.row_hi;
+    const long long slot = grow - p.row_lo;
+    float thr = -INFINITY;
+    float gmin[32];
+    if (MODE == TC_SAMPLE) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) gmin[c] = INFINITY;
+    }
+    if (MODE == TC_FILTER && row_ok) thr = p.thr[slot];
+    uint32_t* my_cand = (MODE == TC_FILTER && row_ok) ? p.cand_idx + slot * (long long)p.cand_cap : nullptr;
+
+    for (long long t = 0; t < n_tiles; ++t) {
+      const int as = (int)(t & 1);
+      mbar_wait(&tfull_bar[as], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN + half * 128);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        tmem_ld_wait();
+        if (MODE == TC_SAMPLE) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(v[c]));
+        } else if (MODE == TC_FILTER) {
+          float mn = __uint_as_float(v[0]);
+#pragma unroll
+          for (int c = 1; c < 32; ++c) mn = fminf(mn, __uint_as_float(v[c]));
+          if (mn <= thr) {
+            const uint32_t j0 = (uint32_t)(t * TC_BN + half * 128 + ch * 32);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              if (__uint_as_float(v[c]) <= thr) {
+                const int pos = atomicAdd(&row_cnt[r_in_tile], 1);
+                if (pos < p.cand_cap) my_cand[pos] = j0 + c;
+              }
+            }
+          }
+        } else {   // TC_DUMP
+          if (row_ok) {
+            const long long j0 = t * TC_BN + half * 128 + ch * 32;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) p.dump[slot * p.dump_ld + j0 + c] = __uint_as_float(v[c]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+
+    // ---- per-row results ----
+    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+    if (MODE == TC_FILTER) {
+      if (half == 0 && row_ok) p.cand_count[slot] = row_cnt[r_in_tile];
+    }
+    if (MODE == TC_SAMPLE) {
+      // all MMAs have retired (last tfull observed) -> the B ring is free: use it as scratch
+      float* gm = reinterpret_cast<float*>(sB);                    // [TC_NGROUP][TC_BM]
+#pragma unroll
+      for (int c = 0; c < 32; ++c) gm[(half * 32 + c) * TC_BM + r_in_tile] = gmin[c];
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+      if (half == 0 && row_ok) {
+        // r-th smallest of the TC_NGROUP group minima (selection by repeated min)
+        float last = -INFINITY; int taken = 0; float tau = INFINITY;
+        while (taken < p.order_stat) {
+          float m = INFINITY; int cnt_eq = 0;
+          for (int g = 0; g < TC_NGROUP; ++g) {
+            const float x = gm[g * TC_BM + r_in_tile];
+            if (x > last) { if (x < m) { m = x; cnt_eq = 1; } else if (x == m) ++cnt_eq; }
+          }
+          if (cnt_eq == 0) break;                                   // fewer distinct values than r
+          taken += cnt_eq; last = m; tau = m;
+        }
+        const double E = tc_row_error(p.dq[grow], p.zq[grow], p.sc, kpad);
+        const float thr_f = __double2float_ru((double)tau + 2.0 * E);
+        const double S = p.scale[0];
+        p.thr[slot] = thr_f;
+        // every non-emitted j has s > thr  =>  S^2 d2 - n_i > thr - E
+        p.bound[slot] = ((double)thr_f - E + p.nrm[grow]) / (S * S);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static double binom_tail_ge(int n, double p, int r) {   // P(Binomial(n,p) >= r)
+  if (r <= 0) return 1.0;
+  if (p <= 0) return 0.0;
+  double q = 1.0 - p, term = pow(q, n), cdf = 0.0;      // k = 0
+  for (int k = 0; k < r; ++k) {
+    cdf += term;
+    term *= (double)(n - k) / (double)(k + 1) * p / q;
+  }
+  return std::max(0.0, 1.0 - cdf);
+}
+
+TcPlan tc_make_plan(long long n_ref, int d, int k) {
+  TcPlan p;
+  p.kpad = (d + 3 + 15) / 16 * 16;
+  p.ksteps = p.kpad / 16;
+  p.n_tiles = (n_ref + TC_BN - 1) / TC_BN;
+  p.n_groups = TC_NGROUP;
+  p.stage_bytes = (size_t)TC_BN * p.kpad * 2;
+  const int k1 = k + 1;
+  // choose (sample size M, order statistic r): P(threshold admits < k+1 refs) <= 1e-4,
+  // minimise   expected candidates + (cost of the sample pass expressed in candidates)
+  double best_cost = 1e300; int best_m = 0, best_r = 0; double best_cnt = 0, best_sd = 0;
+  for (long long m = 2048; m <= 65536; m <<= 1) {
+    if (m > n_ref && m > 2048) break;
+    const long long mm = std::min<long long>(m, (n_ref / TC_BN) * TC_BN > 0 ? (n_ref / TC_BN) * TC_BN : TC_BN);
+    const double per_group = (double)mm / TC_NGROUP;
+    const double pg = 1.0 - exp(-(double)k1 * per_group / (double)n_ref);
+    int r = 1;
+    while (r <= TC_NGROUP / 2 && binom_tail_ge(TC_NGROUP, pg, r) > 1e-4) ++r;
+    if (r > TC_NGROUP / 2) continue;
+    double h = 0, h2 = 0;
+    for (int i = 0; i < r; ++i) { h += 1.0 / (TC_NGROUP - i); h2 += 1.0 / ((double)(TC_NGROUP - i) * (TC_NGROUP - i)); }
+    const double scale = (double)n_ref / per_group;
+    const double cnt = scale * h, sd = scale * sqrt(h2);
+    const double cost = cnt + 0.004 * (double)mm;     // one sampled reference costs ~0.004 reranked candidates per row
+    if (cost < best_cost) { best_cost = cost; best_m = (int)mm; best_r = r; best_cnt = cnt; best_sd = sd; }
+  }
+  if (best_m == 0) {            // tiny n: everything is a candidate
+    best_m = (int)std::min<long long>(2048, p.n_tiles * TC_BN); best_r = TC_NGROUP / 2;
+    best_cnt = (double)n_ref; best_sd = 0;
+  }
+  p.sample_size = (best_m + TC_BN - 1) / TC_BN * TC_BN;
+  p.order_stat = best_r;
+  double cap = (best_cnt + 6.0 * best_sd) * 1.5 + 64;
+  cap = std::max(cap, (double)(2 * k1));
+  cap = std::min(cap, (double)n_ref);
+  cap = std::min(cap, 8192.0);
+  p.cand_cap = (int)((cap + 63) / 64) * 64;
+  return p;
+}
+
+long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
+  // keep the candidate lists of one chunk under ~12 GB
+  long long rows = (long long)(12e9 / ((double)p.cand_cap * 4.0));
+  rows = std::max<long long>(rows / TC_BM * TC_BM, TC_BM * 148);
+  return std::min<long long>(rows, 1 << 20);
+}
+
+static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk, TcState* st) {
+  const long long n_a = (n_ref + TC_BM - 1) / TC_BM * TC_BM;
+  const long long n_b = p.n_tiles * TC_BN;
+  (void)n_a;   // A tiles are staged by the same kernel that walks the n_b padded rows
+  st->a_tiles = a.take<__half>((size_t)n_b * p.kpad);
+  st->b_tiles = a.take<__half>((size_t)n_b * p.kpad);
+  st->s_tiles = a.take<__half>((size_t)p.sample_size * p.kpad);
+  st->centre = a.take<double>(4096);
+  st->colsum = a.take<double>(4096);
+  st->scale = a.take<double>(8);
+  st->nrm = a.take<double>((size_t)n_b);
+  st->dq = a.take<float>((size_t)n_b);
+  st->zq = a.take<float>((size_t)n_b);
+  st->sc = a.take<TcScalars>(2);
+  st->sample_rows = a.take<int32_t>((size_t)p.sample_size);
+  st->thr = a.take<float>((size_t)chunk + TC_BM);
+  st->maxabs = a.take<unsigned long long>(8);
+}
+
+size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query) {
+  Arena a(nullptr, 0);
+  TcState st;
+  tc_carve(a, p, n_ref, n_query, &st);
+  return a.off + 1024;
+}
+
+static size_t tc_smem_bytes(int kpad, int nstage) {
+  return (size_t)TC_BM * kpad * 2 + (size_t)nstage * TC_BN * kpad * 2 + 13 * 8 + 16 + TC_BM * 4 + 64;
+}
+
+static int tc_pick_stages(int kpad) {
+  for (int s = 3; s >= 2; --s)
+    if (tc_smem_bytes(kpad, s) <= 227 * 1024) return s;
+  return 0;
+}
+
+static long long coprime_multiplier(long long n) {
+  long long m = (long long)(0.6180339887498949 * (double)n);
+  if (m < 1) m = 1;
+  auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
+  while (gcd(m, n) != 1) ++m;
+  return m;
+}
+
+int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, const TcPlan& p,
+               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream) {
+  if (p.kpad > TC_MAX_KPAD || tc_pick_stages(p.kpad) == 0) {
+    set_error("tensor kNN path supports feature width <= %d (got %d); use SBK_KNN_EXACT", TC_MAX_KPAD - 3, d);
+    return SBK_ERR_INVALID;
+  }
+  Arena a(ws, ws_bytes);
+  tc_carve(a, p, n_ref, chunk, st);
+  if (!a.ok()) { set_error("tensor kNN: staging workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
+  st->nstage = tc_pick_stages(p.kpad);
+  st->n_ref = n_ref; st->d = d;
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->colsum, 0, 4096 * sizeof(double), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->maxabs, 0, 8 * sizeof(unsigned long long), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->sc, 0, 2 * sizeof(TcScalars), stream));
+  const unsigned cb = (unsigned)((n_ref + 1023) / 1024);
+  const long long n_b = p.n_tiles * TC_BN;
+  const long long n_a = (n_ref + TC_BM - 1) / TC_BM * TC_BM;
+  // zero the A padding rows beyond n_b (n_a <= n_b always since TC_BN is a multiple of TC_BM)
+  (void)n_a;
+  if (dtype == SBK_F32) tc_colstat_kernel<float><<<cb, 256, 0, stream>>>((const float*)X, n_ref, d, ld, st->colsum, st->maxabs);
+  else tc_colstat_kernel<double><<<cb, 256, 0, stream>>>((const double*)X, n_ref, d, ld, st->colsum, st->maxabs);
+  SBK_LAUNCH_CHECK();
+  tc_centre_kernel<<<1, 256, 0, stream>>>(st->colsum, st->maxabs, n_ref, d, st->centre, st->scale);
+  SBK_LAUNCH_CHECK();
+  const unsigned sb = (unsigned)((n_b + 127) / 128);
+  if (dtype == SBK_F32)
+    tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad,
+                                                   st->b_tiles, st->a_tiles, st->nrm, st->dq, st->zq, st->sc);
+  else
+    tc_stage_kernel<double><<<sb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad,
+                                                    st->b_tiles, st->a_tiles, st->nrm, st->dq, st->zq, st->sc);
+  SBK_LAUNCH_CHECK();
+  // pseudo-random (golden-ratio stride) sample without repeats
+  const long long mult = coprime_multiplier(n_ref);
+  tc_sample_rows_kernel<<<(p.sample_size + 255) / 256, 256, 0, stream>>>(st->sample_rows, p.sample_size, n_ref, mult, n_ref / 3);
+  SBK_LAUNCH_CHECK();
+  const unsigned ssb = (unsigned)((p.sample_size + 127) / 128);
+  if (dtype == SBK_F32)
+    tc_stage_kernel<float><<<ssb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
+                                                    p.kpad, st->s_tiles, nullptr, nullptr, nullptr, nullptr, st->sc);
+  else
+    tc_stage_kernel<double><<<ssb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
+                                                     p.kpad, st->s_tiles, nullptr, nullptr, nullptr, nullptr, st->sc);
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}
+
+template <int MODE>
+static int tc_launch(const TcArgs& args, long long n_mtiles, cudaStream_t stream) {
+  const size_t smem = tc_smem_bytes(args.kpad, args.nstage);
+  SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_kernel<MODE><<<(unsigned)n_mtiles, TC_THREADS, smem, stream>>>(args);
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}
+
+static void tc_chunk_args(TcState* st, const TcPlan& p, long long row0, long long n_rows, TcArgs& a,
+                          long long& n_mtiles) {
+  memset(&a, 0, sizeof(a));
+  a.a_tiles = st->a_tiles;
+  a.kpad = p.kpad; a.nstage = st->nstage;
+  a.tile_m0 = row0 / TC_BM;
+  n_mtiles = (row0 + n_rows + TC_BM - 1) / TC_BM - a.tile_m0;
+  a.row_lo = row0; a.row_hi = row0 + n_rows;
+  a.order_stat = p.order_stat;
+  a.dq = st->dq; a.zq = st->zq; a.nrm = st->nrm; a.sc = st->sc; a.scale = st->scale;
+  a.thr = st->thr; a.cand_cap = p.cand_cap;
+}
+
+int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
+                    cudaStream_t stream) {
+  TcArgs a; long long n_mtiles;
+  tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
+  a.bound = bound;
+  a.b_tiles = st->s_tiles; a.n_btiles = p.sample_size / TC_BN;
+  return tc_launch<TC_SAMPLE>(a, n_mtiles, stream);
+}
+
+int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
+                    uint32_t* cand_idx, int32_t* cand_count, cudaStream_t stream) {
+  TcArgs a; long long n_mtiles;
+  tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
+  a.cand_idx = cand_idx; a.cand_count = cand_count;
+  a.b_tiles = st->b_tiles; a.n_btiles = p.n_tiles;
+  return tc_launch<TC_FILTER>(a, n_mtiles, stream);
+}
+
+int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream) {
+  TcArgs a; memset(&a, 0, sizeof(a));
+  a.a_tiles = st->a_tiles; a.b_tiles = st->b_tiles; a.n_btiles = p.n_tiles;
+  a.kpad = p.kpad; a.nstage = st->nstage;
+  a.tile_m0 = 0; a.row_lo = 0; a.row_hi = n_q;
+  a.dump = out; a.dump_ld = out_ld;
+  return tc_launch<TC_DUMP>(a, (n_q + TC_BM - 1) / TC_BM, stream);
+}
+
+__global__ void tc_row_error_kernel(const float* dq, const float* zq, const TcScalars* sc, const double* nrm,
+                                    const double* scale, int kpad, long long n, double* E, double* nrm_out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  E[i] = tc_row_error(dq[i], zq[i], sc, kpad);
+  nrm_out[i] = nrm[i];
+  if (i == 0) nrm_out[n] = scale[0];            // scale S appended after the norms
+}
+
+int tc_row_errors(TcState* st, const TcPlan& p, long long n, double* E, double* nrm_out, cudaStream_t stream) {
+  tc_row_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st->dq, st->zq, st->sc, st->nrm, st->scale, p.kpad, n, E, nrm_out);
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}
+
+}  // namespace sbk

@@ -1,0 +1,123 @@
+"""Row-block sharding of the kNN graph build across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU
+tests).  The reference matrix is replicated; rank r computes query rows
+[r*N/G, (r+1)*N/G) and the fixed-size (idx int32, dist) blocks are all-gathered.
+Rank-local row-major order + ascending rank order = global row-major order, so
+nothing is re-sorted.  The only other exchange on the
+path is the 20-bin all-reduce of the max_node threshold counts
+(SemiBin/cluster.py:122).
+"""
+import numpy as np
+
+
+def row_block(n, rank, world):
+    """Contiguous, balanced split: the first n % world ranks get one extra row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def world_info(group=None):
+    dist = _dist()
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def all_gather_rows(local, n_total, group=None):
+    """Gather row blocks of possibly different heights (differ by at most one
+    row) into the full [n_total, ...] tensor on every rank."""
+    import torch
+    dist = _dist()
+    rank, world = world_info(group)
+    if world == 1:
+        return local
+    sizes = [row_block(n_total, r, world) for r in range(world)]
+    max_rows = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    parts = [out[r * max_rows: r * max_rows + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
+    return torch.cat(parts, dim=0)
+
+
+def knn_sharded(X, n_neighbors, *, group=None, algo='auto', gather=True, local_knn=None):
+    """Every rank holds the full X; returns the full (dist, idx) on every rank
+    (gather=True) or only this rank's row block (gather=False).
+    `local_knn(X, k, q_begin, q_end)` defaults to the libsbk kernel path."""
+    rank, world = world_info(group)
+    n = X.shape[0]
+    lo, hi = row_block(n, rank, world)
+    if local_knn is None:
+        from .neighbors import knn
+        d, i = knn(X, n_neighbors, q_begin=lo, q_end=hi, algo=algo)
+    else:
+        d, i = local_knn(X, n_neighbors, lo, hi)
+    if not gather or world == 1:
+        return d, i
+    return all_gather_rows(d, n, group), all_gather_rows(i, n, group)
+
+
+def allreduce_counts(counts, group=None):
+    """Sum of the per-threshold row counts over ranks (cluster.py:122)."""
+    dist = _dist()
+    rank, world = world_info(group)
+    if world > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def gather_edges(X, Y, V, group=None):
+    """Concatenate per-rank edge blocks in rank order (= global row-major order)."""
+    import torch
+    dist = _dist()
+    rank, world = world_info(group)
+    if world == 1:
+        return X, Y, V
+    n_local = torch.tensor([X.shape[0]], dtype=torch.int64, device=X.device)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    counts = [int(c.item()) for c in counts]
+    m = max(counts) if counts else 0
+    outs = []
+    for t in (X, Y, V):
+        pad = torch.zeros((m,), dtype=t.dtype, device=t.device)
+        pad[:t.shape[0]] = t
+        buf = torch.empty((world * m,), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, pad, group=group)
+        outs.append(torch.cat([buf[r * m: r * m + counts[r]] for r in range(world)]))
+    return tuple(outs)
+
+
+def build_edge_list_sharded(embedding, features, depth, *, max_edges, max_node, is_combined, n_sample,
+                            group=None, algo='auto'):
+    """Multi-GPU version of cluster.build_edge_list: kNN graphs, intersection
+    and edge weights on this rank's row block; one all-reduce (threshold
+    counts) and one gather (edge blocks).  Returns host arrays on every rank."""
+    import torch
+    from . import cluster
+    from .neighbors import knn, _as_device_matrix
+    rank, world = world_info(group)
+    emb = _as_device_matrix(embedding).float()
+    feat = _as_device_matrix(features)
+    n = emb.shape[0]
+    k = min(int(max_edges), n - 1)
+    lo, hi = row_block(n, rank, world)
+    a_d, a_i = knn(emb, k, q_begin=lo, q_end=hi, algo=algo)
+    b_d, b_i = knn(feat, k, q_begin=lo, q_end=hi, algo=algo)
+    w, rowmax, counts = cluster.edges_stage1(a_d, a_i, b_d, b_i, cluster.threshold_sequence())
+    counts = allreduce_counts(counts.contiguous(), group)
+    threshold = cluster.pick_threshold(counts.cpu().numpy(), n, max_node)
+    dep = None
+    if not is_combined:
+        dep = torch.as_tensor(np.ascontiguousarray(depth, dtype=np.float32)).cuda()
+    X, Y, V = cluster.edges_stage2(w, a_i, lo, threshold, dep, n_sample, is_combined)
+    X, Y, V = gather_edges(X, Y, V, group)
+    return X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()

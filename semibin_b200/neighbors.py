@@ -1,0 +1,114 @@
+"""kNN graph drop-in for sklearn.neighbors.kneighbors_graph on the path
+SemiBin/cluster.py:94-105 and SemiBin/long_read_cluster.py:108-113.
+
+`kneighbors_graph(X, n_neighbors, mode='distance', p=2, n_jobs=None)` returns
+the same object the reference gets from scikit-learn: a scipy csr_matrix with
+exactly k entries per row ordered by ascending distance, float64 data (values
+float32-rounded for float32 input), int64 indices (sklearn/neighbors/_base.py:
+1031-1041).  `knn()` is the array-level call (device tensors in / out) used by
+the fused entry points and by the row-block sharding in dist.py.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+
+def _as_device_matrix(X):
+    """Accept numpy (host) or torch (host/device) 2-D float32/float64; return a
+    contiguous CUDA tensor.  Host inputs go through pinned memory."""
+    import torch
+    if isinstance(X, np.ndarray):
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        X = np.ascontiguousarray(X)
+        t = torch.from_numpy(X)
+        return t.pin_memory().cuda(non_blocking=True) if t.numel() else t.cuda()
+    if not isinstance(X, torch.Tensor):
+        raise TypeError('X must be a numpy array or a torch tensor')
+    if X.dtype not in (torch.float32, torch.float64):
+        X = X.double()
+    return X.contiguous().cuda()
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """Reusable workspace tensor (grown on demand) so repeated calls do not
+    re-allocate; owned by this module, passed to the C-ABI as a plain buffer."""
+    import torch
+    t = _ws_cache.get(device)
+    if t is None or t.numel() < nbytes:
+        _ws_cache.pop(device, None)
+        t = None
+        torch.cuda.empty_cache()
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[device] = t
+    return t
+
+
+def release_workspace():
+    _ws_cache.clear()
+
+
+def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=False):
+    """Exact Euclidean kNN of rows [q_begin, q_end) of X among all rows of X
+    (self excluded by index).  X: CUDA tensor [N, D] float32/float64.
+    Returns (dist, idx): dist float32 (float64 for float64 input) [n, k],
+    idx int32 [n, k], both CUDA tensors, rows ordered by (distance, index)."""
+    import torch
+    _lib.require_cuda()
+    lib = _lib.load()
+    if X.dim() != 2:
+        raise ValueError('X must be 2-D')
+    N, D = X.shape
+    if q_end is None:
+        q_end = N
+    k = int(n_neighbors)
+    if not (0 < k < N):
+        # same condition/message family as sklearn/neighbors/_base.py:840-851
+        raise ValueError(f'Expected n_neighbors < n_samples_fit, but n_neighbors = {k}, n_samples_fit = {N}, '
+                         f'n_samples = {q_end - q_begin}')
+    dtype = _lib.SBK_F32 if X.dtype == torch.float32 else _lib.SBK_F64
+    n_q = q_end - q_begin
+    a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
+    ws_bytes = lib.sbk_knn_workspace_bytes(dtype, N, D, n_q, k, a)
+    if ws_bytes == 0:
+        raise ValueError(_lib.last_error())
+    ws = _workspace(ws_bytes, X.device)
+    out_d = torch.empty((n_q, k), dtype=X.dtype, device=X.device)
+    out_i = torch.empty((n_q, k), dtype=torch.int32, device=X.device)
+    stats = _lib.KnnStats()
+    rc = lib.sbk_knn(_lib.ptr(X), dtype, N, D, X.stride(0), q_begin, q_end, k,
+                     _lib.ptr(out_d), _lib.ptr(out_i), _lib.ptr(ws), ws.numel(), a,
+                     C.byref(stats), _lib.stream_ptr())
+    _lib.check(rc)
+    if return_stats:
+        return out_d, out_i, stats.as_dict()
+    return out_d, out_i
+
+
+def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2, metric_params=None,
+                     include_self=False, n_jobs=None, algo='auto'):
+    """Same signature as sklearn.neighbors.kneighbors_graph for the arguments
+    the reference uses (cluster.py:94-105): mode='distance', p=2, n_jobs
+    ignored (it is ignored by sklearn's brute path as well).  Returns csr_matrix."""
+    from scipy.sparse import csr_matrix
+    if mode not in ('distance', 'connectivity'):
+        raise ValueError("Unsupported mode, must be one of 'connectivity', or 'distance' but got '%s' instead" % mode)
+    if metric not in ('minkowski', 'euclidean', 'l2') or (metric == 'minkowski' and p != 2) or metric_params:
+        raise ValueError('semibin_b200.kneighbors_graph implements the Euclidean (p=2) metric only')
+    if include_self not in (False, 'auto'):
+        raise ValueError('include_self=True is not on the SemiBin path')
+    Xd = _as_device_matrix(X)
+    N = Xd.shape[0]
+    dist, idx = knn(Xd, n_neighbors, algo=algo)
+    k = int(n_neighbors)
+    indices = idx.cpu().numpy().astype(np.int64).ravel()
+    if mode == 'distance':
+        data = dist.cpu().numpy().astype(np.float64).ravel()
+    else:
+        data = np.ones(N * k, dtype=np.float64)
+    indptr = np.arange(0, N * k + 1, k, dtype=np.int64)
+    return csr_matrix((data, indices, indptr), shape=(N, N))

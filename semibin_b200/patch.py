@@ -1,0 +1,33 @@
+"""Bind an installed SemiBin to the GPU path (the seam SURVEY.md section 8(b)
+describes: "replace these call sites / monkey-patch these names").
+
+    import semibin_b200.patch; semibin_b200.patch.install()
+
+After install(), `SemiBin.cluster.run_embed_infomap` is the fused GPU version
+and `SemiBin.long_read_cluster`'s `kneighbors_graph` / `dbscan` names resolve to
+the libsbk-backed drop-ins; `uninstall()` restores the originals.
+"""
+_saved = {}
+
+
+def install():
+    import SemiBin.cluster as rc
+    import SemiBin.long_read_cluster as rl
+    from . import cluster, long_read, neighbors
+    if _saved:
+        return
+    _saved.update(run_embed_infomap=rc.run_embed_infomap, kneighbors_graph=rl.kneighbors_graph, dbscan=rl.dbscan)
+    rc.run_embed_infomap = cluster.run_embed_infomap
+    rl.kneighbors_graph = neighbors.kneighbors_graph
+    rl.dbscan = long_read._SweepCache()
+
+
+def uninstall():
+    if not _saved:
+        return
+    import SemiBin.cluster as rc
+    import SemiBin.long_read_cluster as rl
+    rc.run_embed_infomap = _saved['run_embed_infomap']
+    rl.kneighbors_graph = _saved['kneighbors_graph']
+    rl.dbscan = _saved['dbscan']
+    _saved.clear()

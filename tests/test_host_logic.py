@@ -1,0 +1,71 @@
+"""CPU tier: host-side logic of the drop-ins (threshold search, row-block
+sharding, gather) incl. a world_size=2 gloo run with the oracle standing in for
+the per-rank kernel call."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from semibin_b200 import cluster as sc, dist as sd, synth
+from oracle import edges as oe, knn as ok
+
+
+def test_threshold_sequence_matches_reference_loop():
+    assert sc.threshold_sequence() == oe.threshold_sequence()
+
+
+@pytest.mark.parametrize('max_node', [1, 0.95, 0.6, 0.3, 0.0])
+def test_pick_threshold(max_node):
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        rowmax = rng.random(997) ** rng.uniform(0.3, 3)
+        counts = [int(np.sum(rowmax > t)) for t in sc.threshold_sequence()]
+        assert sc.pick_threshold(counts, 997, max_node) == oe.max_node_threshold(rowmax, 997, max_node)
+
+
+def test_row_block_partition():
+    for n in (1, 7, 128, 1000003):
+        for w in (1, 2, 3, 8):
+            blocks = [sd.row_block(n, r, w) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    X = synth.embeddings(1001, seed=11)
+
+    def local_knn(Xt, k, lo, hi):
+        d, i = ok.knn_restated(Xt.numpy(), k, q_begin=lo, q_end=hi)
+        return torch.from_numpy(d.astype(np.float32)), torch.from_numpy(i.astype(np.int32))
+
+    d, i = sd.knn_sharded(torch.from_numpy(X), 17, local_knn=local_knn)
+    c = torch.tensor([rank + 1, 10 * (rank + 1)], dtype=torch.int64)
+    sd.allreduce_counts(c)
+    lo, hi = sd.row_block(1001, rank, world)
+    ex = torch.arange(lo, lo + 3 + rank, dtype=torch.int32)
+    gx, gy, gv = sd.gather_edges(ex, ex + 1, ex.double() * 0.5)
+    np.savez(os.path.join(tmp, f'r{rank}.npz'), d=d.numpy(), i=i.numpy(), c=c.numpy(), gx=gx.numpy(), gv=gv.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_knn_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    X = synth.embeddings(1001, seed=11)
+    d, i = ok.knn_restated(X, 17)
+    for r in range(2):
+        z = np.load(tmp_path / f'r{r}.npz')
+        np.testing.assert_array_equal(z['i'], i.astype(np.int32))          # 1-rank result == gathered result
+        np.testing.assert_array_equal(z['d'], d.astype(np.float32))
+        np.testing.assert_array_equal(z['c'], [3, 30])
+        np.testing.assert_array_equal(z['gx'], [0, 1, 2, 501, 502, 503, 504])
+        np.testing.assert_array_equal(z['gv'], np.array([0, 1, 2, 501, 502, 503, 504]) * 0.5)
