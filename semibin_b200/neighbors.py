@@ -111,4 +111,7 @@ def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2
     else:
         data = np.ones(N * k, dtype=np.float64)
     indptr = np.arange(0, N * k + 1, k, dtype=np.int64)
-    return csr_matrix((data, indices, indptr), shape=(N, N))
+    g = csr_matrix((data, indices, indptr), shape=(N, N))
+    if g.indices.dtype != np.int64:          # scipy narrows small index arrays; sklearn hands back int64
+        g.indices, g.indptr = indices, indptr
+    return g
