@@ -260,7 +260,7 @@ def run_ours(args):
             'roofline': roofline,
             'stages_ms': stage_ms,
             'knn_stats': {kk: stats[-1][kk] for kk in ('algo_used', 'n_chunks', 'n_fallback_rows', 'n_candidates',
-                                                       'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
+                                                       'n_reranked', 'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
         }
         if world == 1 and not args.no_cpu_baseline:
             Xn = X_host.numpy()

@@ -63,7 +63,7 @@ typedef struct sbk_knn_stats {
   int32_t algo_used;             /* sbk_knn_algo actually run */
   int32_t n_chunks;              /* query chunks processed */
   int64_t n_fallback_rows;       /* rows whose certificate failed -> exact filter */
-  int64_t n_candidates;          /* total candidates reranked in FP64 */
+  int64_t n_candidates;          /* total candidates emitted by the filter */
   int32_t sample_size;           /* reference sample used for thresholds (tensor path) */
   int32_t cand_capacity;         /* per-row candidate slots (tensor path) */
   int32_t order_stat;            /* which group-min order statistic set the threshold */
@@ -77,6 +77,7 @@ typedef struct sbk_knn_stats {
   float ms_rerank;               /* FP64 rerank + certificate */
   float ms_fallback;             /* exact filter + rerank of uncertified rows */
   float ms_exact_filter;         /* exact path: FP64 filter */
+  int64_t n_reranked;            /* candidates that survived the score cut and got an FP64 distance */
 } sbk_knn_stats;
 
 int sbk_version(void);

@@ -22,7 +22,8 @@ class KnnStats(C.Structure):
                 ('order_stat', C.c_int32), ('kpad', C.c_int32),
                 ('n_launches', C.c_int32), ('reserved', C.c_int32),
                 ('ms_prepare', C.c_float), ('ms_sample', C.c_float), ('ms_filter', C.c_float),
-                ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float)]
+                ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float),
+                ('n_reranked', C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -25,7 +25,7 @@ static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk 
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
 
 struct KnnWs {
-  uint32_t* cand_idx; int32_t* cand_count; double* bound;
+  uint32_t* cand_idx; float* cand_val; int32_t* cand_count; double* bound; float* errb;
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
   void* tc;                                             // tensor-path staging area
@@ -60,8 +60,9 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     s.chunk = std::min<long long>(std::max<long long>(n_q, 1), tc_chunk_rows(s.plan, n_ref));
     s.cand_stride = s.plan.cand_cap;
     s.fb_rows = std::min<long long>(s.chunk, 8192);   // fallback rows handled per round
-    s.fb_split = 8;
+    s.fb_split = 32;                                  // few rows x all references: parallelise over references
     if (n_ref / 2048 < s.fb_split) s.fb_split = (int)std::max<long long>(1, n_ref / 2048);
+    while (s.fb_split > 1 && (size_t)s.fb_split * k1 * 12 > 150 * 1024) s.fb_split /= 2;
   }
   return s;
 }
@@ -69,11 +70,13 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
 static void carve(Arena& a, const KnnShape& s, long long n_ref, int k, KnnWs& w) {
   const int k1 = k + 1;
   w.cand_idx = a.take<uint32_t>((size_t)s.chunk * s.cand_stride);
-  w.cand_count = a.take<int32_t>((size_t)s.chunk);
+  w.cand_val = s.algo == SBK_KNN_TENSOR ? a.take<float>((size_t)s.chunk * s.cand_stride) : nullptr;
+  w.cand_count = a.take<int32_t>((size_t)s.chunk * 4);
   w.bound = a.take<double>((size_t)s.chunk);
+  w.errb = a.take<float>((size_t)s.chunk);
   w.fail_rows = a.take<int32_t>((size_t)s.chunk + (size_t)s.fb_rows + 1);
   w.n_fail = a.take<int>(64);
-  w.cand_total = a.take<unsigned long long>(8);
+  w.cand_total = a.take<unsigned long long>(8);   // [0] candidates emitted, [1] candidates reranked in FP64
   w.fb_idx = a.take<uint32_t>((size_t)s.fb_rows * s.fb_split * k1);
   w.fb_count = a.take<int32_t>((size_t)s.fb_rows + 1);
   w.tc = nullptr; w.tc_bytes = 0;
@@ -166,7 +169,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
   sbk_knn_stats st; memset(&st, 0, sizeof(st));
   st.algo_used = s.algo;
   const size_t esz = dtype == SBK_F32 ? 4 : 8;
-  SBK_CUDA_CHECK(cudaMemsetAsync(w.cand_total, 0, sizeof(unsigned long long), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(w.cand_total, 0, 8 * sizeof(unsigned long long), stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail, 0, 64 * sizeof(int), stream));
 
   StageTimer tm(stream, stats != nullptr);
@@ -194,23 +197,23 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
-      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, s.cand_stride, w.cand_count,
-                         nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
+                         nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 2;
       if (rc) return rc;
     } else {
       int h = tm.begin(&st.ms_sample);
-      rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, stream);
+      rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, w.errb, stream);
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_filter);
-      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, w.cand_idx, w.cand_count, stream);
+      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, w.cand_idx, w.cand_val, w.cand_count, stream);
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
-      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, s.cand_stride, w.cand_count,
-                         w.bound, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, w.cand_val, s.cand_stride, 4, w.cand_count,
+                         w.bound, w.errb, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 3;
       if (rc) return rc;
@@ -233,21 +236,22 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
                                  w.fb_idx, (long long)s.fb_split * k1, w.fb_count, stream);
         if (rc) return rc;
         // n_fail doubles as the (unused) failure sink of the fallback rerank
-        rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, (long long)s.fb_split * k1,
-                           w.fb_count, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
+        rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
+                           w.fb_count, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
         if (rc) return rc;
       }
       tm.end(hfb);
     }
     st.n_chunks++;
   }
-  unsigned long long h_total = 0;
+  unsigned long long h_total[2] = {0, 0};
   int h_fb_fail = 0;
-  SBK_CUDA_CHECK(cudaMemcpyAsync(&h_total, w.cand_total, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaMemcpyAsync(h_total, w.cand_total, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fb_fail, w.n_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (h_fb_fail > 0) { set_error("knn: exact fallback left %d rows unresolved", h_fb_fail); return SBK_ERR_INTERNAL; }
-  st.n_candidates = (long long)h_total;
+  st.n_candidates = (long long)h_total[0];
+  st.n_reranked = (long long)h_total[1];
   tm.collect();
   if (stats) *stats = st;
   return SBK_OK;

@@ -79,37 +79,42 @@ __device__ __forceinline__ double sqdist_row(const double* __restrict__ q, const
 template <>
 __device__ __forceinline__ double sqdist_row<float>(const double* __restrict__ q,
                                                     const float* __restrict__ y, int d) {
-  double acc = 0.0;
+  // four independent accumulators (column c goes to accumulator c mod 4) so the FMA
+  // latency chain is 4x shorter; the final combination order is fixed -> deterministic
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int c = 0;
   if ((((uintptr_t)y) & 15) == 0) {
     const float4* y4 = reinterpret_cast<const float4*>(y);
+#pragma unroll 4
     for (; c + 4 <= d; c += 4) {
       float4 v = __ldg(y4 + (c >> 2));
       double t0 = q[c] - (double)v.x, t1 = q[c + 1] - (double)v.y;
       double t2 = q[c + 2] - (double)v.z, t3 = q[c + 3] - (double)v.w;
-      acc = fma(t0, t0, acc); acc = fma(t1, t1, acc);
-      acc = fma(t2, t2, acc); acc = fma(t3, t3, acc);
+      a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1);
+      a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
     }
   }
-  for (; c < d; ++c) { double t = q[c] - (double)__ldg(y + c); acc = fma(t, t, acc); }
-  return acc;
+  for (; c < d; ++c) { double t = q[c] - (double)__ldg(y + c); a0 = fma(t, t, a0); }
+  return (a0 + a1) + (a2 + a3);
 }
 
 template <>
 __device__ __forceinline__ double sqdist_row<double>(const double* __restrict__ q,
                                                      const double* __restrict__ y, int d) {
-  double acc = 0.0;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int c = 0;
   if ((((uintptr_t)y) & 15) == 0) {
     const double2* y2 = reinterpret_cast<const double2*>(y);
-    for (; c + 2 <= d; c += 2) {
-      double2 v = __ldg(y2 + (c >> 1));
-      double t0 = q[c] - v.x, t1 = q[c + 1] - v.y;
-      acc = fma(t0, t0, acc); acc = fma(t1, t1, acc);
+#pragma unroll 4
+    for (; c + 4 <= d; c += 4) {
+      double2 v = __ldg(y2 + (c >> 1)), w = __ldg(y2 + (c >> 1) + 1);
+      double t0 = q[c] - v.x, t1 = q[c + 1] - v.y, t2 = q[c + 2] - w.x, t3 = q[c + 3] - w.y;
+      a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1);
+      a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
     }
   }
-  for (; c < d; ++c) { double t = q[c] - __ldg(y + c); acc = fma(t, t, acc); }
-  return acc;
+  for (; c < d; ++c) { double t = q[c] - __ldg(y + c); a0 = fma(t, t, a0); }
+  return (a0 + a1) + (a2 + a3);
 }
 
 }  // namespace sbk

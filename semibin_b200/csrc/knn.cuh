@@ -13,10 +13,10 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
                         cudaStream_t stream);
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
-                  const uint32_t* cand_idx, long long cand_stride, const int32_t* cand_count,
-                  const double* bound, int k,
+                  const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
+                  const int32_t* cand_count, const double* bound, const float* errb, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
-                  int32_t* fail_rows, int* n_fail, unsigned long long* cand_total,
+                  int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream);
 
 // ---- tensor-core (tcgen05) filter: knn_tc.cu ----
@@ -51,10 +51,11 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, c
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
-                    cudaStream_t stream);
-// Filter pass over all references: fills cand_idx[slot*cand_cap..], cand_count[slot].
+                    float* errb, cudaStream_t stream);
+// Filter pass over all references: fills 4 segments of cand_cap/4 per slot (cand_idx / cand_val),
+// cand_count[slot*4 + segment].
 int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
-                    uint32_t* cand_idx, int32_t* cand_count, cudaStream_t stream);
+                    uint32_t* cand_idx, float* cand_val, int32_t* cand_count, cudaStream_t stream);
 int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
 int tc_row_errors(TcState* st, const TcPlan& p, long long n, double* E, double* nrm_out, cudaStream_t stream);
 

@@ -11,6 +11,7 @@
 // from SemiBin/cluster.py:94-105 and long_read_cluster.py:108-113.
 #include "common.cuh"
 #include "knn.cuh"
+#include <algorithm>
 
 namespace sbk {
 
@@ -63,15 +64,44 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
     for (int qi = 0; qi < XF_QT; ++qi) acc[qi] = 0.0;
     if (valid) {
       const T* y = X + j * ld;
-      for (int c = 0; c < d; ++c) {
-        const double yv = (double)__ldg(y + c);
-        const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)c * XF_QT);
+      // 16 columns per step: the loads of a step are independent (memory-level parallelism),
+      // 16-byte vector loads when the row is aligned
+      const bool vec_ok = ((((uintptr_t)y) & 15) == 0);
+      for (int c0 = 0; c0 < d; c0 += 16) {
+        double yv[16];
+        const int nc = min(16, d - c0);
+        if (vec_ok && nc == 16) {
+          if (sizeof(T) == 4) {
+            const float4* y4 = reinterpret_cast<const float4*>(y + c0);
 #pragma unroll
-        for (int h = 0; h < XF_QT / 2; ++h) {
-          double2 qq = q2[h];
-          double t0 = qq.x - yv, t1 = qq.y - yv;
-          acc[2 * h] = fma(t0, t0, acc[2 * h]);
-          acc[2 * h + 1] = fma(t1, t1, acc[2 * h + 1]);
+            for (int u = 0; u < 4; ++u) {
+              const float4 f = __ldg(y4 + u);
+              yv[4 * u] = (double)f.x; yv[4 * u + 1] = (double)f.y; yv[4 * u + 2] = (double)f.z; yv[4 * u + 3] = (double)f.w;
+            }
+          } else {
+            const double2* y2 = reinterpret_cast<const double2*>(y + c0);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const double2 f = __ldg(y2 + u);
+              yv[2 * u] = f.x; yv[2 * u + 1] = f.y;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) yv[u] = (u < nc) ? (double)__ldg(y + c0 + u) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (u < nc) {
+            const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)(c0 + u) * XF_QT);
+#pragma unroll
+            for (int h = 0; h < XF_QT / 2; ++h) {
+              double2 qq = q2[h];
+              double t0 = qq.x - yv[u], t1 = qq.y - yv[u];
+              acc[2 * h] = fma(t0, t0, acc[2 * h]);
+              acc[2 * h + 1] = fma(t1, t1, acc[2 * h + 1]);
+            }
+          }
         }
       }
 #pragma unroll
@@ -143,62 +173,158 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
 // ---------------------------------------------------------------------------
 // rerank
 // ---------------------------------------------------------------------------
-static constexpr int RR_THREADS = 256;
+static constexpr int RR_THREADS = 128;
+
+// order-preserving map float -> uint32
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
 
 // One CTA per candidate slot.
 //   rows       : global row id per slot (NULL -> q_begin + slot)
-//   bound      : per slot, every reference NOT in the candidate list is known to
-//                have d2 > bound (NULL -> +inf, i.e. the list is a guaranteed superset)
-//   fail_rows / n_fail : rows whose certificate failed are appended here (and
-//                their output left untouched)
+//   cand_idx   : [slot][n_seg][seg_cap] candidate columns, cand_count[slot*n_seg+seg] valid per segment
+//   cand_val   : tensor-core scores of the candidates (NULL on the exact path)
+//   errb       : per slot bound E_i on |score - exact| (with cand_val): candidates whose score exceeds
+//                (k+1)-th smallest score + 2 E_i cannot be among the k+1 nearest and are not reranked
+//   bound      : per slot, every reference NOT in the candidate list is known to have d2 > bound
+//                (NULL -> +inf, i.e. the list is a guaranteed superset)
+//   fail_rows / n_fail : rows whose certificate failed are appended here (output left untouched)
 template <typename T, typename OutT>
 __global__ void __launch_bounds__(RR_THREADS)
 rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ rows, long long q_begin,
-              const uint32_t* __restrict__ cand_idx, long long cand_stride,
-              const int32_t* __restrict__ cand_count, const double* __restrict__ bound,
-              int k, int pmax,
+              const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
+              long long cand_stride, int n_seg, const int32_t* __restrict__ cand_count,
+              const double* __restrict__ bound, const float* __restrict__ errb,
+              int k, int ncand_cap, int pmax,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
-              unsigned long long* __restrict__ cand_total) {
+              unsigned long long* __restrict__ totals) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* q = reinterpret_cast<double*>(smem_raw);           // [d]
-  double* key = q + ((d + 1) & ~1);                          // [pmax]
-  uint32_t* id = reinterpret_cast<uint32_t*>(key + pmax);    // [pmax]
-  __shared__ int s_drop;
+  double* key = q + ((d + 1) & ~1);                          // [pmax]  survivors: exact d2
+  uint32_t* id = reinterpret_cast<uint32_t*>(key + pmax);    // [pmax]  survivors: column
+  uint32_t* cid = id + pmax;                                 // [ncand_cap]  all candidates (tensor path only)
+  float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_remaining;
+  __shared__ int s_drop, s_m;
 
   const int tid = threadIdx.x;
   const long long slot = blockIdx.x;
   const long long row = rows ? (long long)rows[slot] : (q_begin + slot);
   const int k1 = k + 1;
+  const int seg_cap = (int)(cand_stride / n_seg);
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-  int n = cand_count[slot];
-  bool fail = (n > cand_stride) || (n < k1);
+  // segment sizes (uniform across the block)
+  int seg_n[4], seg_off[4], n = 0;
+  bool fail = false;
+#pragma unroll
+  for (int sgm = 0; sgm < 4; ++sgm) {
+    seg_n[sgm] = 0; seg_off[sgm] = n;
+    if (sgm < n_seg) {
+      const int c = cand_count[slot * n_seg + sgm];
+      fail |= (c > seg_cap);
+      seg_n[sgm] = min(c, seg_cap);
+      n += seg_n[sgm];
+    }
+  }
+  fail |= (n < k1);
   if (fail) {
     if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
     return;
   }
   for (int c = tid; c < d; c += RR_THREADS) q[c] = (double)X[row * ld + c];
-  if (tid == 0) { s_drop = -1; if (cand_total) atomicAdd(cand_total, (unsigned long long)n); }
-  int P = (int)pow2ceil((uint32_t)n);
-  if (P < 2) P = 2;
+  if (tid == 0) { s_drop = -1; s_m = 0; }
+  uint32_t* cdst = cand_val ? cid : id;          // exact path: candidates ARE the survivors
+#pragma unroll
+  for (int sgm = 0; sgm < 4; ++sgm) {
+    const uint32_t* ci = cand_idx + slot * cand_stride + (long long)sgm * seg_cap;
+    const float* cv = cand_val ? cand_val + slot * cand_stride + (long long)sgm * seg_cap : nullptr;
+    for (int c = tid; c < seg_n[sgm]; c += RR_THREADS) {
+      cdst[seg_off[sgm] + c] = ci[c];
+      if (cv) cval[seg_off[sgm] + c] = cv[c];
+    }
+  }
   __syncthreads();
-  const uint32_t* ci = cand_idx + slot * cand_stride;
+
+  int m;
+  if (cand_val) {
+    // ---- (k+1)-th smallest score by 4-pass radix select, then the 2E cut ----
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k1;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      hist[tid] = 0; hist[tid + 128] = 0;
+      __syncthreads();
+      for (int c = tid; c < n; c += RR_THREADS) {
+        const uint32_t u = f2ord(cval[c]);
+        if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        uint32_t loc[8], sum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { loc[b] = hist[tid * 8 + b]; sum += loc[b]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+          if (tid >= o) incl += y;
+        }
+        const uint32_t excl = incl - sum;
+        if (excl < remaining && remaining <= incl) {
+          uint32_t run = excl;
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            if (run < remaining && remaining <= run + loc[b]) {
+              s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
+              s_remaining = remaining - run;
+            }
+            run += loc[b];
+          }
+        }
+      }
+      __syncthreads();
+      prefix = s_prefix; remaining = s_remaining; mask |= 0xffu << shift;
+    }
+    const float kth_score = ord2f(prefix);
+    const float cut = __fadd_ru(kth_score, __fmul_ru(2.0f, errb[slot]));
+    for (int c = tid; c < n; c += RR_THREADS) {
+      if (cval[c] <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
+    }
+    __syncthreads();
+    m = s_m;
+    if (m > pmax) {                              // more survivors than the sort buffer: exact filter takes the row
+      if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
+      return;
+    }
+  } else {
+    m = n;
+  }
+  if (tid == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
+
+  // ---- exact FP64 distances of the survivors ----
+  int P = (int)pow2ceil((uint32_t)m);
+  if (P < 2) P = 2;
   for (int c = tid; c < P; c += RR_THREADS) {
     double kk = INF; uint32_t jj = 0xffffffffu;
-    if (c < n) {
-      jj = ci[c];
+    if (c < m) {
+      jj = id[c];
       if (jj != 0xffffffffu) kk = sqdist_row<T>(q, X + (long long)jj * ld, d);
     }
-    key[c] = kk; id[c] = jj;
+    key[c] = kk;
+    if (c >= m) id[c] = jj;
   }
   block_bitonic_sort<RR_THREADS>(key, id, P, tid);
   // certificate: the (k+1)-th smallest exact d2 must be strictly below every
   // excluded reference's lower bound
-  double kth = key[k];
-  double b = bound ? bound[slot] : INF;
-  if (!(kth < b) || id[k] == 0xffffffffu) {
+  const double kth = (m >= k1) ? key[k] : INF;
+  const double b = bound ? bound[slot] : INF;
+  if (m < k1 || !(kth < b) || id[k] == 0xffffffffu) {
     if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
     return;
   }
@@ -223,30 +349,37 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   }
 }
 
-size_t rerank_smem(int d, int pmax) { return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + 16; }
+size_t rerank_smem(int d, int pmax, int ncand_cap) {
+  return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 8 + 16;
+}
 
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
-                  const uint32_t* cand_idx, long long cand_stride, const int32_t* cand_count,
-                  const double* bound, int k,
+                  const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
+                  const int32_t* cand_count, const double* bound, const float* errb, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
-                  int32_t* fail_rows, int* n_fail, unsigned long long* cand_total,
+                  int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream) {
   if (n_slots <= 0) return SBK_OK;
+  // tensor path: all candidates staged (ncand_cap), survivors of the score cut sorted in a
+  // buffer of pmax entries; exact path: every candidate is a survivor
+  int ncand_cap = cand_val ? (int)cand_stride : 0;
   int pmax = (int)pow2ceil((uint32_t)cand_stride);
-  size_t smem = rerank_smem(d, pmax);
+  if (cand_val) pmax = std::min(pmax, std::max(1024, (int)pow2ceil((uint32_t)(2 * (k + 1)))));
+  size_t smem = rerank_smem(d, pmax, ncand_cap);
   if (smem > 227 * 1024) { set_error("rerank: candidate capacity %lld too large", cand_stride); return SBK_ERR_INVALID; }
+  if (n_seg < 1 || n_seg > 4 || cand_stride % n_seg) { set_error("rerank: bad segmentation"); return SBK_ERR_INVALID; }
   dim3 grid((unsigned)n_slots);
   if (dtype == SBK_F32) {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<float, float><<<grid, RR_THREADS, smem, stream>>>(
-        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_stride, cand_count, bound, k, pmax,
-        (float*)out_dist, out_idx, out_row0, fail_rows, n_fail, cand_total);
+        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, errb,
+        k, ncand_cap, pmax, (float*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   } else {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<double, double><<<grid, RR_THREADS, smem, stream>>>(
-        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_stride, cand_count, bound, k, pmax,
-        (double*)out_dist, out_idx, out_row0, fail_rows, n_fail, cand_total);
+        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, errb,
+        k, ncand_cap, pmax, (double*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   }
   SBK_LAUNCH_CHECK();
   return SBK_OK;

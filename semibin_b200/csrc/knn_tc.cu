@@ -28,8 +28,10 @@
 //   warp 1     : single-thread tcgen05.mma issuer, M=128 N=256 K=16, FP16 in /
 //                FP32 accumulate in TMEM, two accumulator stages (2 x 256 cols)
 //   warp 2     : TMEM allocator
-//   warps 4-11 : epilogue: tcgen05.ld 32x32b.x32, FMNMX3 min-tree against the
-//                per-row threshold, rare-path append to the candidate list
+//   warps 4-19 : epilogue (4 warps per TMEM lane quadrant, 64 tile columns each):
+//                tcgen05.ld 32x32b.x32, FMNMX3 min-tree over groups of 8 against
+//                the per-row threshold, rare-path append to the thread's own
+//                candidate segment (register counter, no atomics)
 #include "common.cuh"
 #include "knn.cuh"
 #include <math.h>
@@ -38,15 +40,23 @@
 
 namespace sbk {
 
-static constexpr int TC_THREADS = 384;
 static constexpr int TC_EPI_WARP0 = 4;
-static constexpr int TC_EPI_WARPS = 8;
-static constexpr int TC_NGROUP = 64;            // group minima per row (2 halves x 32 columns)
+static constexpr int TC_EPI_WARPS = 16;         // 4 per TMEM lane quadrant, 64 of the 256 tile columns each
+static constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
+static constexpr int TC_NGROUP = 128;           // group minima per row (4 column quarters x 32 columns)
 static constexpr int TC_MAX_KPAD = 176;
 static constexpr uint32_t TC_IDESC =            // kind::f16: A,B = F16 (0), D = F32 (1<<4), K-major,
     (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N>>3 @17, M>>4 @24
 
 enum TcMode { TC_SAMPLE = 0, TC_FILTER = 1, TC_DUMP = 2 };
+
+// bytes of the reference-tile ring; at least the SAMPLE epilogue's scratch
+// ([TC_NGROUP][TC_BM] floats) which reuses it once the pipeline has drained
+__host__ __device__ static inline size_t tc_ring_bytes(int kpad, int nstage) {
+  const size_t ring = (size_t)nstage * TC_BN * kpad * 2;
+  const size_t scratch = (size_t)TC_NGROUP * TC_BM * 4;
+  return ring > scratch ? ring : scratch;
+}
 
 // device scalars produced by staging (non-negative doubles stored as ordered bits)
 struct TcScalars {
@@ -73,16 +83,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");   // suspend-time hint (ns)
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 8000000000LL) {        // ~4 s
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 8000000000LL) {        // ~4 s
       printf("sbk: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
@@ -278,7 +289,8 @@ struct TcArgs {
   float* thr;                 // [slots]
   double* bound;              // [slots]
   // FILTER
-  uint32_t* cand_idx; int32_t* cand_count; int cand_cap;
+  uint32_t* cand_idx; float* cand_val; int32_t* cand_count; int cand_cap;   // 4 segments of cand_cap/4 per row
+  float* errb;                // SAMPLE: per-slot error bound E_i (scaled domain)
   // DUMP
   float* dump; long long dump_ld;
 };
@@ -292,14 +304,13 @@ tc_kernel(const TcArgs p) {
   const uint32_t b_bytes = (uint32_t)TC_BN * kpad * 2;
   unsigned char* sA = smem;
   unsigned char* sB = smem + a_bytes;
-  unsigned char* tail = sB + (size_t)p.nstage * b_bytes;
+  unsigned char* tail = sB + tc_ring_bytes(kpad, p.nstage);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [nstage]
   uint64_t* empty_bar = full_bar + 4;                              // [nstage]
   uint64_t* tfull_bar = empty_bar + 4;                             // [2]
   uint64_t* tempty_bar = tfull_bar + 2;                            // [2]
   uint64_t* a_bar = tempty_bar + 2;                                // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
-  int* row_cnt = reinterpret_cast<int*>(tmem_slot + 2);            // [TC_BM]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -312,7 +323,6 @@ tc_kernel(const TcArgs p) {
     mbar_init(a_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < TC_BM) row_cnt[threadIdx.x] = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -363,7 +373,7 @@ tc_kernel(const TcArgs p) {
   } else if (warp >= TC_EPI_WARP0) {
     // ===== epilogue =====
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
-    const int half = (warp - TC_EPI_WARP0) >> 2; // column half of the 256-wide tile
+    const int w4 = (warp - TC_EPI_WARP0) >> 2;   // which 64-column quarter of the 256-wide tile
     const int r_in_tile = q * 32 + lane;
     const long long grow = tile_m * TC_BM + r_in_tile;
     const bool row_ok = grow >= p.row_lo && grow < p.row_hi;
@@ -374,61 +384,85 @@ tc_kernel(const TcArgs p) {
 #pragma unroll
       for (int c = 0; c < 32; ++c) gmin[c] = INFINITY;
     }
-    if (MODE == TC_FILTER && row_ok) thr = p.thr[slot];
-    uint32_t* my_cand = (MODE == TC_FILTER && row_ok) ? p.cand_idx + slot * (long long)p.cand_cap : nullptr;
+    const int seg_cap = p.cand_cap >> 2;
+    int cnt = 0;                                 // candidates this thread has emitted for its row segment
+    uint32_t* my_idx = nullptr; float* my_val = nullptr;
+    if (MODE == TC_FILTER && row_ok) {
+      thr = p.thr[slot];
+      my_idx = p.cand_idx + slot * (long long)p.cand_cap + (long long)w4 * seg_cap;
+      my_val = p.cand_val + slot * (long long)p.cand_cap + (long long)w4 * seg_cap;
+    }
 
     for (long long t = 0; t < n_tiles; ++t) {
       const int as = (int)(t & 1);
       mbar_wait(&tfull_bar[as], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN + half * 128);
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        tmem_ld_wait();
-        if (MODE == TC_SAMPLE) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(v[c]));
-        } else if (MODE == TC_FILTER) {
-          float mn = __uint_as_float(v[0]);
-#pragma unroll
-          for (int c = 1; c < 32; ++c) mn = fminf(mn, __uint_as_float(v[c]));
-          if (mn <= thr) {
-            const uint32_t j0 = (uint32_t)(t * TC_BN + half * 128 + ch * 32);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              if (__uint_as_float(v[c]) <= thr) {
-                const int pos = atomicAdd(&row_cnt[r_in_tile], 1);
-                if (pos < p.cand_cap) my_cand[pos] = j0 + c;
-              }
-            }
-          }
-        } else {   // TC_DUMP
-          if (row_ok) {
-            const long long j0 = t * TC_BN + half * 128 + ch * 32;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) p.dump[slot * p.dump_ld + j0 + c] = __uint_as_float(v[c]);
-          }
-        }
-      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN + w4 * 64);
+      uint32_t va[32], vb[32];
+      tmem_ld32(taddr, va);
+      tmem_ld32(taddr + 32, vb);
+      tmem_ld_wait();
+      // the accumulator stage is free as soon as its values sit in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (MODE == TC_SAMPLE) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          gmin[c] = fminf(gmin[c], fminf(__uint_as_float(va[c]), __uint_as_float(vb[c])));
+      } else if (MODE == TC_FILTER) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t* v = hh ? vb : va;
+          float m8[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float a0 = fminf(fminf(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1])), __uint_as_float(v[8 * g + 2]));
+            const float a1 = fminf(fminf(__uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4])), __uint_as_float(v[8 * g + 5]));
+            m8[g] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
+          }
+          const float mn = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
+          if (mn <= thr) {
+            const uint32_t j0 = (uint32_t)(t * TC_BN + w4 * 64 + hh * 32);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (m8[g] <= thr) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float x = __uint_as_float(v[8 * g + c]);
+                  const bool hit = x <= thr;
+                  if (hit && cnt < seg_cap) { my_idx[cnt] = j0 + 8 * g + c; my_val[cnt] = x; }
+                  cnt += hit ? 1 : 0;
+                }
+              }
+            }
+          }
+        }
+      } else {   // TC_DUMP
+        if (row_ok) {
+          const long long j0 = t * TC_BN + w4 * 64;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            p.dump[slot * p.dump_ld + j0 + c] = __uint_as_float(va[c]);
+            p.dump[slot * p.dump_ld + j0 + 32 + c] = __uint_as_float(vb[c]);
+          }
+        }
+      }
     }
 
     // ---- per-row results ----
-    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
     if (MODE == TC_FILTER) {
-      if (half == 0 && row_ok) p.cand_count[slot] = row_cnt[r_in_tile];
+      if (row_ok) p.cand_count[slot * 4 + w4] = cnt;
     }
     if (MODE == TC_SAMPLE) {
-      // all MMAs have retired (last tfull observed) -> the B ring is free: use it as scratch
+      asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+      // all MMAs have retired (last tfull observed by every epilogue warp) -> the B ring
+      // is free: use it as scratch
       float* gm = reinterpret_cast<float*>(sB);                    // [TC_NGROUP][TC_BM]
 #pragma unroll
-      for (int c = 0; c < 32; ++c) gm[(half * 32 + c) * TC_BM + r_in_tile] = gmin[c];
+      for (int c = 0; c < 32; ++c) gm[(w4 * 32 + c) * TC_BM + r_in_tile] = gmin[c];
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-      if (half == 0 && row_ok) {
+      if (w4 == 0 && row_ok) {
         // r-th smallest of the TC_NGROUP group minima (selection by repeated min)
         float last = -INFINITY; int taken = 0; float tau = INFINITY;
         while (taken < p.order_stat) {
@@ -444,6 +478,7 @@ tc_kernel(const TcArgs p) {
         const float thr_f = __double2float_ru((double)tau + 2.0 * E);
         const double S = p.scale[0];
         p.thr[slot] = thr_f;
+        p.errb[slot] = __double2float_ru(E);
         // every non-emitted j has s > thr  =>  S^2 d2 - n_i > thr - E
         p.bound[slot] = ((double)thr_f - E + p.nrm[grow]) / (S * S);
       }
@@ -503,17 +538,20 @@ TcPlan tc_make_plan(long long n_ref, int d, int k) {
   }
   p.sample_size = (best_m + TC_BN - 1) / TC_BN * TC_BN;
   p.order_stat = best_r;
-  double cap = (best_cnt + 6.0 * best_sd) * 1.5 + 64;
-  cap = std::max(cap, (double)(2 * k1));
-  cap = std::min(cap, (double)n_ref);
-  cap = std::min(cap, 8192.0);
-  p.cand_cap = (int)((cap + 63) / 64) * 64;
+  // candidates are written to 4 per-row segments (one per epilogue warp of a TMEM lane quadrant,
+  // each covering a fixed quarter of every reference tile): size a segment for total/4 + 6 sigma
+  double tot = (best_cnt + 6.0 * best_sd) * 1.5 + 64;
+  tot = std::max(tot, (double)(2 * k1));
+  tot = std::min(tot, (double)n_ref + 4.0);
+  double seg = tot / 4.0 + 6.0 * sqrt(tot / 4.0) + 16.0;
+  seg = std::min(seg, 2048.0);
+  p.cand_cap = 4 * ((int)((seg + 63) / 64) * 64);
   return p;
 }
 
 long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
   // keep the candidate lists of one chunk under ~12 GB
-  long long rows = (long long)(12e9 / ((double)p.cand_cap * 4.0));
+  long long rows = (long long)(40e9 / ((double)p.cand_cap * 8.0));
   rows = std::max<long long>(rows / TC_BM * TC_BM, TC_BM * 148);
   return std::min<long long>(rows, 1 << 20);
 }
@@ -545,11 +583,11 @@ size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query) {
 }
 
 static size_t tc_smem_bytes(int kpad, int nstage) {
-  return (size_t)TC_BM * kpad * 2 + (size_t)nstage * TC_BN * kpad * 2 + 13 * 8 + 16 + TC_BM * 4 + 64;
+  return (size_t)TC_BM * kpad * 2 + tc_ring_bytes(kpad, nstage) + 13 * 8 + 16 + 64;
 }
 
 static int tc_pick_stages(int kpad) {
-  for (int s = 3; s >= 2; --s)
+  for (int s = 4; s >= 2; --s)
     if (tc_smem_bytes(kpad, s) <= 227 * 1024) return s;
   return 0;
 }
@@ -632,19 +670,19 @@ static void tc_chunk_args(TcState* st, const TcPlan& p, long long row0, long lon
 }
 
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
-                    cudaStream_t stream) {
+                    float* errb, cudaStream_t stream) {
   TcArgs a; long long n_mtiles;
   tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
-  a.bound = bound;
+  a.bound = bound; a.errb = errb;
   a.b_tiles = st->s_tiles; a.n_btiles = p.sample_size / TC_BN;
   return tc_launch<TC_SAMPLE>(a, n_mtiles, stream);
 }
 
 int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
-                    uint32_t* cand_idx, int32_t* cand_count, cudaStream_t stream) {
+                    uint32_t* cand_idx, float* cand_val, int32_t* cand_count, cudaStream_t stream) {
   TcArgs a; long long n_mtiles;
   tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
-  a.cand_idx = cand_idx; a.cand_count = cand_count;
+  a.cand_idx = cand_idx; a.cand_val = cand_val; a.cand_count = cand_count;
   a.b_tiles = st->b_tiles; a.n_btiles = p.n_tiles;
   return tc_launch<TC_FILTER>(a, n_mtiles, stream);
 }
