@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""bench_path.py -- stage-by-stage timings of the remaining SURVEY section 8 rows
+(not the driver's benchmark; that is bench.py).  Prints one JSON line per config:
+
+  C2  short-read, N=200k, S=1  : both kNN graphs + edge list (KL)
+  C3  multi-sample, N=1M, S=10 : (ii) KL-weighted edges; (i) combined D=146 with --combined
+  C4  long-read, N=500k, D=100+S: kNN graph + 12-eps sweep + DBSCAN labels
+
+Achieved GB/s figures use the ALGORITHMIC bytes of SURVEY section 8(d) / DESIGN.md section 4.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+
+def timed(fn, reps=1):
+    import torch
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1) / reps
+
+
+def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
+    import torch
+    from semibin_b200 import synth, cluster
+    from semibin_b200.neighbors import knn
+    emb, feat, depth, L = synth.short_read_case(n, n_sample=S, seed=20243)
+    if combined:
+        f = np.concatenate([feat, depth[:, 0::2].astype(np.float64) / 100.0], axis=1)
+        f = f / np.sum(f, axis=0)
+        f = f / np.abs(f).sum(axis=1, keepdims=True)
+        feat = f
+    E = torch.from_numpy(emb).cuda()
+    F = torch.from_numpy(np.ascontiguousarray(feat)).cuda()
+    Dp = torch.from_numpy(depth).cuda()
+    res = {}
+    knn(E, k)  # warm
+    (a_d, a_i, st_a), res['knn_emb_ms'] = timed(lambda: knn(E, k, return_stats=True))
+    knn(F, k)
+    (b_d, b_i, st_b), res['knn_feat_ms'] = timed(lambda: knn(F, k, return_stats=True))
+    ths = cluster.threshold_sequence()
+    cluster.edges_stage1(a_d, a_i, b_d, b_i, ths)
+    (w, rowmax, counts), res['stage1_ms'] = timed(lambda: cluster.edges_stage1(a_d, a_i, b_d, b_i, ths))
+    thr = cluster.pick_threshold(counts.cpu().numpy(), n, max_node)
+    cluster.edges_stage2(w, a_i, 0, thr, Dp, S, combined)
+    (X, Y, V), res['stage2_ms'] = timed(lambda: cluster.edges_stage2(w, a_i, 0, thr, Dp, S, combined))
+    n_edges = int(X.shape[0])
+    kept_dir = n_edges * 2                       # directed edges surviving ~ 2x upper triangle
+    res.update(n=n, S=S, combined=combined, k=k, d_feat=int(F.shape[1]), threshold=thr, n_edges=n_edges,
+               stats_emb={k2: st_a[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')},
+               stats_feat={k2: st_b[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')})
+    b1 = n * k * (4 + 4 + 4 + 8) + n * k * 8
+    res['stage1_GBps'] = b1 / res['stage1_ms'] / 1e6
+    b2 = n * k * 12 + kept_dir * (8 * S if not combined else 0) + n_edges * 16 * 2
+    res['stage2_GBps'] = b2 / res['stage2_ms'] / 1e6
+    res['edge_list_total_ms'] = res['knn_emb_ms'] + res['knn_feat_ms'] + res['stage1_ms'] + res['stage2_ms']
+    res['tflops_feat_filter'] = 2.0 * n * n * F.shape[1] / (st_b['ms_filter'] * 1e-3) / 1e12 if st_b['ms_filter'] else None
+    if cpu_check:
+        from oracle import edges as oe, compare
+        t0 = time.perf_counter()
+        RX, RY, RV, t = oe.edge_list_restated(a_d.cpu().numpy().astype(np.float64), a_i.cpu().numpy().astype(np.int64),
+                                              b_d.cpu().numpy(), b_i.cpu().numpy().astype(np.int64), depth,
+                                              max_node=max_node, is_combined=combined, n_sample=S)
+        res['cpu_sparse_restatement_s'] = time.perf_counter() - t0
+        res['parity'] = compare.compare_edges((RX, RY, RV), (X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()))
+    return res
+
+
+def long_read(n, S, k=200, cpu_check=False):
+    import torch
+    from semibin_b200 import synth, long_read as lr
+    from semibin_b200.neighbors import knn
+    X, L = synth.long_read_case(n, n_sample=S, seed=20244)
+    Xd = torch.from_numpy(X).cuda()
+    Ld = torch.from_numpy(L.astype(np.float64)).cuda()
+    res = dict(n=n, S=S, k=k, d=int(X.shape[1]))
+    knn(Xd, k)
+    (dist, idx, st), res['knn_ms'] = timed(lambda: knn(Xd, k, return_stats=True))
+    lr.radius_sweep(dist, idx, lr.EPS_GRID, min_samples=5, sample_weight=Ld)
+    (plen, core), res['sweep_ms'] = timed(lambda: lr.radius_sweep(dist, idx, lr.EPS_GRID, min_samples=5, sample_weight=Ld))
+    lr.dbscan_labels(idx, plen, core)
+    labels, res['labels_ms'] = timed(lambda: lr.dbscan_labels(idx, plen, core))
+    res['sweep_GBps'] = (n * k * 8 + n * 12 * 5) / res['sweep_ms'] / 1e6
+    res['n_clusters'] = [int(labels[e].max().item()) + 1 for e in range(12)]
+    res['stats'] = {k2: st[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')}
+    res['total_ms'] = res['knn_ms'] + res['sweep_ms'] + res['labels_ms']
+    if cpu_check:
+        from oracle import dbscan as od
+        nb = min(n, 50000)
+        d = dist[:nb].cpu().numpy().astype(np.float64)
+        # CPU baseline: the reference's dbscan call on a 50k-row sub-graph is not meaningful (indices
+        # point outside); instead time sklearn on a fresh 50k problem
+        from semibin_b200 import synth as sy
+        Xs, Ls = sy.long_read_case(nb, n_sample=S, seed=20245)
+        from sklearn.neighbors import kneighbors_graph
+        from sklearn.cluster import dbscan
+        import warnings
+        t0 = time.perf_counter()
+        G = kneighbors_graph(Xs, k, mode='distance', p=2)
+        res['cpu_knn_50k_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            for eps in (0.05, 0.3, 0.55):
+                dbscan(G, eps=eps, min_samples=5, metric='precomputed', sample_weight=Ls)
+        res['cpu_dbscan_50k_s_per_eps'] = (time.perf_counter() - t0) / 3
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--config', default='C2')
+    ap.add_argument('--n', type=int, default=0)
+    ap.add_argument('--combined', action='store_true')
+    ap.add_argument('--cpu-check', action='store_true')
+    a = ap.parse_args()
+    if a.config == 'C2':
+        r = short_read(a.n or 200000, 1, False, cpu_check=a.cpu_check)
+    elif a.config == 'C3':
+        r = short_read(a.n or 1000000, 10, a.combined, cpu_check=a.cpu_check)
+    elif a.config == 'C4':
+        r = long_read(a.n or 500000, 1, cpu_check=a.cpu_check)
+    else:
+        raise SystemExit('unknown config')
+    r['config'] = a.config
+    print(json.dumps(r), flush=True)
+
+
+if __name__ == '__main__':
+    main()

@@ -78,6 +78,13 @@ typedef struct sbk_knn_stats {
   float ms_fallback;             /* exact filter + rerank of uncertified rows */
   float ms_exact_filter;         /* exact path: FP64 filter */
   int64_t n_reranked;            /* candidates that survived the score cut and got an FP64 distance */
+  /* why rows went to the exact fallback (tensor path) */
+  int64_t n_fail_overflow;       /* a candidate segment overflowed */
+  int64_t n_fail_few;            /* fewer than k+1 candidates passed the threshold */
+  int64_t n_fail_survivors;      /* more survivors of the score cut than the sort buffer holds */
+  int64_t n_fail_certificate;    /* (k+1)-th exact distance not below the exclusion bound */
+  int32_t n_split_cols;          /* high-energy columns given an FP16 hi+lo representation */
+  int32_t reserved2;
 } sbk_knn_stats;
 
 int sbk_version(void);

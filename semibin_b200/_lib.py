@@ -23,7 +23,9 @@ class KnnStats(C.Structure):
                 ('n_launches', C.c_int32), ('reserved', C.c_int32),
                 ('ms_prepare', C.c_float), ('ms_sample', C.c_float), ('ms_filter', C.c_float),
                 ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float),
-                ('n_reranked', C.c_int64)]
+                ('n_reranked', C.c_int64), ('n_fail_overflow', C.c_int64), ('n_fail_few', C.c_int64),
+                ('n_fail_survivors', C.c_int64), ('n_fail_certificate', C.c_int64),
+                ('n_split_cols', C.c_int32), ('reserved2', C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

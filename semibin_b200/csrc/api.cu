@@ -180,8 +180,9 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
     tm.end(h);
     st.n_launches += 5;
     if (rc) return rc;
+    tm.on = (stats != nullptr);
     st.sample_size = s.plan.sample_size; st.cand_capacity = s.plan.cand_cap;
-    st.order_stat = s.plan.order_stat; st.kpad = s.plan.kpad;
+    st.order_stat = s.plan.order_stat; st.kpad = s.plan.kpad; st.n_split_cols = s.plan.n_split;
   }
 
   for (long long c0 = 0; c0 < n_q; c0 += s.chunk) {
@@ -244,7 +245,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
     }
     st.n_chunks++;
   }
-  unsigned long long h_total[2] = {0, 0};
+  unsigned long long h_total[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int h_fb_fail = 0;
   SBK_CUDA_CHECK(cudaMemcpyAsync(h_total, w.cand_total, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fb_fail, w.n_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -252,6 +253,8 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
   if (h_fb_fail > 0) { set_error("knn: exact fallback left %d rows unresolved", h_fb_fail); return SBK_ERR_INTERNAL; }
   st.n_candidates = (long long)h_total[0];
   st.n_reranked = (long long)h_total[1];
+  st.n_fail_overflow = (long long)h_total[2]; st.n_fail_few = (long long)h_total[3];
+  st.n_fail_survivors = (long long)h_total[4]; st.n_fail_certificate = (long long)h_total[5];
   tm.collect();
   if (stats) *stats = st;
   return SBK_OK;

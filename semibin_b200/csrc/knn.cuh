@@ -21,7 +21,10 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
 
 // ---- tensor-core (tcgen05) filter: knn_tc.cu ----
 struct TcPlan {
-  int kpad;            // padded K (multiple of 16) = d + 3 norm columns rounded up
+  int kpad;            // padded K (multiple of 16) = d + 3 norm columns + 2 per split column, rounded up
+  int kpad_alloc;      // widest kpad the staging buffers are sized for
+  int max_split;       // most columns tc_prepare may split
+  int n_split;         // columns actually split (set by tc_prepare)
   int ksteps;          // kpad / 16
   long long n_tiles;   // reference tiles of TC_BN rows
   int sample_size;     // rows in the threshold sample (multiple of TC_BN)
@@ -46,7 +49,7 @@ TcPlan tc_make_plan(long long n_ref, int d, int k);
 long long tc_chunk_rows(const TcPlan& p, long long n_ref);
 size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query);
 // Stage operands, centre/scale, sample; `chunk` = max query rows per tc_filter_chunk call.
-int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, const TcPlan& p,
+int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
                long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream);
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].

@@ -234,9 +234,11 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       n += seg_n[sgm];
     }
   }
-  fail |= (n < k1);
-  if (fail) {
-    if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
+  if (fail || n < k1) {
+    if (tid == 0) {
+      int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row;
+      if (totals) atomicAdd(&totals[fail ? 2 : 3], 1ull);        // [2] segment overflow, [3] too few candidates
+    }
     return;
   }
   for (int c = tid; c < d; c += RR_THREADS) q[c] = (double)X[row * ld + c];
@@ -299,7 +301,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     __syncthreads();
     m = s_m;
     if (m > pmax) {                              // more survivors than the sort buffer: exact filter takes the row
-      if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
+      if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
       return;
     }
   } else {
@@ -325,7 +327,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   const double kth = (m >= k1) ? key[k] : INF;
   const double b = bound ? bound[slot] : INF;
   if (m < k1 || !(kth < b) || id[k] == 0xffffffffu) {
-    if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
+    if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[5], 1ull); }
     return;
   }
   // self removal by index; if absent drop entry 0 (neighbors/_base.py:943-957)

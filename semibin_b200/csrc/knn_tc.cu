@@ -45,6 +45,7 @@ static constexpr int TC_EPI_WARPS = 16;         // 4 per TMEM lane quadrant, 64 
 static constexpr int TC_THREADS = 32 * (TC_EPI_WARP0 + TC_EPI_WARPS);
 static constexpr int TC_NGROUP = 128;           // group minima per row (4 column quarters x 32 columns)
 static constexpr int TC_MAX_KPAD = 176;
+static constexpr int TC_MAX_SPLIT = 12;         // columns that may get an FP16 hi+lo representation
 static constexpr uint32_t TC_IDESC =            // kind::f16: A,B = F16 (0), D = F32 (1<<4), K-major,
     (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);   // N>>3 @17, M>>4 @24
 
@@ -63,7 +64,10 @@ struct TcScalars {
   unsigned long long zmax2_bits;   // max_j ||z_j||^2
   unsigned long long dmax2_bits;   // max_j ||delta_j||^2
   unsigned long long rmax_bits;    // max_j |nrep_j - n_j|
-  unsigned long long zhmax2_bits;  // max_j ||zh_j||^2
+  unsigned long long zhmax2_bits;  // max_j ||a_j||^2   (a = representable part: zh, + zl on split columns)
+  unsigned long long lmax2_bits;   // max_j ||zl_j||^2  (low parts of the split columns)
+  int n_split;                     // number of split ("precision") columns chosen for this matrix
+  int split_cols[TC_MAX_SPLIT];
 };
 
 // ---------------------------------------------------------------------------
@@ -143,37 +147,64 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <typename T>
 __global__ void __launch_bounds__(256)
 tc_colstat_kernel(const T* __restrict__ X, long long n, int d, long long ld,
-                  double* __restrict__ colsum, unsigned long long* __restrict__ maxabs_bits) {
+                  double* __restrict__ colsum, double* __restrict__ colsumsq,
+                  unsigned long long* __restrict__ maxabs_bits) {
   // block handles 1024 rows; thread t accumulates columns t, t+256, ...
   const long long r0 = (long long)blockIdx.x * 1024;
   const long long r1 = min(n, r0 + 1024);
   double mx = 0.0;
   for (int c = threadIdx.x; c < d; c += 256) {
-    double s = 0.0;
-    for (long long r = r0; r < r1; ++r) { double v = (double)X[r * ld + c]; s += v; mx = fmax(mx, fabs(v)); }
+    double s = 0.0, s2 = 0.0;
+    for (long long r = r0; r < r1; ++r) { double v = (double)X[r * ld + c]; s += v; s2 = fma(v, v, s2); mx = fmax(mx, fabs(v)); }
     atomicAdd(&colsum[c], s);
+    atomicAdd(&colsumsq[c], s2);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   if ((threadIdx.x & 31) == 0) atomicMax(maxabs_bits, (unsigned long long)__double_as_longlong(mx));
 }
 
-__global__ void tc_centre_kernel(const double* __restrict__ colsum, const unsigned long long* __restrict__ maxabs_bits,
-                                 long long n, int d, double* __restrict__ centre, double* __restrict__ scale) {
-  // single block
+// Single block: centre, scale, and the choice of "precision" columns.  A column whose
+// energy (sum of squared centred values) is far above the average dominates the FP16
+// rounding error of every score; such columns get an FP16 hi+lo representation in two
+// extra K columns each (cross terms zl_i*zh_j + zh_i*zl_j), which removes their share
+// of the error bound.  Homogeneous matrices (the embedding) select none.
+__global__ void tc_centre_kernel(const double* __restrict__ colsum, const double* __restrict__ colsumsq,
+                                 const unsigned long long* __restrict__ maxabs_bits,
+                                 long long n, int d, int max_split, double* __restrict__ centre,
+                                 double* __restrict__ scale, TcScalars* __restrict__ sc) {
   __shared__ double cmax;
-  if (threadIdx.x == 0) cmax = 0.0;
+  __shared__ double energy[4096];
+  __shared__ double total;
+  __shared__ int n_sel;
+  if (threadIdx.x == 0) { cmax = 0.0; total = 0.0; n_sel = 0; }
   __syncthreads();
-  double m = 0.0;
+  double m = 0.0, esum = 0.0;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     double cv = colsum[c] / (double)n;
     cv = (double)(float)cv;                       // keep the centre float-representable
     centre[c] = cv;
     m = fmax(m, fabs(cv));
+    // sum (x - cv)^2 = sumsq - 2 cv sum + n cv^2
+    const double e = fmax(0.0, colsumsq[c] - 2.0 * cv * colsum[c] + (double)n * cv * cv);
+    energy[c] = e;
+    esum += e;
   }
   atomicMax((unsigned long long*)&cmax, (unsigned long long)__double_as_longlong(m));
+  atomicAdd(&total, esum);
+  __syncthreads();
+  const double avg = total / (double)d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    const double e = energy[c];
+    if (e > 4.0 * avg) {
+      int rank = 0;
+      for (int o = 0; o < d; ++o) rank += (energy[o] > e || (energy[o] == e && o < c)) ? 1 : 0;
+      if (rank < max_split) { sc->split_cols[rank] = c; atomicAdd(&n_sel, 1); }
+    }
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
+    sc->n_split = n_sel;                          // ranks 0..n_sel-1 are exactly the selected columns
     double bound = __longlong_as_double((long long)*maxabs_bits) + cmax;   // >= max |x - c|
     if (!(bound > 0.0)) bound = 1.0;
     // power of two S with S * bound in [4, 8): FP16 elements stay far from overflow and
@@ -185,8 +216,9 @@ __global__ void tc_centre_kernel(const double* __restrict__ colsum, const unsign
 }
 
 // One thread per staged row.  `src_rows` (optional) gathers a sample.
-//   b_tiles : reference-side operand, tiles of TC_BN rows:  -2*zh | n_hi n_mid n_lo | 0
-//   a_tiles : query-side operand, tiles of TC_BM rows:        zh  |  1    1     1   | 0   (NULL for samples)
+//   b_tiles : reference-side operand, tiles of TC_BN rows:  -2*zh | n_hi n_mid n_lo | (-2*zh_c, -2*zl_c) per split column | 0
+//   a_tiles : query-side operand, tiles of TC_BM rows:        zh  |  1    1     1   | (  zl_c ,   zh_c ) per split column | 0
+//             (NULL for samples)
 // tile layout (FP16 elements): [kpad/8 chunks][R rows][8]  -> core matrices of 8 rows x 16 B
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -243,6 +275,31 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
     bdst[(long long)(c >> 3) * TC_BN * 8 + (c & 7)] = hn[e];
     if (adst) adst[(long long)(c >> 3) * TC_BM * 8 + (c & 7)] = __float2half_rn(real ? 1.0f : 0.0f);
   }
+  // split columns: hi+lo representation, two K columns each
+  double l2 = 0.0;
+  const int n_split = sc->n_split;
+  for (int t = 0; t < n_split; ++t) {
+    const int c = sc->split_cols[t];
+    float zhf = 0.f, zlf = 0.f;
+    if (real) {
+      const double z = S * ((double)X[src * ld + c] - centre[c]);
+      zhf = __half2float(__double2half(z));
+      const double r = z - (double)zhf;
+      zlf = __half2float(__double2half(r));
+      const double rr = r - (double)zlf;
+      d2 += rr * rr - r * r;                                     // residual of this column is now rr
+      zh2 += ((double)zhf + (double)zlf) * ((double)zhf + (double)zlf) - (double)zhf * (double)zhf;
+      l2 += (double)zlf * (double)zlf;
+    }
+    const int k0 = d + 3 + 2 * t, k1c = k0 + 1;
+    bdst[(long long)(k0 >> 3) * TC_BN * 8 + (k0 & 7)] = __float2half_rn(-2.0f * zhf);     // x A: zl_i
+    bdst[(long long)(k1c >> 3) * TC_BN * 8 + (k1c & 7)] = __float2half_rn(-2.0f * zlf);   // x A: zh_i
+    if (adst) {
+      adst[(long long)(k0 >> 3) * TC_BM * 8 + (k0 & 7)] = __float2half_rn(zlf);
+      adst[(long long)(k1c >> 3) * TC_BM * 8 + (k1c & 7)] = __float2half_rn(zhf);
+    }
+  }
+  if (d2 < 0.0) d2 = 0.0;
   if (real && !src_rows) {
     nrm[row] = n2;
     dq[row] = __double2float_ru(sqrt(d2));
@@ -251,6 +308,7 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
     atomicMax(&sc->dmax2_bits, (unsigned long long)__double_as_longlong(d2));
     atomicMax(&sc->rmax_bits, (unsigned long long)__double_as_longlong(fabs(rep)));
     atomicMax(&sc->zhmax2_bits, (unsigned long long)__double_as_longlong(zh2));
+    atomicMax(&sc->lmax2_bits, (unsigned long long)__double_as_longlong(l2));
   }
 }
 
@@ -266,7 +324,9 @@ __device__ __forceinline__ double tc_row_error(float dqi, float zqi, const TcSca
   const double zhmax = sqrt(__longlong_as_double((long long)sc->zhmax2_bits));
   const double rmax = __longlong_as_double((long long)sc->rmax_bits);
   const double nmax = zmax * zmax;
-  const double rounding = 2.0 * ((double)dqi * zmax + (double)zqi * dmax);
+  const double lmax2 = __longlong_as_double((long long)sc->lmax2_bits);
+  // <z_i,z_j> - [<a_i,a_j> - sum_split zl_i zl_j] = <delta_i,z_j> + <a_i,delta_j> + sum_split zl_i zl_j
+  const double rounding = 2.0 * ((double)dqi * zmax + (double)zqi * dmax + lmax2);
   // FP32 accumulation inside the tensor core: assume no better than truncation at
   // every one of the kpad additions (2^-23 relative each) of the absolute sum
   const double acc = (double)kpad * 1.1920928955078125e-07 * (nmax + 2.0 * (double)zqi * zhmax);
@@ -508,7 +568,11 @@ static double binom_tail_ge(int n, double p, int r) {   // P(Binomial(n,p) >= r)
 
 TcPlan tc_make_plan(long long n_ref, int d, int k) {
   TcPlan p;
-  p.kpad = (d + 3 + 15) / 16 * 16;
+  // split ("precision") columns are chosen from the data by tc_prepare; size the staging
+  // buffers for the most it may choose
+  p.max_split = std::max(0, std::min(TC_MAX_SPLIT, std::min(d, (TC_MAX_KPAD - d - 3) / 2)));
+  p.kpad_alloc = (d + 3 + 2 * p.max_split + 15) / 16 * 16;
+  p.kpad = p.kpad_alloc;          // replaced by the actual width in tc_prepare
   p.ksteps = p.kpad / 16;
   p.n_tiles = (n_ref + TC_BN - 1) / TC_BN;
   p.n_groups = TC_NGROUP;
@@ -560,11 +624,11 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
   const long long n_a = (n_ref + TC_BM - 1) / TC_BM * TC_BM;
   const long long n_b = p.n_tiles * TC_BN;
   (void)n_a;   // A tiles are staged by the same kernel that walks the n_b padded rows
-  st->a_tiles = a.take<__half>((size_t)n_b * p.kpad);
-  st->b_tiles = a.take<__half>((size_t)n_b * p.kpad);
-  st->s_tiles = a.take<__half>((size_t)p.sample_size * p.kpad);
+  st->a_tiles = a.take<__half>((size_t)n_b * p.kpad_alloc);
+  st->b_tiles = a.take<__half>((size_t)n_b * p.kpad_alloc);
+  st->s_tiles = a.take<__half>((size_t)p.sample_size * p.kpad_alloc);
   st->centre = a.take<double>(4096);
-  st->colsum = a.take<double>(4096);
+  st->colsum = a.take<double>(2 * 4096);     // column sums, then column sums of squares
   st->scale = a.take<double>(8);
   st->nrm = a.take<double>((size_t)n_b);
   st->dq = a.take<float>((size_t)n_b);
@@ -600,18 +664,17 @@ static long long coprime_multiplier(long long n) {
   return m;
 }
 
-int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, const TcPlan& p,
+int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
                long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream) {
-  if (p.kpad > TC_MAX_KPAD || tc_pick_stages(p.kpad) == 0) {
+  if ((d + 3 + 15) / 16 * 16 > TC_MAX_KPAD || d > 4096) {
     set_error("tensor kNN path supports feature width <= %d (got %d); use SBK_KNN_EXACT", TC_MAX_KPAD - 3, d);
     return SBK_ERR_INVALID;
   }
   Arena a(ws, ws_bytes);
   tc_carve(a, p, n_ref, chunk, st);
   if (!a.ok()) { set_error("tensor kNN: staging workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
-  st->nstage = tc_pick_stages(p.kpad);
   st->n_ref = n_ref; st->d = d;
-  SBK_CUDA_CHECK(cudaMemsetAsync(st->colsum, 0, 4096 * sizeof(double), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->colsum, 0, 2 * 4096 * sizeof(double), stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(st->maxabs, 0, 8 * sizeof(unsigned long long), stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(st->sc, 0, 2 * sizeof(TcScalars), stream));
   const unsigned cb = (unsigned)((n_ref + 1023) / 1024);
@@ -619,11 +682,21 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, c
   const long long n_a = (n_ref + TC_BM - 1) / TC_BM * TC_BM;
   // zero the A padding rows beyond n_b (n_a <= n_b always since TC_BN is a multiple of TC_BM)
   (void)n_a;
-  if (dtype == SBK_F32) tc_colstat_kernel<float><<<cb, 256, 0, stream>>>((const float*)X, n_ref, d, ld, st->colsum, st->maxabs);
-  else tc_colstat_kernel<double><<<cb, 256, 0, stream>>>((const double*)X, n_ref, d, ld, st->colsum, st->maxabs);
+  if (dtype == SBK_F32) tc_colstat_kernel<float><<<cb, 256, 0, stream>>>((const float*)X, n_ref, d, ld, st->colsum, st->colsum + 4096, st->maxabs);
+  else tc_colstat_kernel<double><<<cb, 256, 0, stream>>>((const double*)X, n_ref, d, ld, st->colsum, st->colsum + 4096, st->maxabs);
   SBK_LAUNCH_CHECK();
-  tc_centre_kernel<<<1, 256, 0, stream>>>(st->colsum, st->maxabs, n_ref, d, st->centre, st->scale);
+  tc_centre_kernel<<<1, 256, 0, stream>>>(st->colsum, st->colsum + 4096, st->maxabs, n_ref, d, p.max_split, st->centre, st->scale, st->sc);
   SBK_LAUNCH_CHECK();
+  // the operand width depends on how many precision columns the data asked for
+  int n_split = 0;
+  SBK_CUDA_CHECK(cudaMemcpyAsync(&n_split, &st->sc->n_split, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+  p.n_split = n_split;
+  p.kpad = (d + 3 + 2 * n_split + 15) / 16 * 16;
+  p.ksteps = p.kpad / 16;
+  p.stage_bytes = (size_t)TC_BN * p.kpad * 2;
+  st->nstage = tc_pick_stages(p.kpad);
+  if (p.kpad > p.kpad_alloc || st->nstage == 0) { set_error("tensor kNN: operand width %d exceeds the staged capacity", p.kpad); return SBK_ERR_INTERNAL; }
   const unsigned sb = (unsigned)((n_b + 127) / 128);
   if (dtype == SBK_F32)
     tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad,
