@@ -3,7 +3,7 @@
 N = 1,000,000 synthetic contigs, embedding width 100 (float32), k = 200
 (SemiBin/cluster.py:94-99, max_edges default 200), exact neighbour sets.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n N] [--k K]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--contigs N] [--neighbors K]
 
 A "step" is one complete kNN-graph build over all N contigs: FP16 staging,
 tcgen05 threshold + filter passes over all N x N pairs, FP64 rerank with the
@@ -25,6 +25,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline) must use every host
+# core, as SemiBin does through --threads (SemiBin/utils.py:71-83).  Set before numpy/sklearn load.
+if ('reference' in sys.argv) or os.environ.get('WORLD_SIZE', '1') == '1':
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count())
 
 import numpy as np  # noqa: E402
 
@@ -288,8 +293,8 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--n', type=int, default=N_DEFAULT)
-    ap.add_argument('--k', type=int, default=K_DEFAULT)
+    ap.add_argument('--contigs', dest='n', type=int, default=N_DEFAULT)
+    ap.add_argument('--neighbors', dest='k', type=int, default=K_DEFAULT)
     ap.add_argument('--algo', default='auto')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -163,14 +163,14 @@ int sbk_dbscan_labels(const int32_t* idx, int64_t n, int32_t k,
                       const int32_t* prefix_len, const uint8_t* core, int32_t n_eps,
                       long long* labels, void* workspace, size_t ws_bytes, void* cuda_stream);
 
-/* Debug / test hook: raw tcgen05 tile product.  Computes, with the same FP16
- * operand staging and MMA pipeline as the tensor filter, the matrix
- *   s[i,j] = ||y_j - c||^2*S^2 - 2*S^2*<x_i - c, y_j - c>   (i < n_q, j < n_ref <= 65536)
- * into out[n_q, ceil(n_ref/256)*256] (float) together with the per-row error
- * bound E[n_q] and the exact scaled row norms nrm[n_q] followed by the scale S
- * (nrm has n_q+1 doubles), so tests can verify |s - (S^2 d2 - nrm_i)| <= E_i. */
+/* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
+ * MMA pipeline as the tensor filter and returns the accumulator values
+ *   L[i,j] <= S^2 d2_ij - nrm_i + norms4[i].w      (i < n_q, j < n_ref <= 65536)
+ * in out[n_q, ceil(n_ref/256)*256] (float), the per-row norms of the error model
+ * norms4[n_ref*4] = (||z||, ||delta||, ||a||, ||l||^2), nrm[n_ref+1] = exact ||z||^2 followed by the
+ * scale S, and info[2] = {kpad, n_split_cols}, so tests can verify the lower/upper bound claims. */
 int sbk_debug_tc_scores(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
-                        int64_t n_q, float* out, double* E, double* nrm,
+                        int64_t n_q, float* out, float* norms4, double* nrm, int32_t* info,
                         void* workspace, size_t ws_bytes, void* cuda_stream);
 size_t sbk_debug_tc_workspace_bytes(int64_t n_ref, int32_t d);
 

@@ -25,7 +25,7 @@ static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk 
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
 
 struct KnnWs {
-  uint32_t* cand_idx; float* cand_val; int32_t* cand_count; double* bound; float* errb;
+  uint32_t* cand_idx; float* cand_val; int32_t* cand_count; double* bound;
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
   void* tc;                                             // tensor-path staging area
@@ -48,7 +48,7 @@ static int exact_split(long long n_q, long long n_ref) {
 static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int k, int algo) {
   KnnShape s; memset(&s, 0, sizeof(s));
   const int k1 = k + 1;
-  if (algo == SBK_KNN_AUTO) algo = (n_ref >= TC_MIN_N && (d + 3 + 15) / 16 * 16 <= 176) ? SBK_KNN_TENSOR : SBK_KNN_EXACT;
+  if (algo == SBK_KNN_AUTO) algo = (n_ref >= TC_MIN_N && (d + 5 + 15) / 16 * 16 <= 176) ? SBK_KNN_TENSOR : SBK_KNN_EXACT;
   s.algo = algo;
   if (algo == SBK_KNN_EXACT) {
     s.chunk = std::min<long long>(std::max<long long>(n_q, 1), EXACT_CHUNK);
@@ -73,7 +73,6 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, int k, KnnWs& w)
   w.cand_val = s.algo == SBK_KNN_TENSOR ? a.take<float>((size_t)s.chunk * s.cand_stride) : nullptr;
   w.cand_count = a.take<int32_t>((size_t)s.chunk * 4);
   w.bound = a.take<double>((size_t)s.chunk);
-  w.errb = a.take<float>((size_t)s.chunk);
   w.fail_rows = a.take<int32_t>((size_t)s.chunk + (size_t)s.fb_rows + 1);
   w.n_fail = a.take<int>(64);
   w.cand_total = a.take<unsigned long long>(8);   // [0] candidates emitted, [1] candidates reranked in FP64
@@ -199,13 +198,13 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
-                         nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         nullptr, nullptr, 0.0, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 2;
       if (rc) return rc;
     } else {
       int h = tm.begin(&st.ms_sample);
-      rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, w.errb, stream);
+      rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, stream);
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_filter);
@@ -214,7 +213,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, w.cand_val, s.cand_stride, 4, w.cand_count,
-                         w.bound, w.errb, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         w.bound, tcs.norms4, tc_c_acc(s.plan.kpad), k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 3;
       if (rc) return rc;
@@ -238,7 +237,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
         if (rc) return rc;
         // n_fail doubles as the (unused) failure sink of the fallback rerank
         rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
-                           w.fb_count, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
+                           w.fb_count, nullptr, nullptr, 0.0, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
         if (rc) return rc;
       }
       tm.end(hfb);
@@ -266,7 +265,7 @@ extern "C" size_t sbk_debug_tc_workspace_bytes(int64_t n_ref, int32_t d) {
 }
 
 extern "C" int sbk_debug_tc_scores(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
-                                   int64_t n_q, float* out, double* E, double* nrm,
+                                   int64_t n_q, float* out, float* norms4, double* nrm, int32_t* info,
                                    void* workspace, size_t ws_bytes, void* cuda_stream) {
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   if (sbk_device_count() < 1) { set_error("no CUDA device"); return SBK_ERR_CUDA; }
@@ -277,7 +276,7 @@ extern "C" int sbk_debug_tc_scores(const void* X, int dtype, int64_t n_ref, int3
   if (rc) return rc;
   rc = tc_dump_scores(&st, p, n_q, out, p.n_tiles * TC_BN, stream);
   if (rc) return rc;
-  rc = tc_row_errors(&st, p, n_q, E, nrm, stream);
+  rc = tc_debug_norms(&st, p, n_ref, norms4, nrm, info, stream);
   if (rc) return rc;
   SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
   return SBK_OK;

@@ -14,7 +14,7 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
                   const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
-                  const int32_t* cand_count, const double* bound, const float* errb, int k,
+                  const int32_t* cand_count, const double* bound, const float4* norms4, double c_acc, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream);
@@ -37,10 +37,35 @@ static constexpr int TC_BM = 128;   // query rows per CTA
 static constexpr int TC_BN = 256;   // reference rows per MMA tile
 
 struct TcScalars;
+
+// ---- per-pair error model of the tensor-core score (shared by knn_tc.cu and the rerank) ----
+// Allowance for the FP32 accumulation inside the tensor core: per MMA instruction (K = 16) each of
+// the 16 products and the running sum may lose up to 2^-24 of the largest magnitude: 17 * 2^-24 < 2^-20
+// relative to the sum of absolute values, per instruction.
+__host__ __device__ static inline double tc_c_acc(int kpad) { return (double)(kpad / 16) * 9.5367431640625e-07; }
+// norms4[j] = ( ||z_j||, ||delta_j||, ||a_j||, ||l_j||^2 ), every entry rounded up.
+//   z = S (x - c) exact, a = FP16-representable part (hi, + lo on split columns), delta = z - a,
+//   l = low parts of the split columns.
+// exact score  e_ij = ||z_j||^2 - 2 <z_i, z_j>;  the MMA yields L_ij with  L_ij <= e_ij + ||l_i||^2  where it
+// subtracted at least  G_ij + J_j:
+//   G_ij = 2 ||delta_i|| ||z_j|| + ||a_i|| (2 ||delta_j|| + 2 c_acc ||a_j||)      (bilinear -> two K columns)
+//   J_j  = c_acc ||z_j||^2 + ||l_j||^2                                             (folded into the norm pieces)
+__host__ __device__ static inline double tc_pair_G(const float4& ni, const float4& nj, double c_acc) {
+  return 2.0 * (double)ni.y * (double)nj.x + (double)ni.z * (2.0 * (double)nj.y + 2.0 * c_acc * (double)nj.z);
+}
+__host__ __device__ static inline double tc_pair_J(const float4& nj, double c_acc) {
+  return c_acc * (double)nj.x * (double)nj.x + (double)nj.w;
+}
+// e_ij <= L_ij + tc_pair_upper_slack: what the MMA subtracted (<= (1+2^-9)^2 G + J + representation slack)
+// plus the true error bound G + J + ||l_i||^2.
+__host__ __device__ static inline double tc_pair_upper_slack(const float4& ni, const float4& nj, double c_acc) {
+  const double G = tc_pair_G(ni, nj, c_acc), J = tc_pair_J(nj, c_acc);
+  return 2.02 * G + 2.02 * J + (double)ni.w + 2.4e-7 * ((double)nj.x + (double)nj.y + (double)ni.z + (double)ni.y) + 4e-7;
+}
 struct TcState {
   __half* a_tiles; __half* b_tiles; __half* s_tiles;
   double* centre; double* colsum; double* scale; double* nrm;
-  float* dq; float* zq; TcScalars* sc; int32_t* sample_rows; float* thr;
+  float4* norms4; TcScalars* sc; int32_t* sample_rows; float* thr;
   unsigned long long* maxabs;
   int nstage; long long n_ref; int d;
 };
@@ -54,12 +79,13 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
-                    float* errb, cudaStream_t stream);
+                    cudaStream_t stream);
 // Filter pass over all references: fills 4 segments of cand_cap/4 per slot (cand_idx / cand_val),
 // cand_count[slot*4 + segment].
 int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
                     uint32_t* cand_idx, float* cand_val, int32_t* cand_count, cudaStream_t stream);
 int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
-int tc_row_errors(TcState* st, const TcPlan& p, long long n, double* E, double* nrm_out, cudaStream_t stream);
+int tc_debug_norms(TcState* st, const TcPlan& p, long long n, float* norms4_out, double* nrm_out, int32_t* info,
+                   cudaStream_t stream);
 
 }  // namespace sbk

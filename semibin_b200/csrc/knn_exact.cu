@@ -173,7 +173,7 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
 // ---------------------------------------------------------------------------
 // rerank
 // ---------------------------------------------------------------------------
-static constexpr int RR_THREADS = 128;
+static constexpr int RR_THREADS = 256;
 
 // order-preserving map float -> uint32
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -187,9 +187,10 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
 // One CTA per candidate slot.
 //   rows       : global row id per slot (NULL -> q_begin + slot)
 //   cand_idx   : [slot][n_seg][seg_cap] candidate columns, cand_count[slot*n_seg+seg] valid per segment
-//   cand_val   : tensor-core scores of the candidates (NULL on the exact path)
-//   errb       : per slot bound E_i on |score - exact| (with cand_val): candidates whose score exceeds
-//                (k+1)-th smallest score + 2 E_i cannot be among the k+1 nearest and are not reranked
+//   cand_val   : tensor-core LOWER bounds L_ij of the candidates' exact scores (NULL on the exact path)
+//   norms4     : per-row norms of the per-pair error model (knn.cuh); U_ij = L_ij + slack_ij is an upper
+//                bound of the exact score, so the (k+1)-th smallest U bounds the (k+1)-th smallest exact
+//                score from above and candidates with L_ij above it cannot be among the k+1 nearest
 //   bound      : per slot, every reference NOT in the candidate list is known to have d2 > bound
 //                (NULL -> +inf, i.e. the list is a guaranteed superset)
 //   fail_rows / n_fail : rows whose certificate failed are appended here (output left untouched)
@@ -199,7 +200,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ rows, long long q_begin,
               const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
               long long cand_stride, int n_seg, const int32_t* __restrict__ cand_count,
-              const double* __restrict__ bound, const float* __restrict__ errb,
+              const double* __restrict__ bound, const float4* __restrict__ norms4, double c_acc,
               int k, int ncand_cap, int pmax,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
@@ -209,7 +210,8 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   double* key = q + ((d + 1) & ~1);                          // [pmax]  survivors: exact d2
   uint32_t* id = reinterpret_cast<uint32_t*>(key + pmax);    // [pmax]  survivors: column
   uint32_t* cid = id + pmax;                                 // [ncand_cap]  all candidates (tensor path only)
-  float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]
+  float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]  lower bounds L
+  float* uval = cval + ncand_cap;                            // [ncand_cap]  upper bounds U
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ int s_drop, s_m;
@@ -257,13 +259,21 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
 
   int m;
   if (cand_val) {
-    // ---- (k+1)-th smallest score by 4-pass radix select, then the 2E cut ----
+    // ---- upper bounds, (k+1)-th smallest of them by 4-pass radix select, then the cut ----
+    {
+      const float4 ni = norms4[row];
+      for (int c = tid; c < n; c += RR_THREADS) {
+        const float4 nj = norms4[cid[c]];
+        uval[c] = __double2float_ru((double)cval[c] + tc_pair_upper_slack(ni, nj, c_acc));
+      }
+    }
+    __syncthreads();
     uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k1;
     for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[tid] = 0; hist[tid + 128] = 0;
+      hist[tid] = 0;
       __syncthreads();
       for (int c = tid; c < n; c += RR_THREADS) {
-        const uint32_t u = f2ord(cval[c]);
+        const uint32_t u = f2ord(uval[c]);
         if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
       }
       __syncthreads();
@@ -293,8 +303,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       __syncthreads();
       prefix = s_prefix; remaining = s_remaining; mask |= 0xffu << shift;
     }
-    const float kth_score = ord2f(prefix);
-    const float cut = __fadd_ru(kth_score, __fmul_ru(2.0f, errb[slot]));
+    const float cut = ord2f(prefix);             // >= the (k+1)-th smallest exact score
     for (int c = tid; c < n; c += RR_THREADS) {
       if (cval[c] <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
     }
@@ -352,13 +361,13 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
 }
 
 size_t rerank_smem(int d, int pmax, int ncand_cap) {
-  return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 8 + 16;
+  return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 12 + 16;
 }
 
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
                   const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
-                  const int32_t* cand_count, const double* bound, const float* errb, int k,
+                  const int32_t* cand_count, const double* bound, const float4* norms4, double c_acc, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream) {
@@ -375,12 +384,12 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
   if (dtype == SBK_F32) {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<float, float><<<grid, RR_THREADS, smem, stream>>>(
-        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, errb,
+        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, norms4, c_acc,
         k, ncand_cap, pmax, (float*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   } else {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<double, double><<<grid, RR_THREADS, smem, stream>>>(
-        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, errb,
+        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, norms4, c_acc,
         k, ncand_cap, pmax, (double*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   }
   SBK_LAUNCH_CHECK();

@@ -16,9 +16,10 @@
 // three spare K columns carry an FP16 hi/mid/lo split of ||z_j||^2 against ones.
 // ||z_i||^2 is constant per row and irrelevant for the ranking.
 //
-// Exactness: |s_ij - (S^2 d2_ij - ||z_i||^2)| <= E_i (bound derived from the
-// actual FP16 rounding residuals, see tc_stage_kernel / tc_finish_thresholds).
-// Every reference that is NOT emitted has d2 > bound_i; the FP64 rerank
+// Exactness: two more K columns make the MMA subtract a rigorous PER-PAIR error bound
+// E_ij (bilinear in per-row norms, see tc_pair_bound in knn.cuh), so the accumulator
+// holds a LOWER bound  L_ij <= S^2 d2_ij - ||z_i||^2 + sigma_i  of the exact score.
+// Every reference that is NOT emitted (L_ij > thr_i) has d2 > bound_i; the FP64 rerank
 // (knn_exact.cu) certifies  d2_(k+1) < bound_i  per row or sends the row to the
 // exact filter.  The neighbour sets are therefore exact, never approximate.
 //
@@ -59,13 +60,8 @@ __host__ __device__ static inline size_t tc_ring_bytes(int kpad, int nstage) {
   return ring > scratch ? ring : scratch;
 }
 
-// device scalars produced by staging (non-negative doubles stored as ordered bits)
+// device scalars produced by the centre/selection kernel
 struct TcScalars {
-  unsigned long long zmax2_bits;   // max_j ||z_j||^2
-  unsigned long long dmax2_bits;   // max_j ||delta_j||^2
-  unsigned long long rmax_bits;    // max_j |nrep_j - n_j|
-  unsigned long long zhmax2_bits;  // max_j ||a_j||^2   (a = representable part: zh, + zl on split columns)
-  unsigned long long lmax2_bits;   // max_j ||zl_j||^2  (low parts of the split columns)
   int n_split;                     // number of split ("precision") columns chosen for this matrix
   int split_cols[TC_MAX_SPLIT];
 };
@@ -226,8 +222,8 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
                 const int32_t* __restrict__ src_rows, long long n_staged,
                 const double* __restrict__ centre, const double* __restrict__ scale, int kpad,
                 __half* __restrict__ b_tiles, __half* __restrict__ a_tiles,
-                double* __restrict__ nrm, float* __restrict__ dq, float* __restrict__ zq,
-                TcScalars* __restrict__ sc) {
+                double* __restrict__ nrm, float4* __restrict__ norms4,
+                const TcScalars* __restrict__ sc) {
   const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
   if (row >= n_staged) return;
   const long long bt = row / TC_BN, br = row % TC_BN;
@@ -260,21 +256,6 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
     *reinterpret_cast<uint4*>(bdst + (long long)ch * TC_BN * 8) = *reinterpret_cast<uint4*>(hb);
     if (adst) *reinterpret_cast<uint4*>(adst + (long long)ch * TC_BM * 8) = *reinterpret_cast<uint4*>(ha);
   }
-  // FP16 hi/mid/lo split of ||z||^2 (padding rows: a huge value so they never pass a threshold)
-  double nn = real ? n2 : 60000.0;
-  const __half h0 = __double2half(nn);
-  const double r0 = nn - (double)__half2float(h0);
-  const __half h1 = __double2half(r0);
-  const double r1 = r0 - (double)__half2float(h1);
-  const __half h2 = __double2half(r1);
-  const double rep = r1 - (double)__half2float(h2);
-  const __half hn[3] = {h0, h1, h2};
-#pragma unroll
-  for (int e = 0; e < 3; ++e) {
-    const int c = d + e;
-    bdst[(long long)(c >> 3) * TC_BN * 8 + (c & 7)] = hn[e];
-    if (adst) adst[(long long)(c >> 3) * TC_BM * 8 + (c & 7)] = __float2half_rn(real ? 1.0f : 0.0f);
-  }
   // split columns: hi+lo representation, two K columns each
   double l2 = 0.0;
   const int n_split = sc->n_split;
@@ -291,7 +272,7 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
       zh2 += ((double)zhf + (double)zlf) * ((double)zhf + (double)zlf) - (double)zhf * (double)zhf;
       l2 += (double)zlf * (double)zlf;
     }
-    const int k0 = d + 3 + 2 * t, k1c = k0 + 1;
+    const int k0 = d + 5 + 2 * t, k1c = k0 + 1;
     bdst[(long long)(k0 >> 3) * TC_BN * 8 + (k0 & 7)] = __float2half_rn(-2.0f * zhf);     // x A: zl_i
     bdst[(long long)(k1c >> 3) * TC_BN * 8 + (k1c & 7)] = __float2half_rn(-2.0f * zlf);   // x A: zh_i
     if (adst) {
@@ -300,37 +281,50 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
     }
   }
   if (d2 < 0.0) d2 = 0.0;
+  // per-row norms, rounded UP (they only enter error bounds); the 1e-4 inflation covers the
+  // accumulation error of the bound columns themselves
+  const double c_acc = tc_c_acc(kpad);
+  const float nz = __double2float_ru(sqrt(n2) * 1.0001);
+  const float nd = __double2float_ru(sqrt(d2) * 1.0001);
+  const float na = __double2float_ru(sqrt(zh2) * 1.0001);
+  const float l2f = __double2float_ru(l2 * 1.0001);
+  // norm columns d..d+2: FP16 hi/mid/lo split of  t_j = ||z_j||^2 (1 - c_acc) - ||l_j||^2  with the last
+  // piece rounded DOWN, so pieces <= t_j  (padding rows: a huge value so they never pass a threshold)
+  double tt = real ? (n2 * (1.0 - c_acc) - (double)l2f - 1e-12 * n2) : 60000.0;
+  const __half h0 = __double2half(tt);
+  const double r0 = tt - (double)__half2float(h0);
+  const __half h1 = __double2half(r0);
+  const double r1 = r0 - (double)__half2float(h1);
+  const __half h2 = __float2half_rd(__double2float_rd(r1));
+  const __half hn[3] = {h0, h1, h2};
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int c = d + e;
+    bdst[(long long)(c >> 3) * TC_BN * 8 + (c & 7)] = hn[e];
+    if (adst) adst[(long long)(c >> 3) * TC_BM * 8 + (c & 7)] = __float2half_rn(real ? 1.0f : 0.0f);
+  }
+  // bound columns d+3, d+4:  A (u_i, v_i) = (||delta_i||, ||a_i||),  B = -(2||z_j||, 2||delta_j|| + 2 c_acc ||a_j||),
+  // every factor rounded up to FP16  ->  the MMA subtracts >= the bilinear part of E_ij
+  {
+    const float pj = real ? 2.0f * nz : 0.f;
+    const float qj = real ? __fadd_ru(2.0f * nd, __double2float_ru(2.0 * c_acc * (double)na)) : 0.f;
+    const int c0 = d + 3, c1 = d + 4;
+    bdst[(long long)(c0 >> 3) * TC_BN * 8 + (c0 & 7)] = __hneg(__float2half_ru(pj));
+    bdst[(long long)(c1 >> 3) * TC_BN * 8 + (c1 & 7)] = __hneg(__float2half_ru(qj));
+    if (adst) {
+      adst[(long long)(c0 >> 3) * TC_BM * 8 + (c0 & 7)] = __float2half_ru(real ? nd : 0.f);
+      adst[(long long)(c1 >> 3) * TC_BM * 8 + (c1 & 7)] = __float2half_ru(real ? na : 0.f);
+    }
+  }
   if (real && !src_rows) {
     nrm[row] = n2;
-    dq[row] = __double2float_ru(sqrt(d2));
-    zq[row] = __double2float_ru(sqrt(zh2));
-    atomicMax(&sc->zmax2_bits, (unsigned long long)__double_as_longlong(n2));
-    atomicMax(&sc->dmax2_bits, (unsigned long long)__double_as_longlong(d2));
-    atomicMax(&sc->rmax_bits, (unsigned long long)__double_as_longlong(fabs(rep)));
-    atomicMax(&sc->zhmax2_bits, (unsigned long long)__double_as_longlong(zh2));
-    atomicMax(&sc->lmax2_bits, (unsigned long long)__double_as_longlong(l2));
+    norms4[row] = make_float4(nz, nd, na, l2f);
   }
 }
 
 __global__ void tc_sample_rows_kernel(int32_t* __restrict__ rows, int m, long long n, long long mult, long long off) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) rows[i] = (int32_t)(((long long)i * mult + off) % n);   // mult coprime to n -> no repeats for m <= n
-}
-
-// Per-row error bound of the tensor-core score (scaled domain), see file header.
-__device__ __forceinline__ double tc_row_error(float dqi, float zqi, const TcScalars* sc, int kpad) {
-  const double zmax = sqrt(__longlong_as_double((long long)sc->zmax2_bits));
-  const double dmax = sqrt(__longlong_as_double((long long)sc->dmax2_bits));
-  const double zhmax = sqrt(__longlong_as_double((long long)sc->zhmax2_bits));
-  const double rmax = __longlong_as_double((long long)sc->rmax_bits);
-  const double nmax = zmax * zmax;
-  const double lmax2 = __longlong_as_double((long long)sc->lmax2_bits);
-  // <z_i,z_j> - [<a_i,a_j> - sum_split zl_i zl_j] = <delta_i,z_j> + <a_i,delta_j> + sum_split zl_i zl_j
-  const double rounding = 2.0 * ((double)dqi * zmax + (double)zqi * dmax + lmax2);
-  // FP32 accumulation inside the tensor core: assume no better than truncation at
-  // every one of the kpad additions (2^-23 relative each) of the absolute sum
-  const double acc = (double)kpad * 1.1920928955078125e-07 * (nmax + 2.0 * (double)zqi * zhmax);
-  return (rmax + rounding + acc) * 1.0001 + 1e-30;
 }
 
 // ---------------------------------------------------------------------------
@@ -345,12 +339,11 @@ struct TcArgs {
   int kpad, nstage;
   // SAMPLE
   int order_stat;             // r (1-based)
-  const float* dq; const float* zq; const double* nrm; const TcScalars* sc; const double* scale;
+  const float4* norms4; const double* nrm; const TcScalars* sc; const double* scale; int d;
   float* thr;                 // [slots]
   double* bound;              // [slots]
   // FILTER
   uint32_t* cand_idx; float* cand_val; int32_t* cand_count; int cand_cap;   // 4 segments of cand_cap/4 per row
-  float* errb;                // SAMPLE: per-slot error bound E_i (scaled domain)
   // DUMP
   float* dump; long long dump_ld;
 };
@@ -534,13 +527,23 @@ tc_kernel(const TcArgs p) {
           if (cnt_eq == 0) break;                                   // fewer distinct values than r
           taken += cnt_eq; last = m; tau = m;
         }
-        const double E = tc_row_error(p.dq[grow], p.zq[grow], p.sc, kpad);
-        const float thr_f = __double2float_ru((double)tau + 2.0 * E);
+        // tau bounds the k+1 smallest LOWER bounds; their exact scores may be up to the per-pair
+        // slack higher.  Estimate that slack for references at the threshold distance (norms of
+        // such neighbours from the triangle inequality); a poor estimate only costs a fallback,
+        // the certificate below is what guarantees exactness.
+        const float4 ni = p.norms4[grow];
+        const double ni2 = p.nrm[grow];
+        const double c_acc = tc_c_acc(kpad);
+        const double rho = sqrt(fmax(0.0, (double)tau + ni2));
+        const double zj = (double)ni.x + rho;
+        const double ratio = fmax(ni.x > 0.f ? (double)ni.y / (double)ni.x : 0.0, 1.220703125e-4);
+        float4 nj; nj.x = (float)zj; nj.y = (float)(ratio * zj + 6e-8 * sqrt((double)p.d)); nj.z = (float)zj; nj.w = ni.w;
+        const double margin = 1.05 * tc_pair_upper_slack(ni, nj, c_acc);
+        const float thr_f = __double2float_ru((double)tau + margin);
         const double S = p.scale[0];
         p.thr[slot] = thr_f;
-        p.errb[slot] = __double2float_ru(E);
-        // every non-emitted j has s > thr  =>  S^2 d2 - n_i > thr - E
-        p.bound[slot] = ((double)thr_f - E + p.nrm[grow]) / (S * S);
+        // every non-emitted j has L_ij > thr  =>  S^2 d2_ij - n_i = e_ij >= L_ij - ||l_i||^2 > thr - ||l_i||^2
+        p.bound[slot] = ((double)thr_f - (double)ni.w + ni2) / (S * S) * (1.0 - 1e-13);
       }
     }
   }
@@ -570,8 +573,8 @@ TcPlan tc_make_plan(long long n_ref, int d, int k) {
   TcPlan p;
   // split ("precision") columns are chosen from the data by tc_prepare; size the staging
   // buffers for the most it may choose
-  p.max_split = std::max(0, std::min(TC_MAX_SPLIT, std::min(d, (TC_MAX_KPAD - d - 3) / 2)));
-  p.kpad_alloc = (d + 3 + 2 * p.max_split + 15) / 16 * 16;
+  p.max_split = std::max(0, std::min(TC_MAX_SPLIT, std::min(d, (TC_MAX_KPAD - d - 5) / 2)));
+  p.kpad_alloc = (d + 5 + 2 * p.max_split + 15) / 16 * 16;
   p.kpad = p.kpad_alloc;          // replaced by the actual width in tc_prepare
   p.ksteps = p.kpad / 16;
   p.n_tiles = (n_ref + TC_BN - 1) / TC_BN;
@@ -631,8 +634,7 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
   st->colsum = a.take<double>(2 * 4096);     // column sums, then column sums of squares
   st->scale = a.take<double>(8);
   st->nrm = a.take<double>((size_t)n_b);
-  st->dq = a.take<float>((size_t)n_b);
-  st->zq = a.take<float>((size_t)n_b);
+  st->norms4 = a.take<float4>((size_t)n_b);
   st->sc = a.take<TcScalars>(2);
   st->sample_rows = a.take<int32_t>((size_t)p.sample_size);
   st->thr = a.take<float>((size_t)chunk + TC_BM);
@@ -666,8 +668,8 @@ static long long coprime_multiplier(long long n) {
 
 int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
                long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream) {
-  if ((d + 3 + 15) / 16 * 16 > TC_MAX_KPAD || d > 4096) {
-    set_error("tensor kNN path supports feature width <= %d (got %d); use SBK_KNN_EXACT", TC_MAX_KPAD - 3, d);
+  if ((d + 5 + 15) / 16 * 16 > TC_MAX_KPAD || d > 4096) {
+    set_error("tensor kNN path supports feature width <= %d (got %d); use SBK_KNN_EXACT", TC_MAX_KPAD - 5, d);
     return SBK_ERR_INVALID;
   }
   Arena a(ws, ws_bytes);
@@ -692,7 +694,7 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   SBK_CUDA_CHECK(cudaMemcpyAsync(&n_split, &st->sc->n_split, sizeof(int), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
   p.n_split = n_split;
-  p.kpad = (d + 3 + 2 * n_split + 15) / 16 * 16;
+  p.kpad = (d + 5 + 2 * n_split + 15) / 16 * 16;
   p.ksteps = p.kpad / 16;
   p.stage_bytes = (size_t)TC_BN * p.kpad * 2;
   st->nstage = tc_pick_stages(p.kpad);
@@ -700,10 +702,10 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   const unsigned sb = (unsigned)((n_b + 127) / 128);
   if (dtype == SBK_F32)
     tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad,
-                                                   st->b_tiles, st->a_tiles, st->nrm, st->dq, st->zq, st->sc);
+                                                   st->b_tiles, st->a_tiles, st->nrm, st->norms4, st->sc);
   else
     tc_stage_kernel<double><<<sb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad,
-                                                    st->b_tiles, st->a_tiles, st->nrm, st->dq, st->zq, st->sc);
+                                                    st->b_tiles, st->a_tiles, st->nrm, st->norms4, st->sc);
   SBK_LAUNCH_CHECK();
   // pseudo-random (golden-ratio stride) sample without repeats
   const long long mult = coprime_multiplier(n_ref);
@@ -712,10 +714,10 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   const unsigned ssb = (unsigned)((p.sample_size + 127) / 128);
   if (dtype == SBK_F32)
     tc_stage_kernel<float><<<ssb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
-                                                    p.kpad, st->s_tiles, nullptr, nullptr, nullptr, nullptr, st->sc);
+                                                    p.kpad, st->s_tiles, nullptr, nullptr, nullptr, st->sc);
   else
     tc_stage_kernel<double><<<ssb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
-                                                     p.kpad, st->s_tiles, nullptr, nullptr, nullptr, nullptr, st->sc);
+                                                     p.kpad, st->s_tiles, nullptr, nullptr, nullptr, st->sc);
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
@@ -738,15 +740,15 @@ static void tc_chunk_args(TcState* st, const TcPlan& p, long long row0, long lon
   n_mtiles = (row0 + n_rows + TC_BM - 1) / TC_BM - a.tile_m0;
   a.row_lo = row0; a.row_hi = row0 + n_rows;
   a.order_stat = p.order_stat;
-  a.dq = st->dq; a.zq = st->zq; a.nrm = st->nrm; a.sc = st->sc; a.scale = st->scale;
+  a.norms4 = st->norms4; a.nrm = st->nrm; a.sc = st->sc; a.scale = st->scale; a.d = st->d;
   a.thr = st->thr; a.cand_cap = p.cand_cap;
 }
 
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
-                    float* errb, cudaStream_t stream) {
+                    cudaStream_t stream) {
   TcArgs a; long long n_mtiles;
   tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
-  a.bound = bound; a.errb = errb;
+  a.bound = bound;
   a.b_tiles = st->s_tiles; a.n_btiles = p.sample_size / TC_BN;
   return tc_launch<TC_SAMPLE>(a, n_mtiles, stream);
 }
@@ -769,17 +771,21 @@ int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long
   return tc_launch<TC_DUMP>(a, (n_q + TC_BM - 1) / TC_BM, stream);
 }
 
-__global__ void tc_row_error_kernel(const float* dq, const float* zq, const TcScalars* sc, const double* nrm,
-                                    const double* scale, int kpad, long long n, double* E, double* nrm_out) {
+__global__ void tc_debug_norms_kernel(const float4* norms4, const double* nrm, const double* scale,
+                                      const TcScalars* sc, int kpad, long long n, float* norms4_out,
+                                      double* nrm_out, int32_t* info) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  E[i] = tc_row_error(dq[i], zq[i], sc, kpad);
+  const float4 v = norms4[i];
+  norms4_out[4 * i] = v.x; norms4_out[4 * i + 1] = v.y; norms4_out[4 * i + 2] = v.z; norms4_out[4 * i + 3] = v.w;
   nrm_out[i] = nrm[i];
-  if (i == 0) nrm_out[n] = scale[0];            // scale S appended after the norms
+  if (i == 0) { nrm_out[n] = scale[0]; info[0] = kpad; info[1] = sc->n_split; }
 }
 
-int tc_row_errors(TcState* st, const TcPlan& p, long long n, double* E, double* nrm_out, cudaStream_t stream) {
-  tc_row_error_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st->dq, st->zq, st->sc, st->nrm, st->scale, p.kpad, n, E, nrm_out);
+int tc_debug_norms(TcState* st, const TcPlan& p, long long n, float* norms4_out, double* nrm_out, int32_t* info,
+                   cudaStream_t stream) {
+  tc_debug_norms_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(st->norms4, st->nrm, st->scale, st->sc, p.kpad, n,
+                                                                        norms4_out, nrm_out, info);
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
