@@ -46,6 +46,19 @@ def env_int(name, default):
         return default
 
 
+def filter_traffic():
+    """DRAM bytes per filter launch from the newest committed ncu --set full capture (profiles/)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, 'profiles', '*_filter_traffic.json')))
+    if not files:
+        return None
+    try:
+        j = json.load(open(files[-1]))
+        return int(j['dram_bytes_read_per_launch']) + int(j['dram_bytes_write_per_launch'])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -205,13 +218,17 @@ def run_ours(args):
     sampler.start()
     stats = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev0.record()
-    for _ in range(args.steps):
+    step_evs[0].record()
+    for s_i in range(args.steps):
         d, i = step(stats)
+        step_evs[s_i + 1].record()
     ev1.record()
     barrier()
     sampler.stop_flag = True
     ms_total = ev0.elapsed_time(ev1)
+    ms_each = [step_evs[j].elapsed_time(step_evs[j + 1]) for j in range(args.steps)]
     t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -235,13 +252,14 @@ def run_ours(args):
     # dominant kernel: tcgen05 filter pass (per launch: one launch per step per rank)
     peaks = measured_peaks()
     filt_ms = float(np.mean([s['ms_filter'] for s in stats])) if stats else 0.0
-    n_filter_launch = stats[0]['n_chunks'] if stats else 1
+    n_filter_launch = max(1, stats[0].get('n_filter_launches') or stats[0]['n_chunks']) if stats else 1
     flops = 2.0 * n_loc * n * D_EMB                               # algorithmic: true D, no padding credit
     roofline = None
     if filt_ms > 0:
         ach = flops / n_filter_launch / (filt_ms / n_filter_launch * 1e-3) / 1e12
         roofline = {'bound': 'tensor', 'kernel': 'tc_kernel<FILTER>', 'achieved': ach, 'peak': peaks['tflops'],
-                    'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'],
+                    'traffic': filter_traffic() if (n == N_DEFAULT and world == 1) else None,
                     'peak_source': peaks['source'], 'ms_per_launch': filt_ms / n_filter_launch,
                     'algorithmic_flops_per_launch': flops / n_filter_launch}
     stage_ms = {key: float(np.mean([s[key] for s in stats])) for key in
@@ -250,7 +268,7 @@ def run_ours(args):
     if rank == 0:
         line = {
             'metric': 'kNN-graph contigs/sec', 'value': n / (ms_step * 1e-3), 'unit': 'contigs/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step,
+            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'ms_each_step_rank0': ms_each,
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f16 tensor-core filter + f64 rerank (exact result)', 'data': 'synthetic',
             'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
@@ -264,7 +282,7 @@ def run_ours(args):
             'gpu_launches': int(sum(s['n_launches'] for s in stats)),
             'roofline': roofline,
             'stages_ms': stage_ms,
-            'knn_stats': {kk: stats[-1][kk] for kk in ('algo_used', 'n_chunks', 'n_fallback_rows', 'n_candidates',
+            'knn_stats': {kk: stats[-1][kk] for kk in ('algo_used', 'n_chunks', 'n_filter_launches', 'n_fallback_rows', 'n_candidates',
                                                        'n_reranked', 'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
         }
         if world == 1 and not args.no_cpu_baseline:

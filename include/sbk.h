@@ -69,7 +69,7 @@ typedef struct sbk_knn_stats {
   int32_t order_stat;            /* which group-min order statistic set the threshold */
   int32_t kpad;                  /* padded K of the FP16 operands */
   int32_t n_launches;            /* kernels launched by this call */
-  int32_t reserved;
+  int32_t n_filter_launches;     /* launches of the tcgen05 filter kernel (one per L2-sized reference chunk and query chunk) */
   /* device time per stage, CUDA events on `cuda_stream`, summed over chunks (ms) */
   float ms_prepare;              /* centre/scale/FP16 staging */
   float ms_sample;               /* tcgen05 threshold pass over the reference sample */

@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (raw page) into the handful of counters DESIGN.md / bench.py quote.
+usage: scripts/ncu_summary.py gpurun_out/x.ncu-rep [more.ncu-rep ...] > profiles/x_summary.txt"""
+import csv, subprocess, sys, io
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg',
+        'sm__cycles_elapsed.avg', 'sm__cycles_elapsed.avg.per_second', 'sm__cycles_active.avg',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed.sum', 'smsp__inst_executed.avg.per_cycle_active', 'sm__inst_issued.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_shared_mem',
+        'launch__occupancy_limit_registers', 'launch__waves_per_multiprocessor',
+        'lts__t_sector_hit_rate.pct', 'lts__t_bytes.sum', 'lts__t_sectors_srcunit_tex.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_membar_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_drain_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_selected_per_issue_active.ratio',
+        'gpc__cycles_elapsed.max', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
+for rep in sys.argv[1:]:
+    out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        d = dict(zip(hdr, r))
+        print(f'== {rep} :: {d.get("Kernel Name", "?")[:100]}  grid={d.get("Grid Size")} block={d.get("Block Size")}')
+        for kname in KEYS:
+            if kname in d:
+                print(f'  {kname:95s} {d[kname]:>18s} {units[hdr.index(kname)]}')

@@ -20,7 +20,7 @@ class KnnStats(C.Structure):
                 ('n_fallback_rows', C.c_int64), ('n_candidates', C.c_int64),
                 ('sample_size', C.c_int32), ('cand_capacity', C.c_int32),
                 ('order_stat', C.c_int32), ('kpad', C.c_int32),
-                ('n_launches', C.c_int32), ('reserved', C.c_int32),
+                ('n_launches', C.c_int32), ('n_filter_launches', C.c_int32),
                 ('ms_prepare', C.c_float), ('ms_sample', C.c_float), ('ms_filter', C.c_float),
                 ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float),
                 ('n_reranked', C.c_int64), ('n_fail_overflow', C.c_int64), ('n_fail_few', C.c_int64),

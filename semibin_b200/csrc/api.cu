@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "knn.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -25,7 +26,7 @@ static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk 
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
 
 struct KnnWs {
-  uint32_t* cand_idx; float* cand_val; int32_t* cand_count; double* bound;
+  uint32_t* cand_idx; uint2* cand_pair; int32_t* cand_count; double* bound;   // exact path: columns; tensor path: (column, score)
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
   void* tc;                                             // tensor-path staging area
@@ -69,8 +70,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
 
 static void carve(Arena& a, const KnnShape& s, long long n_ref, int k, KnnWs& w) {
   const int k1 = k + 1;
-  w.cand_idx = a.take<uint32_t>((size_t)s.chunk * s.cand_stride);
-  w.cand_val = s.algo == SBK_KNN_TENSOR ? a.take<float>((size_t)s.chunk * s.cand_stride) : nullptr;
+  w.cand_idx = s.algo == SBK_KNN_TENSOR ? nullptr : a.take<uint32_t>((size_t)s.chunk * s.cand_stride);
+  w.cand_pair = s.algo == SBK_KNN_TENSOR ? a.take<uint2>((size_t)s.chunk * s.cand_stride) : nullptr;
   w.cand_count = a.take<int32_t>((size_t)s.chunk * 4);
   w.bound = a.take<double>((size_t)s.chunk);
   w.fail_rows = a.take<int32_t>((size_t)s.chunk + (size_t)s.fb_rows + 1);
@@ -198,7 +199,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
-                         nullptr, nullptr, 0.0, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 2;
       if (rc) return rc;
@@ -208,12 +209,17 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_filter);
-      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, w.cand_idx, w.cand_val, w.cand_count, stream);
+      int nfl = 0;
+      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, w.cand_pair, w.cand_count, &nfl, stream);
+      st.n_filter_launches += nfl; st.n_launches += nfl - 1;
+      if (getenv("SBK_TC_PROBE") && atoi(getenv("SBK_TC_PROBE")) > 0) {   // profiling aid: time the filter variants only
+        tm.end(h); SBK_CUDA_CHECK(cudaStreamSynchronize(stream)); st.n_chunks++; continue;
+      }
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
-      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, w.cand_val, s.cand_stride, 4, w.cand_count,
-                         w.bound, tcs.norms4, tc_c_acc(s.plan.kpad), k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+                         w.bound, tcs.nrm, tcs.norms4, tcs.scale, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 3;
       if (rc) return rc;
@@ -237,7 +243,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
         if (rc) return rc;
         // n_fail doubles as the (unused) failure sink of the fallback rerank
         rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
-                           w.fb_count, nullptr, nullptr, 0.0, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
+                           w.fb_count, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
         if (rc) return rc;
       }
       tm.end(hfb);

@@ -71,50 +71,56 @@ __device__ __forceinline__ void block_bitonic_sort(double* key, uint32_t* id, in
   __syncthreads();
 }
 
-// FP64 direct-difference squared distance between a query held in shared memory
-// (as double) and row j of X.
+// FP64 direct-difference squared distance between a query held in shared memory (as double)
+// and a row y of X, evaluated by a group of 8 consecutive lanes: lane `sub` (0..7) of the group
+// takes the 16-byte chunks sub, sub+8, ... of the row (one coalesced 128-byte request per
+// group and step) and the partial sums are combined by a fixed xor-shuffle tree, so the value
+// does not depend on the launch shape or on the alignment of the row (the unaligned path reads
+// the same columns with scalar loads).  All 32 lanes of the warp must call (shuffles); every
+// lane of a group returns the group's sum.
 template <typename T>
-__device__ __forceinline__ double sqdist_row(const double* __restrict__ q, const T* __restrict__ y, int d);
-
-template <>
-__device__ __forceinline__ double sqdist_row<float>(const double* __restrict__ q,
-                                                    const float* __restrict__ y, int d) {
-  // four independent accumulators (column c goes to accumulator c mod 4) so the FMA
-  // latency chain is 4x shorter; the final combination order is fixed -> deterministic
+__device__ __forceinline__ double sqdist_g8(const double* __restrict__ q, const T* __restrict__ y, int d, int sub) {
+  constexpr int V = 16 / (int)sizeof(T);             // columns per 16-byte chunk
+  const int nfull = d / V;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int c = 0;
   if ((((uintptr_t)y) & 15) == 0) {
-    const float4* y4 = reinterpret_cast<const float4*>(y);
 #pragma unroll 4
-    for (; c + 4 <= d; c += 4) {
-      float4 v = __ldg(y4 + (c >> 2));
-      double t0 = q[c] - (double)v.x, t1 = q[c + 1] - (double)v.y;
-      double t2 = q[c + 2] - (double)v.z, t3 = q[c + 3] - (double)v.w;
-      a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1);
-      a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
+    for (int ch = sub; ch < nfull; ch += 8) {
+      const int c = ch * V;
+      if (sizeof(T) == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(y) + ch);
+        const double t0 = q[c] - (double)v.x, t1 = q[c + 1] - (double)v.y;
+        const double t2 = q[c + 2] - (double)v.z, t3 = q[c + 3] - (double)v.w;
+        a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
+      } else {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(y) + ch);
+        const double t0 = q[c] - v.x, t1 = q[c + 1] - v.y;
+        if ((ch >> 3) & 1) { a2 = fma(t0, t0, a2); a3 = fma(t1, t1, a3); }
+        else { a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); }
+      }
+    }
+  } else {
+    for (int ch = sub; ch < nfull; ch += 8) {
+      const int c = ch * V;
+      if (sizeof(T) == 4) {
+        const double t0 = q[c] - (double)__ldg(y + c), t1 = q[c + 1] - (double)__ldg(y + c + 1);
+        const double t2 = q[c + 2] - (double)__ldg(y + c + 2), t3 = q[c + 3] - (double)__ldg(y + c + 3);
+        a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
+      } else {
+        const double t0 = q[c] - (double)__ldg(y + c), t1 = q[c + 1] - (double)__ldg(y + c + 1);
+        if ((ch >> 3) & 1) { a2 = fma(t0, t0, a2); a3 = fma(t1, t1, a3); }
+        else { a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); }
+      }
     }
   }
-  for (; c < d; ++c) { double t = q[c] - (double)__ldg(y + c); a0 = fma(t, t, a0); }
-  return (a0 + a1) + (a2 + a3);
-}
-
-template <>
-__device__ __forceinline__ double sqdist_row<double>(const double* __restrict__ q,
-                                                     const double* __restrict__ y, int d) {
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int c = 0;
-  if ((((uintptr_t)y) & 15) == 0) {
-    const double2* y2 = reinterpret_cast<const double2*>(y);
-#pragma unroll 4
-    for (; c + 4 <= d; c += 4) {
-      double2 v = __ldg(y2 + (c >> 1)), w = __ldg(y2 + (c >> 1) + 1);
-      double t0 = q[c] - v.x, t1 = q[c + 1] - v.y, t2 = q[c + 2] - w.x, t3 = q[c + 3] - w.y;
-      a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1);
-      a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
-    }
-  }
-  for (; c < d; ++c) { double t = q[c] - __ldg(y + c); a0 = fma(t, t, a0); }
-  return (a0 + a1) + (a2 + a3);
+  // tail columns (d not a multiple of the chunk width): column nfull*V + t goes to lane t
+  const int ct = nfull * V + sub;
+  if (sub < V && ct < d) { const double t = q[ct] - (double)__ldg(y + ct); a0 = fma(t, t, a0); }
+  double s = (a0 + a1) + (a2 + a3);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
 }
 
 }  // namespace sbk

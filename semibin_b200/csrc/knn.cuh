@@ -13,8 +13,9 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
                         cudaStream_t stream);
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
-                  const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
-                  const int32_t* cand_count, const double* bound, const float4* norms4, double c_acc, int k,
+                  const uint32_t* cand_idx, const uint2* cand_pair, long long cand_stride, int n_seg,
+                  const int32_t* cand_count, const double* bound, const double* nrm, const float4* norms4,
+                  const double* scale, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream);
@@ -67,7 +68,7 @@ struct TcState {
   double* centre; double* colsum; double* scale; double* nrm;
   float4* norms4; TcScalars* sc; int32_t* sample_rows; float* thr;
   unsigned long long* maxabs;
-  int nstage; long long n_ref; int d;
+  int nstage; int cg; long long n_ref; int d;   // cg: CTAs per MMA (tcgen05 cta_group)
 };
 
 TcPlan tc_make_plan(long long n_ref, int d, int k);
@@ -80,10 +81,10 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
                     cudaStream_t stream);
-// Filter pass over all references: fills 4 segments of cand_cap/4 per slot (cand_idx / cand_val),
+// Filter pass over all references: fills 4 segments of cand_cap/4 (column, score) pairs per slot,
 // cand_count[slot*4 + segment].
 int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
-                    uint32_t* cand_idx, float* cand_val, int32_t* cand_count, cudaStream_t stream);
+                    uint2* cand, int32_t* cand_count, int* n_launches, cudaStream_t stream);
 int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
 int tc_debug_norms(TcState* st, const TcPlan& p, long long n, float* norms4_out, double* nrm_out, int32_t* info,
                    cudaStream_t stream);

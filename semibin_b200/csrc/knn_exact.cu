@@ -184,13 +184,31 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
+// exact d2 of survivors id[lo..hi) -> key[lo..hi); 8 lanes per survivor (sqdist_g8)
+template <typename T>
+__device__ __forceinline__ void rr_distances(const T* __restrict__ X, long long ld, int d, const double* q,
+                                             const uint32_t* id, double* key, int lo, int hi, int tid) {
+  const int sub = tid & 7;
+  for (int c0 = lo; c0 < hi; c0 += RR_THREADS / 8) {       // warp-uniform trip count (shuffles inside)
+    const int c = c0 + (tid >> 3);
+    const bool ok = c < hi;
+    const uint32_t jj = ok ? id[c] : id[lo];
+    const double v = sqdist_g8<T>(q, X + (long long)jj * ld, d, sub);
+    if (ok && sub == 0) key[c] = v;
+  }
+}
+
 // One CTA per candidate slot.
 //   rows       : global row id per slot (NULL -> q_begin + slot)
 //   cand_idx   : [slot][n_seg][seg_cap] candidate columns, cand_count[slot*n_seg+seg] valid per segment
-//   cand_val   : tensor-core LOWER bounds L_ij of the candidates' exact scores (NULL on the exact path)
-//   norms4     : per-row norms of the per-pair error model (knn.cuh); U_ij = L_ij + slack_ij is an upper
-//                bound of the exact score, so the (k+1)-th smallest U bounds the (k+1)-th smallest exact
-//                score from above and candidates with L_ij above it cannot be among the k+1 nearest
+//   cand_pair  : (column, tensor-core LOWER bound) pairs, same segmentation (tensor path; else NULL):
+//                lower bounds L_ij <= S^2 d2_ij - nrm_i + sigma_i of the candidates (NULL on
+//                the exact path, where every candidate is evaluated).  Tensor path, two phases:
+//                  1. T = the candidates with the k+1 smallest L (radix select); exact FP64 d2 of T;
+//                     dmax = max d2 over T  >=  the (k+1)-th smallest exact d2 of the row
+//                  2. a candidate outside T can only matter if its lower bound allows d2 <= dmax, i.e.
+//                     L_ij <= S^2 dmax - nrm_i + sigma_i; those are evaluated too, the rest are dropped
+//   nrm / norms4 / scale : exact ||z_i||^2, (.., .., .., sigma_i) and S of the staging (tensor path)
 //   bound      : per slot, every reference NOT in the candidate list is known to have d2 > bound
 //                (NULL -> +inf, i.e. the list is a guaranteed superset)
 //   fail_rows / n_fail : rows whose certificate failed are appended here (output left untouched)
@@ -198,9 +216,10 @@ template <typename T, typename OutT>
 __global__ void __launch_bounds__(RR_THREADS)
 rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ rows, long long q_begin,
-              const uint32_t* __restrict__ cand_idx, const float* __restrict__ cand_val,
+              const uint32_t* __restrict__ cand_idx, const uint2* __restrict__ cand_pair,
               long long cand_stride, int n_seg, const int32_t* __restrict__ cand_count,
-              const double* __restrict__ bound, const float4* __restrict__ norms4, double c_acc,
+              const double* __restrict__ bound, const double* __restrict__ nrm,
+              const float4* __restrict__ norms4, const double* __restrict__ scale,
               int k, int ncand_cap, int pmax,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
@@ -211,10 +230,10 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   uint32_t* id = reinterpret_cast<uint32_t*>(key + pmax);    // [pmax]  survivors: column
   uint32_t* cid = id + pmax;                                 // [ncand_cap]  all candidates (tensor path only)
   float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]  lower bounds L
-  float* uval = cval + ncand_cap;                            // [ncand_cap]  upper bounds U
   __shared__ uint32_t hist[256];
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ int s_drop, s_m;
+  __shared__ unsigned long long s_dmax;
 
   const int tid = threadIdx.x;
   const long long slot = blockIdx.x;
@@ -244,36 +263,31 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     return;
   }
   for (int c = tid; c < d; c += RR_THREADS) q[c] = (double)X[row * ld + c];
-  if (tid == 0) { s_drop = -1; s_m = 0; }
-  uint32_t* cdst = cand_val ? cid : id;          // exact path: candidates ARE the survivors
+  if (tid == 0) { s_drop = -1; s_m = 0; s_dmax = 0ull; }
 #pragma unroll
   for (int sgm = 0; sgm < 4; ++sgm) {
-    const uint32_t* ci = cand_idx + slot * cand_stride + (long long)sgm * seg_cap;
-    const float* cv = cand_val ? cand_val + slot * cand_stride + (long long)sgm * seg_cap : nullptr;
-    for (int c = tid; c < seg_n[sgm]; c += RR_THREADS) {
-      cdst[seg_off[sgm] + c] = ci[c];
-      if (cv) cval[seg_off[sgm] + c] = cv[c];
+    if (cand_pair) {
+      const uint2* cp = cand_pair + slot * cand_stride + (long long)sgm * seg_cap;
+      for (int c = tid; c < seg_n[sgm]; c += RR_THREADS) {
+        const uint2 e = cp[c];
+        cid[seg_off[sgm] + c] = e.x; cval[seg_off[sgm] + c] = __uint_as_float(e.y);
+      }
+    } else {                                     // exact path: candidates ARE the survivors
+      const uint32_t* ci = cand_idx + slot * cand_stride + (long long)sgm * seg_cap;
+      for (int c = tid; c < seg_n[sgm]; c += RR_THREADS) id[seg_off[sgm] + c] = ci[c];
     }
   }
   __syncthreads();
 
   int m;
-  if (cand_val) {
-    // ---- upper bounds, (k+1)-th smallest of them by 4-pass radix select, then the cut ----
-    {
-      const float4 ni = norms4[row];
-      for (int c = tid; c < n; c += RR_THREADS) {
-        const float4 nj = norms4[cid[c]];
-        uval[c] = __double2float_ru((double)cval[c] + tc_pair_upper_slack(ni, nj, c_acc));
-      }
-    }
-    __syncthreads();
+  if (cand_pair) {
+    // ---- phase 1: (k+1)-th smallest lower bound by 4-pass radix select ----
     uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k1;
     for (int shift = 24; shift >= 0; shift -= 8) {
       hist[tid] = 0;
       __syncthreads();
       for (int c = tid; c < n; c += RR_THREADS) {
-        const uint32_t u = f2ord(uval[c]);
+        const uint32_t u = f2ord(cval[c]);
         if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
       }
       __syncthreads();
@@ -303,33 +317,62 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       __syncthreads();
       prefix = s_prefix; remaining = s_remaining; mask |= 0xffu << shift;
     }
-    const float cut = ord2f(prefix);             // >= the (k+1)-th smallest exact score
+    const uint32_t kth_ord = prefix;             // ordered bits of the (k+1)-th smallest L
     for (int c = tid; c < n; c += RR_THREADS) {
-      if (cval[c] <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
+      if (f2ord(cval[c]) <= kth_ord) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
     }
     __syncthreads();
-    m = s_m;
-    if (m > pmax) {                              // more survivors than the sort buffer: exact filter takes the row
+    const int m1 = s_m;                          // >= k+1 (more only on equal lower bounds)
+    if (m1 > pmax) {                             // more survivors than the sort buffer: exact filter takes the row
       if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
       return;
     }
+    rr_distances<T>(X, ld, d, q, id, key, 0, m1, tid);
+    __syncthreads();
+    {
+      unsigned long long mx = 0ull;              // d2 >= 0: the bit pattern is monotone
+      for (int c = tid; c < m1; c += RR_THREADS) mx = max(mx, (unsigned long long)__double_as_longlong(key[c]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if ((tid & 31) == 0) atomicMax(&s_dmax, mx);
+    }
+    __syncthreads();
+    // ---- phase 2: candidates whose lower bound does not exclude d2 <= dmax ----
+    {
+      const double S = scale[0];
+      const double dmax = __longlong_as_double((long long)s_dmax);
+      // L_ij <= S^2 d2_ij - nrm_i + sigma_i; the inflation covers the rounding of dmax and of this expression
+      const double cut = S * S * dmax * (1.0 + 1e-12) - nrm[row] * (1.0 - 1e-12) + (double)norms4[row].w + 1e-300;
+      for (int c = tid; c < n; c += RR_THREADS) {
+        const float l = cval[c];
+        if (f2ord(l) > kth_ord && (double)l <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
+      }
+    }
+    __syncthreads();
+    m = s_m;
+    if (m > pmax) {
+      if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
+      return;
+    }
+    rr_distances<T>(X, ld, d, q, id, key, m1, m, tid);
   } else {
     m = n;
+    // ---- exact path: FP64 distances of every candidate (padding entries 0xffffffff stay +inf) ----
+    const int sub = tid & 7;
+    for (int c0 = 0; c0 < m; c0 += RR_THREADS / 8) {
+      const int c = c0 + (tid >> 3);
+      const bool ok = c < m;
+      const uint32_t jj = ok ? id[c] : 0xffffffffu;
+      const bool real = jj != 0xffffffffu;
+      const double v = sqdist_g8<T>(q, X + (long long)(real ? jj : 0u) * ld, d, sub);
+      if (ok && sub == 0) key[c] = real ? v : INF;
+    }
   }
   if (tid == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
 
-  // ---- exact FP64 distances of the survivors ----
   int P = (int)pow2ceil((uint32_t)m);
   if (P < 2) P = 2;
-  for (int c = tid; c < P; c += RR_THREADS) {
-    double kk = INF; uint32_t jj = 0xffffffffu;
-    if (c < m) {
-      jj = id[c];
-      if (jj != 0xffffffffu) kk = sqdist_row<T>(q, X + (long long)jj * ld, d);
-    }
-    key[c] = kk;
-    if (c >= m) id[c] = jj;
-  }
+  for (int c = m + tid; c < P; c += RR_THREADS) { key[c] = INF; id[c] = 0xffffffffu; }
   block_bitonic_sort<RR_THREADS>(key, id, P, tid);
   // certificate: the (k+1)-th smallest exact d2 must be strictly below every
   // excluded reference's lower bound
@@ -361,22 +404,23 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
 }
 
 size_t rerank_smem(int d, int pmax, int ncand_cap) {
-  return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 12 + 16;
+  return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 8 + 16;
 }
 
 int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld,
                   const int32_t* rows, long long q_begin, long long n_slots,
-                  const uint32_t* cand_idx, const float* cand_val, long long cand_stride, int n_seg,
-                  const int32_t* cand_count, const double* bound, const float4* norms4, double c_acc, int k,
+                  const uint32_t* cand_idx, const uint2* cand_pair, long long cand_stride, int n_seg,
+                  const int32_t* cand_count, const double* bound, const double* nrm, const float4* norms4,
+                  const double* scale, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream) {
   if (n_slots <= 0) return SBK_OK;
-  // tensor path: all candidates staged (ncand_cap), survivors of the score cut sorted in a
+  // tensor path: all candidates staged (ncand_cap), survivors of the two-phase cut sorted in a
   // buffer of pmax entries; exact path: every candidate is a survivor
-  int ncand_cap = cand_val ? (int)cand_stride : 0;
+  int ncand_cap = cand_pair ? (int)cand_stride : 0;
   int pmax = (int)pow2ceil((uint32_t)cand_stride);
-  if (cand_val) pmax = std::min(pmax, std::max(1024, (int)pow2ceil((uint32_t)(2 * (k + 1)))));
+  if (cand_pair) pmax = std::min(pmax, std::max(1024, (int)pow2ceil((uint32_t)(2 * (k + 1)))));
   size_t smem = rerank_smem(d, pmax, ncand_cap);
   if (smem > 227 * 1024) { set_error("rerank: candidate capacity %lld too large", cand_stride); return SBK_ERR_INVALID; }
   if (n_seg < 1 || n_seg > 4 || cand_stride % n_seg) { set_error("rerank: bad segmentation"); return SBK_ERR_INVALID; }
@@ -384,12 +428,12 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
   if (dtype == SBK_F32) {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<float, float><<<grid, RR_THREADS, smem, stream>>>(
-        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, norms4, c_acc,
+        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale,
         k, ncand_cap, pmax, (float*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   } else {
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rerank_kernel<double, double><<<grid, RR_THREADS, smem, stream>>>(
-        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_val, cand_stride, n_seg, cand_count, bound, norms4, c_acc,
+        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale,
         k, ncand_cap, pmax, (double*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
   }
   SBK_LAUNCH_CHECK();
