@@ -20,7 +20,6 @@ import argparse
 import json
 import os
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -71,49 +70,63 @@ def measured_peaks():
     return dict(tflops=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)')
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs: the `nvidia-smi -lms 200`
+    line of B200_PROFILING.md as a child process (an in-process NVML poller can hold driver locks the CUDA
+    launches of this process need; a 50 ms pynvml thread cost an occasional 100+ ms stall in one step)."""
+    FIELDS = ('clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
+        self.proc = None
         self.stop_flag = False
-        self.samples = []
-        self.max_mhz = None
-        self.reasons = set()
         self.err = None
+        self.lines = []
 
-    def run(self):
+    def start(self):
+        import subprocess
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8): 'hw_slowdown',
-                getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40): 'hw_thermal_slowdown',
-                getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20): 'sw_thermal_slowdown',
-                getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4): 'sw_power_cap',
-            }
-            while not self.stop_flag:
-                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                util = nv.nvmlDeviceGetUtilizationRates(h).gpu
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((mhz, util))
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.05)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
+    def join(self, timeout=None):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+            self.lines = [ln for ln in out.splitlines() if ln.strip()]
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+
     def summary(self):
-        loaded = [m for m, u in self.samples if u >= 50] or [m for m, _ in self.samples]
+        samples, reasons, max_mhz = [], set(), None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                samples.append((float(f[0]), float(f[2])))
+                max_mhz = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        loaded = [m for m, u in samples if u >= 50] or [m for m, _ in samples]
         med = float(np.median(loaded)) if loaded else None
-        out = {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+        out = {'sm_mhz': med, 'sm_max_mhz': max_mhz, 'reasons': sorted(reasons), 'samples': len(samples),
+               'how': 'nvidia-smi -lms 200 child process during the timed steps'}
         if self.err:
             out['error'] = self.err
         return out
@@ -171,7 +184,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from semibin_b200 import _lib
-    from semibin_b200.neighbors import knn
+    from semibin_b200.neighbors import knn, knn_host
     from semibin_b200 import dist as sdist
 
     rank = env_int('RANK', 0)
@@ -200,10 +213,8 @@ def run_ours(args):
         return d, i
 
     def step_e2e():
-        Xd = X_host.cuda(non_blocking=True)                       # H2D of this step's input
-        d, i = knn(Xd, k, q_begin=lo, q_end=hi, algo=args.algo)
-        out_d_host.copy_(d, non_blocking=True)                    # D2H of this step's result
-        out_i_host.copy_(i, non_blocking=True)
+        # H2D of this step's input, the build, D2H of this step's result: all inside the public host-buffer call
+        knn_host(X_host, k, q_begin=lo, q_end=hi, out_dist=out_d_host, out_idx=out_i_host, algo=args.algo)
         torch.cuda.synchronize()
 
     def barrier():
@@ -226,7 +237,7 @@ def run_ours(args):
         step_evs[s_i + 1].record()
     ev1.record()
     barrier()
-    sampler.stop_flag = True
+    sampler.join()
     ms_total = ev0.elapsed_time(ev1)
     ms_each = [step_evs[j].elapsed_time(step_evs[j + 1]) for j in range(args.steps)]
     t = torch.tensor([ms_total], dtype=torch.float64, device='cuda')
@@ -247,7 +258,6 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te.item())
-    sampler.join(timeout=2)
 
     # dominant kernel: tcgen05 filter pass (per launch: one launch per step per rank)
     peaks = measured_peaks()
@@ -278,7 +288,7 @@ def run_ours(args):
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
                     'h2d_bytes_per_step': int(X_host.numel() * 4),
                     'd2h_bytes_per_step': int(out_d_host.numel() * 4 + out_i_host.numel() * 4),
-                    'api': 'semibin_b200.neighbors.knn on a pinned host embedding, (dist f32, idx i32) row block copied back to pinned host memory'},
+                    'api': 'semibin_b200.neighbors.knn_host: pinned host embedding in, (dist f32, idx i32) row block out in pinned host memory; row blocks downloaded while the next block is computed'},
             'gpu_launches': int(sum(s['n_launches'] for s in stats)),
             'roofline': roofline,
             'stages_ms': stage_ms,

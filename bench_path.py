@@ -118,6 +118,35 @@ def long_read(n, S, k=200, cpu_check=False):
     return res
 
 
+def scaling_case(n, k=200, check_rows=512):
+    """C5: kNN graph of N=4M embeddings (several query chunks per call), sampled-row parity against
+    live scikit-learn on the host."""
+    import torch
+    from semibin_b200 import synth
+    from semibin_b200.neighbors import knn
+    X = synth.embeddings(n, seed=20245)
+    Xd = torch.from_numpy(X).cuda()
+    res = dict(n=n, k=k, d=int(X.shape[1]))
+    (dist, idx, st), res['knn_first_ms'] = timed(lambda: knn(Xd, k, return_stats=True))
+    (dist, idx, st), res['knn_ms'] = timed(lambda: knn(Xd, k, return_stats=True))
+    res['contigs_per_s'] = n / (res['knn_ms'] * 1e-3)
+    res['filter_tflops_true_d'] = 2.0 * n * n * X.shape[1] / (st['ms_filter'] * 1e-3) / 1e12
+    res['stats'] = {k2: st[k2] for k2 in ('n_chunks', 'n_filter_launches', 'n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_prepare',
+                                          'ms_filter', 'ms_rerank', 'ms_sample', 'ms_fallback', 'kpad', 'cand_capacity',
+                                          'order_stat', 'sample_size')}
+    if check_rows:
+        from oracle import knn as ok, compare
+        rng = np.random.default_rng(5)
+        lo = int(rng.integers(0, n - check_rows))
+        t0 = time.perf_counter()
+        rd, ri = ok.knn_sklearn(X, k, q_begin=lo, q_end=lo + check_rows)
+        res['cpu_rows_per_s'] = check_rows / (time.perf_counter() - t0)
+        r = compare.compare_knn(rd, ri, dist[lo:lo + check_rows].cpu().numpy().astype(np.float64),
+                                idx[lo:lo + check_rows].cpu().numpy().astype(np.int64), rtol=1e-5)
+        res['parity'] = {kk: r[kk] for kk in ('n_rows_bad', 'n_rows_tied')}
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', default='C2')
@@ -131,6 +160,8 @@ def main():
         r = short_read(a.n or 1000000, 10, a.combined, cpu_check=a.cpu_check)
     elif a.config == 'C4':
         r = long_read(a.n or 500000, 1, cpu_check=a.cpu_check)
+    elif a.config == 'C5':
+        r = scaling_case(a.n or 4000000)
     else:
         raise SystemExit('unknown config')
     r['config'] = a.config

@@ -123,4 +123,81 @@ __device__ __forceinline__ double sqdist_g8(const double* __restrict__ q, const 
   return s;
 }
 
+// Register-resident query row for the common narrow case: a group of LPC consecutive lanes evaluates one
+// candidate row, lane `sub` owning the 16-byte chunks sub, sub+LPC, ... (NCH of them at most) of every row.
+// The lane's slice of the query lives in registers as double, so the inner loop is one 16-byte global
+// load per chunk and FP64 arithmetic -- no shared-memory traffic (the load/store pipe was the busiest unit
+// of the rerank when the query sat in shared memory).  Fixed xor-shuffle tree -> deterministic.
+template <typename T> struct DistCfg;
+template <> struct DistCfg<float>  { static constexpr int LPC = 8,  NCH = 4, V = 4; };   // d <= 128
+template <> struct DistCfg<double> { static constexpr int LPC = 16, NCH = 5, V = 2; };   // d <= 160
+
+template <typename T>
+struct RegQuery {
+  using C = DistCfg<T>;
+  static constexpr int MAX_D = C::LPC * C::NCH * C::V;
+  double q[C::NCH * C::V];
+  double qt;
+  int nfull, d;
+  bool vec;
+
+  __device__ __forceinline__ void load(const T* __restrict__ x, int d_, int sub, bool vec_ok) {
+    d = d_; nfull = d_ / C::V; vec = vec_ok;
+#pragma unroll
+    for (int j = 0; j < C::NCH; ++j) {
+      const int ch = sub + C::LPC * j;
+#pragma unroll
+      for (int e = 0; e < C::V; ++e) q[j * C::V + e] = ch < nfull ? (double)x[ch * C::V + e] : 0.0;
+    }
+    const int ct = nfull * C::V + sub;
+    qt = (sub < C::V && ct < d_) ? (double)x[ct] : 0.0;
+  }
+
+  // all 32 lanes call; every lane of a group returns the group's squared distance
+  __device__ __forceinline__ double eval(const T* __restrict__ y, int sub) const {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (sizeof(T) == 4) {
+      float4 v[C::NCH];
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {
+        const int ch = sub + C::LPC * j;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ch < nfull) {
+          if (vec) v[j] = __ldg(reinterpret_cast<const float4*>(y) + ch);
+          else v[j] = make_float4((float)__ldg(y + ch * 4), (float)__ldg(y + ch * 4 + 1), (float)__ldg(y + ch * 4 + 2), (float)__ldg(y + ch * 4 + 3));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {      // inactive chunks hold zeros on both sides
+        const double t0 = q[4 * j] - (double)v[j].x, t1 = q[4 * j + 1] - (double)v[j].y;
+        const double t2 = q[4 * j + 2] - (double)v[j].z, t3 = q[4 * j + 3] - (double)v[j].w;
+        a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
+      }
+    } else {
+      double2 v[C::NCH];
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {
+        const int ch = sub + C::LPC * j;
+        v[j] = make_double2(0.0, 0.0);
+        if (ch < nfull) {
+          if (vec) v[j] = __ldg(reinterpret_cast<const double2*>(y) + ch);
+          else v[j] = make_double2((double)__ldg(y + ch * 2), (double)__ldg(y + ch * 2 + 1));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {
+        const double t0 = q[2 * j] - v[j].x, t1 = q[2 * j + 1] - v[j].y;
+        if (j & 1) { a2 = fma(t0, t0, a2); a3 = fma(t1, t1, a3); }
+        else { a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); }
+      }
+    }
+    const int ct = nfull * C::V + sub;
+    if (sub < C::V && ct < d) { const double t = qt - (double)__ldg(y + ct); a0 = fma(t, t, a0); }
+    double s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = C::LPC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  }
+};
+
 }  // namespace sbk

@@ -184,17 +184,23 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
 }
 
-// exact d2 of survivors id[lo..hi) -> key[lo..hi); 8 lanes per survivor (sqdist_g8)
-template <typename T>
+// exact d2 of survivors id[lo..hi) -> key[lo..hi).  REGQ: LPC lanes per survivor, query slice in registers
+// (RegQuery); otherwise 8 lanes per survivor, query in shared memory (sqdist_g8).  Entries 0xffffffff
+// (padding of the exact path) get +inf.
+template <typename T, bool REGQ>
 __device__ __forceinline__ void rr_distances(const T* __restrict__ X, long long ld, int d, const double* q,
-                                             const uint32_t* id, double* key, int lo, int hi, int tid) {
-  const int sub = tid & 7;
-  for (int c0 = lo; c0 < hi; c0 += RR_THREADS / 8) {       // warp-uniform trip count (shuffles inside)
-    const int c = c0 + (tid >> 3);
+                                             const RegQuery<T>& rq, const uint32_t* id, double* key, int lo, int hi, int tid) {
+  constexpr int LPC = REGQ ? DistCfg<T>::LPC : 8;
+  const int sub = tid & (LPC - 1);
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  for (int c0 = lo; c0 < hi; c0 += RR_THREADS / LPC) {     // warp-uniform trip count (shuffles inside)
+    const int c = c0 + tid / LPC;
     const bool ok = c < hi;
-    const uint32_t jj = ok ? id[c] : id[lo];
-    const double v = sqdist_g8<T>(q, X + (long long)jj * ld, d, sub);
-    if (ok && sub == 0) key[c] = v;
+    const uint32_t jj = ok ? id[c] : 0xffffffffu;
+    const bool real = jj != 0xffffffffu;
+    const T* y = X + (long long)(real ? jj : 0u) * ld;
+    const double v = REGQ ? rq.eval(y, sub) : sqdist_g8<T>(q, y, d, sub);
+    if (ok && sub == 0) key[c] = real ? v : INF;
   }
 }
 
@@ -212,8 +218,8 @@ __device__ __forceinline__ void rr_distances(const T* __restrict__ X, long long 
 //   bound      : per slot, every reference NOT in the candidate list is known to have d2 > bound
 //                (NULL -> +inf, i.e. the list is a guaranteed superset)
 //   fail_rows / n_fail : rows whose certificate failed are appended here (output left untouched)
-template <typename T, typename OutT>
-__global__ void __launch_bounds__(RR_THREADS)
+template <typename T, typename OutT, bool REGQ>
+__global__ void __launch_bounds__(RR_THREADS, REGQ ? 3 : 2)
 rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ rows, long long q_begin,
               const uint32_t* __restrict__ cand_idx, const uint2* __restrict__ cand_pair,
@@ -230,9 +236,9 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   uint32_t* id = reinterpret_cast<uint32_t*>(key + pmax);    // [pmax]  survivors: column
   uint32_t* cid = id + pmax;                                 // [ncand_cap]  all candidates (tensor path only)
   float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]  lower bounds L
-  __shared__ uint32_t hist[256];
+  __shared__ uint32_t hist[512];
   __shared__ uint32_t s_prefix, s_remaining;
-  __shared__ int s_drop, s_m;
+  __shared__ int s_drop, s_m, s_m2;
   __shared__ unsigned long long s_dmax;
 
   const int tid = threadIdx.x;
@@ -262,8 +268,14 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     }
     return;
   }
-  for (int c = tid; c < d; c += RR_THREADS) q[c] = (double)X[row * ld + c];
-  if (tid == 0) { s_drop = -1; s_m = 0; s_dmax = 0ull; }
+  RegQuery<T> rq;
+  if (REGQ) {
+    const bool vec_ok = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)sizeof(T)) & 15) == 0);
+    rq.load(X + row * ld, d, tid & (DistCfg<T>::LPC - 1), vec_ok);
+  } else {
+    for (int c = tid; c < d; c += RR_THREADS) q[c] = (double)X[row * ld + c];
+  }
+  if (tid == 0) { s_drop = -1; s_m = 0; s_m2 = 0; s_dmax = 0ull; }
 #pragma unroll
   for (int sgm = 0; sgm < 4; ++sgm) {
     if (cand_pair) {
@@ -277,24 +289,26 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       for (int c = tid; c < seg_n[sgm]; c += RR_THREADS) id[seg_off[sgm] + c] = ci[c];
     }
   }
+  hist[tid] = 0; hist[256 + tid] = 0;            // radix-select histograms (zeroed before the barrier below)
   __syncthreads();
 
   int m;
   if (cand_pair) {
-    // ---- phase 1: (k+1)-th smallest lower bound by 4-pass radix select ----
+    // ---- phase 1: the k+1 smallest lower bounds by radix select on the top 24 bits of the ordered float
+    // (three 8-bit passes, two alternating histograms -> two barriers per pass).  Candidates that agree with
+    // the (k+1)-th in those 24 bits are all taken: any superset of the k+1 smallest is a valid T.
     uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k1;
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      hist[tid] = 0;
-      __syncthreads();
+    for (int shift = 24; shift >= 8; shift -= 8) {
+      uint32_t* h = hist + ((shift >> 3) & 1) * 256;
       for (int c = tid; c < n; c += RR_THREADS) {
         const uint32_t u = f2ord(cval[c]);
-        if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        if ((u & mask) == prefix) atomicAdd(&h[(u >> shift) & 255u], 1u);
       }
       __syncthreads();
       if (tid < 32) {
         uint32_t loc[8], sum = 0;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) { loc[b] = hist[tid * 8 + b]; sum += loc[b]; }
+        for (int b = 0; b < 8; ++b) { loc[b] = h[tid * 8 + b]; sum += loc[b]; }
         uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -316,8 +330,9 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       }
       __syncthreads();
       prefix = s_prefix; remaining = s_remaining; mask |= 0xffu << shift;
+      h[tid] = 0;                                // reused two passes later, after two more barriers
     }
-    const uint32_t kth_ord = prefix;             // ordered bits of the (k+1)-th smallest L
+    const uint32_t kth_ord = prefix | 0xffu;     // every candidate sharing the (k+1)-th's top 24 bits is in T
     for (int c = tid; c < n; c += RR_THREADS) {
       if (f2ord(cval[c]) <= kth_ord) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
     }
@@ -327,7 +342,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
       return;
     }
-    rr_distances<T>(X, ld, d, q, id, key, 0, m1, tid);
+    rr_distances<T, REGQ>(X, ld, d, q, rq, id, key, 0, m1, tid);
     __syncthreads();
     {
       unsigned long long mx = 0ull;              // d2 >= 0: the bit pattern is monotone
@@ -354,26 +369,72 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
       return;
     }
-    rr_distances<T>(X, ld, d, q, id, key, m1, m, tid);
+    rr_distances<T, REGQ>(X, ld, d, q, rq, id, key, m1, m, tid);
+    __syncthreads();
+    // T alone holds k+1 rows within dmax, so a phase-2 survivor farther than dmax cannot be among the k+1
+    // nearest: compact [m1, m) down to those within dmax (keeps the sort at 256 entries for almost every row)
+    {
+      double kk[4]; uint32_t ii[4]; int nk = 0;
+      const double dmax = __longlong_as_double((long long)s_dmax);
+      for (int c = m1 + tid; c < m; c += RR_THREADS) {
+        const double v = key[c];
+        if (v <= dmax && nk < 4) { kk[nk] = v; ii[nk] = id[c]; ++nk; }
+      }
+      __syncthreads();
+      if (nk) {
+        const int p0 = atomicAdd(&s_m2, nk);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (u < nk) { key[m1 + p0 + u] = kk[u]; id[m1 + p0 + u] = ii[u]; }
+      }
+      __syncthreads();
+      m = m1 + s_m2;
+    }
   } else {
     m = n;
     // ---- exact path: FP64 distances of every candidate (padding entries 0xffffffff stay +inf) ----
-    const int sub = tid & 7;
-    for (int c0 = 0; c0 < m; c0 += RR_THREADS / 8) {
-      const int c = c0 + (tid >> 3);
-      const bool ok = c < m;
-      const uint32_t jj = ok ? id[c] : 0xffffffffu;
-      const bool real = jj != 0xffffffffu;
-      const double v = sqdist_g8<T>(q, X + (long long)(real ? jj : 0u) * ld, d, sub);
-      if (ok && sub == 0) key[c] = real ? v : INF;
-    }
+    rr_distances<T, REGQ>(X, ld, d, q, rq, id, key, 0, m, tid);
   }
   if (tid == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
 
-  int P = (int)pow2ceil((uint32_t)m);
-  if (P < 2) P = 2;
-  for (int c = m + tid; c < P; c += RR_THREADS) { key[c] = INF; id[c] = 0xffffffffu; }
-  block_bitonic_sort<RR_THREADS>(key, id, P, tid);
+  if (m <= 2 * RR_THREADS) {
+    // ---- rank sort: every thread counts how many survivors precede its own in (d2, index) order and drops
+    // its pair at that position.  O(m^2 / threads) broadcast reads but only two block barriers, against the
+    // ~40 of a bitonic network (the rerank is barrier- and latency-bound, not issue-bound).  Only the first
+    // k+1 positions are needed; (d2, index) pairs are distinct, +inf padding of the exact path ranks last.
+    __syncthreads();
+    double kt[2]; uint32_t it[2]; int rk[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = tid + u * RR_THREADS;
+      rk[u] = -1;
+      if (c < m) { kt[u] = key[c]; it[u] = id[c]; rk[u] = 0; }
+    }
+    if (rk[0] == 0) {
+      if (rk[1] == 0) {
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+          const double kj = key[j]; const uint32_t ij = id[j];
+          rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
+          rk[1] += (kj < kt[1] || (kj == kt[1] && ij < it[1])) ? 1 : 0;
+        }
+      } else {
+#pragma unroll 4
+        for (int j = 0; j < m; ++j) {
+          const double kj = key[j]; const uint32_t ij = id[j];
+          rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (rk[u] >= 0 && rk[u] < k1) { key[rk[u]] = kt[u]; id[rk[u]] = it[u]; }
+    __syncthreads();
+  } else {
+    int P = (int)pow2ceil((uint32_t)m);
+    for (int c = m + tid; c < P; c += RR_THREADS) { key[c] = INF; id[c] = 0xffffffffu; }
+    block_bitonic_sort<RR_THREADS>(key, id, P, tid);
+  }
   // certificate: the (k+1)-th smallest exact d2 must be strictly below every
   // excluded reference's lower bound
   const double kth = (m >= k1) ? key[k] : INF;
@@ -425,17 +486,19 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
   if (smem > 227 * 1024) { set_error("rerank: candidate capacity %lld too large", cand_stride); return SBK_ERR_INVALID; }
   if (n_seg < 1 || n_seg > 4 || cand_stride % n_seg) { set_error("rerank: bad segmentation"); return SBK_ERR_INVALID; }
   dim3 grid((unsigned)n_slots);
+#define SBK_RR_LAUNCH(T, REGQ)                                                                                          \
+  do {                                                                                                                  \
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T, T, REGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    rerank_kernel<T, T, REGQ><<<grid, RR_THREADS, smem, stream>>>(                                                      \
+        (const T*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale, \
+        k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);                                \
+  } while (0)
   if (dtype == SBK_F32) {
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rerank_kernel<float, float><<<grid, RR_THREADS, smem, stream>>>(
-        (const float*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale,
-        k, ncand_cap, pmax, (float*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
+    if (d <= RegQuery<float>::MAX_D) SBK_RR_LAUNCH(float, true); else SBK_RR_LAUNCH(float, false);
   } else {
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<double, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rerank_kernel<double, double><<<grid, RR_THREADS, smem, stream>>>(
-        (const double*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale,
-        k, ncand_cap, pmax, (double*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);
+    if (d <= RegQuery<double>::MAX_D) SBK_RR_LAUNCH(double, true); else SBK_RR_LAUNCH(double, false);
   }
+#undef SBK_RR_LAUNCH
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }

@@ -89,6 +89,57 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
     return out_d, out_i
 
 
+def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=2, algo='auto'):
+    """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
+    host tensors (pinned ones are allocated when none are passed).  The query rows are processed in
+    `n_blocks` row blocks; the device->host copy of a finished block runs on a second stream while the
+    next block is computed, so only the upload and the last block's download are exposed.
+    Returns (dist, idx) host tensors [n, k]."""
+    import torch
+    _lib.require_cuda()
+    if isinstance(X_host, np.ndarray):
+        X_host = torch.from_numpy(np.ascontiguousarray(X_host))
+    N = X_host.shape[0]
+    if q_end is None:
+        q_end = N
+    n_q = q_end - q_begin
+    k = int(n_neighbors)
+    if out_dist is None:
+        out_dist = torch.empty((n_q, k), dtype=X_host.dtype).pin_memory()
+    if out_idx is None:
+        out_idx = torch.empty((n_q, k), dtype=torch.int32).pin_memory()
+    Xd = X_host.cuda(non_blocking=True)
+    compute = torch.cuda.current_stream()
+    copy = _copy_stream(Xd.device)
+    n_blocks = max(1, min(int(n_blocks), (n_q + 65535) // 65536))
+    step = ((n_q + n_blocks - 1) // n_blocks + 255) // 256 * 256
+    keep = []
+    for b0 in range(0, n_q, step):
+        b1 = min(n_q, b0 + step)
+        d, i = knn(Xd, k, q_begin=q_begin + b0, q_end=q_begin + b1, algo=algo)
+        ev = torch.cuda.Event()
+        ev.record(compute)
+        copy.wait_event(ev)
+        with torch.cuda.stream(copy):
+            out_dist[b0:b1].copy_(d, non_blocking=True)
+            out_idx[b0:b1].copy_(i, non_blocking=True)
+        keep.append((d, i))              # keep the device blocks alive until their copies have run
+    copy.synchronize()
+    return out_dist, out_idx
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    import torch
+    s = _copy_streams.get(device)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _copy_streams[device] = s
+    return s
+
+
 def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2, metric_params=None,
                      include_self=False, n_jobs=None, algo='auto'):
     """Same signature as sklearn.neighbors.kneighbors_graph for the arguments

@@ -138,3 +138,14 @@ def test_kneighbors_graph_csr_layout(golden):
     assert G.data.dtype == np.float64 and G.indices.dtype == np.int64 and G.indptr.dtype == np.int64
     np.testing.assert_array_equal(G.indptr, np.arange(0, 801, 20))
     compare.assert_knn_parity(g['emb_k20_d'], g['emb_k20_i'], G.data.reshape(40, 20), G.indices.reshape(40, 20), rtol=1e-7, atol=1e-6)
+
+
+def test_knn_host_blocks_equal_device_call():
+    """Host-buffer entry point (row blocks, download overlapped with the next block) == one device call."""
+    import torch
+    from semibin_b200.neighbors import knn, knn_host
+    X = synth.embeddings(150000, seed=77)
+    Xd = torch.from_numpy(X).cuda()
+    d0, i0 = knn(Xd, 50, q_begin=1000, q_end=141000)
+    hd, hi = knn_host(torch.from_numpy(X).pin_memory(), 50, q_begin=1000, q_end=141000, n_blocks=3)
+    assert torch.equal(hd, d0.cpu()) and torch.equal(hi, i0.cpu())
