@@ -9,29 +9,47 @@ namespace sbk {
 static constexpr int E_THREADS = 128;
 static constexpr int E_MAXK = 1024;
 
-// Stage 1: one CTA per row.  w = 1 - min(d_emb, 1) where the column is in both
-// graphs and neither distance is an explicit zero (eliminate_zeros,
-// cluster.py:109,112); row max (cluster.py:119).
-__global__ void __launch_bounds__(E_THREADS)
+// Stage 1: one warp per row.  w = 1 - min(d_emb, 1) where the column is in both graphs and neither
+// distance is an explicit zero (eliminate_zeros, cluster.py:109,112); row max (cluster.py:119).
+// The feature-graph columns of the row go into a per-warp open-addressing hash set in shared memory
+// (load factor <= 0.5), so the intersection is O(k) per row and the kernel streams at HBM speed
+// instead of doing k^2 compares.
+static constexpr int E1_WARPS = 4;
+__global__ void __launch_bounds__(E1_WARPS * 32)
 edges_stage1_kernel(const float* __restrict__ emb_dist, const int32_t* __restrict__ emb_idx,
                     const double* __restrict__ kmer_dist, const int32_t* __restrict__ kmer_idx,
-                    int k, double* __restrict__ w, double* __restrict__ rowmax) {
-  __shared__ int32_t bidx[E_MAXK];
-  __shared__ double red[E_THREADS / 32];
-  const long long r = blockIdx.x;
-  const int tid = threadIdx.x;
-  for (int c = tid; c < k; c += E_THREADS) {
-    int32_t j = kmer_idx[r * k + c];
-    if (kmer_dist && kmer_dist[r * k + c] == 0.0) j = -1;       // explicit zero -> eliminated
-    bidx[c] = j;
+                    long long n_rows, int k, int tab_size, double* __restrict__ w, double* __restrict__ rowmax) {
+  extern __shared__ int32_t e1_tab[];                           // [E1_WARPS][tab_size], tab_size = power of two >= 2k
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long r = (long long)blockIdx.x * E1_WARPS + wp;
+  if (r >= n_rows) return;
+  int32_t* tab = e1_tab + wp * tab_size;
+  const uint32_t tmask = (uint32_t)tab_size - 1u;
+  for (int t = lane; t < tab_size; t += 32) tab[t] = -1;
+  __syncwarp();
+  for (int c = lane; c < k; c += 32) {
+    const int32_t j = kmer_idx[r * k + c];
+    if (kmer_dist && kmer_dist[r * k + c] == 0.0) continue;     // explicit zero -> eliminated
+    uint32_t h = ((uint32_t)j * 2654435761u) & tmask;
+    for (;;) {
+      const int32_t prev = atomicCAS(&tab[h], -1, j);
+      if (prev == -1 || prev == j) break;
+      h = (h + 1) & tmask;
+    }
   }
-  __syncthreads();
+  __syncwarp();
   double mx = 0.0;                                              // implicit zeros count
-  for (int c = tid; c < k; c += E_THREADS) {
+  for (int c = lane; c < k; c += 32) {
     const int32_t j = emb_idx[r * k + c];
     const double d = (double)emb_dist[r * k + c];
     bool found = false;
-    for (int t = 0; t < k; ++t) found |= (bidx[t] == j);
+    uint32_t h = ((uint32_t)j * 2654435761u) & tmask;
+    for (;;) {
+      const int32_t t = tab[h];
+      if (t == j) { found = true; break; }
+      if (t == -1) break;
+      h = (h + 1) & tmask;
+    }
     double ww = 0.0;
     if (found && d != 0.0) ww = 1.0 - fmin(d, 1.0);
     w[r * k + c] = ww;
@@ -39,12 +57,7 @@ edges_stage1_kernel(const float* __restrict__ emb_dist, const int32_t* __restric
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if ((tid & 31) == 0) red[tid >> 5] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 1; i < E_THREADS / 32; ++i) mx = fmax(mx, red[i]);
-    rowmax[r] = mx;
-  }
+  if (lane == 0) rowmax[r] = mx;
 }
 
 // counts[m] += #{r : rowmax[r] > thresholds[m]}   (cluster.py:122)
@@ -83,10 +96,11 @@ threshold_count_kernel(const double* __restrict__ rowmax, long long n,
 //   (log v_j - log v_i)/2 + ((m_j - m_i)^2 + v_i) / (2 v_j) - 0.5, clipped to [1e-6, 1-1e-6]
 // every operation individually rounded to float32 (no FMA contraction).  The
 // float32 log is taken as the correctly rounded value of the float64 log.
-__device__ __forceinline__ float kl_term(float mi, float vi, float mj, float vj) {
-  mi = fmaxf(mi, 1e-6f); mj = fmaxf(mj, 1e-6f);
-  vi = fmaxf(vi, 1.0f);  vj = fmaxf(vj, 1.0f);
-  const float lvi = (float)log((double)vi), lvj = (float)log((double)vj);
+// (mi, vi, lvi) arrive clamped / precomputed for the row: max(m, 1e-6), max(v, 1), float(log(v)).
+__device__ __forceinline__ float kl_term(float mi, float vi, float lvi, float mj, float vj) {
+  mj = fmaxf(mj, 1e-6f);
+  vj = fmaxf(vj, 1.0f);
+  const float lvj = (float)log((double)vj);
   float v_div = __fsub_rn(lvj, lvi);
   v_div = __fdiv_rn(v_div, 2.0f);
   float m_dif = __fsub_rn(mj, mi);
@@ -111,28 +125,37 @@ edges_stage2_kernel(const double* __restrict__ w, const int32_t* __restrict__ em
   __shared__ uint32_t sid[E_MAXK];
   __shared__ double sval[E_MAXK];
   __shared__ int s_n;
+  extern __shared__ float row_mvl[];                          // [n_sample][3]: the row's own (m, v, log v), clamped
   const long long r = blockIdx.x;
   const long long gi = row_begin + r;
   const int tid = threadIdx.x;
   if (tid == 0) s_n = 0;
+  if (!is_combined) {
+    for (int s2 = tid; s2 < n_sample; s2 += E_THREADS) {
+      const float m = fmaxf(depth[gi * 2 * n_sample + 2 * s2], 1e-6f);
+      const float v = fmaxf(depth[gi * 2 * n_sample + 2 * s2 + 1], 1.0f);
+      row_mvl[3 * s2] = m; row_mvl[3 * s2 + 1] = v; row_mvl[3 * s2 + 2] = (float)log((double)v);
+    }
+  }
   __syncthreads();
   for (int c = tid; c < k; c += E_THREADS) {
     double ww = w[r * k + c];
     const int32_t j = emb_idx[r * k + c];
-    bool keep = (ww != 0.0) && !(ww <= threshold);           // cluster.py:127-128
+    // only the upper triangle is emitted (cluster.py:146-148): test it first, the KL factor of a dropped
+    // entry is never looked at
+    bool keep = (ww != 0.0) && !(ww <= threshold) && ((long long)j > gi);   // cluster.py:127-128
     if (keep && !is_combined) {
-      const float* di = depth + gi * 2 * n_sample;
       const float* dj = depth + (long long)j * 2 * n_sample;
       float acc = 0.f;
       for (int s = 0; s < n_sample; ++s) {
-        const float kl = kl_term(di[2 * s], di[2 * s + 1], dj[2 * s], dj[2 * s + 1]);
+        const float kl = kl_term(row_mvl[3 * s], row_mvl[3 * s + 1], row_mvl[3 * s + 2], dj[2 * s], dj[2 * s + 1]);
         acc = (s == 0) ? -kl : __fsub_rn(acc, kl);            // kl *= -1 ; kl_matrix -= kl
       }
       acc = __fadd_rn(acc, (float)n_sample);                   // += n_sample
       acc = __fdiv_rn(acc, (float)n_sample);                   // /= n_sample
       ww = ww * (double)acc;                                   // cluster.py:141 (f64 * f32)
     }
-    keep = keep && !(ww <= 1e-6) && ((long long)j > gi);       // :143, :146-148
+    keep = keep && !(ww <= 1e-6);                              // :143
     if (keep) {
       int p = atomicAdd(&s_n, 1);
       skey[p] = (double)j; sid[p] = (uint32_t)p; sval[p] = ww;
@@ -142,8 +165,19 @@ edges_stage2_kernel(const double* __restrict__ w, const int32_t* __restrict__ em
   const int n = s_n;
   if (tid == 0) row_cnt[r] = n;
   if (n == 0) return;
+  if (n <= 2 * E_THREADS) {
+    // rank sort by column (columns of a row are distinct): no barriers, each entry lands at its rank
+    for (int t = tid; t < n; t += E_THREADS) {
+      const double kt = skey[t];
+      int rk = 0;
+#pragma unroll 4
+      for (int u = 0; u < n; ++u) rk += skey[u] < kt ? 1 : 0;
+      stage_y[r * k + rk] = (int32_t)kt;
+      stage_v[r * k + rk] = sval[t];
+    }
+    return;
+  }
   int P = (int)pow2ceil((uint32_t)n);
-  if (P < 2) P = 2;
   for (int t = n + tid; t < P; t += E_THREADS) { skey[t] = __longlong_as_double(0x7ff0000000000000LL); sid[t] = 0xffffffffu; }
   block_bitonic_sort<E_THREADS>(skey, sid, P, tid);
   for (int t = tid; t < n; t += E_THREADS) {
@@ -185,7 +219,10 @@ extern "C" int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
   if (k < 1 || k > E_MAXK) { set_error("edges: k=%d outside [1,%d]", k, E_MAXK); return SBK_ERR_INVALID; }
   if (n_thresholds < 0 || n_thresholds > SBK_MAX_THRESHOLDS) { set_error("edges: n_thresholds=%d", n_thresholds); return SBK_ERR_INVALID; }
   if (n_rows <= 0) return SBK_OK;
-  edges_stage1_kernel<<<(unsigned)n_rows, E_THREADS, 0, stream>>>(emb_dist, emb_idx, kmer_dist, kmer_idx, k, w, rowmax);
+  const int tab_size = (int)pow2ceil((uint32_t)(2 * k));
+  const size_t smem1 = (size_t)E1_WARPS * tab_size * sizeof(int32_t);
+  edges_stage1_kernel<<<(unsigned)((n_rows + E1_WARPS - 1) / E1_WARPS), E1_WARPS * 32, smem1, stream>>>(
+      emb_dist, emb_idx, kmer_dist, kmer_idx, n_rows, k, tab_size, w, rowmax);
   SBK_LAUNCH_CHECK();
   if (n_thresholds > 0) {
     int blocks = (int)((n_rows + 256 * 16 - 1) / (256 * 16));
@@ -223,7 +260,8 @@ extern "C" int sbk_edges_stage2(const double* w, const int32_t* emb_idx,
   long long* bsum = a.take<long long>(scan_workspace_elems(n_rows));
   if (!a.ok()) { set_error("edges stage2: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   if (n_rows <= 0) { SBK_CUDA_CHECK(cudaMemsetAsync(n_edges, 0, sizeof(long long), stream)); return SBK_OK; }
-  edges_stage2_kernel<<<(unsigned)n_rows, E_THREADS, 0, stream>>>(w, emb_idx, row_begin, k, threshold, depth, n_sample,
+  if (n_sample > 1024) { set_error("edges stage2: n_sample=%d > 1024", n_sample); return SBK_ERR_INVALID; }
+  edges_stage2_kernel<<<(unsigned)n_rows, E_THREADS, (size_t)(is_combined ? 0 : n_sample) * 3 * sizeof(float), stream>>>(w, emb_idx, row_begin, k, threshold, depth, n_sample,
                                                                  is_combined, stage_y, stage_v, row_cnt);
   SBK_LAUNCH_CHECK();
   int rc = exclusive_scan(row_cnt, n_rows, row_off, bsum, stream);

@@ -58,28 +58,47 @@ radius_sweep_kernel(const float* __restrict__ dist, const int32_t* __restrict__ 
 static constexpr int L_NONE = 0x7fffffff;
 
 __global__ void label_init_kernel(const uint8_t* __restrict__ core, long long total, long long n,
-                                  int32_t* __restrict__ L) {
+                                  int32_t* __restrict__ L, uint8_t* __restrict__ dirty) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < total) L[i] = core[i] ? (int32_t)(i % n) : L_NONE;
+  if (i < total) { L[i] = core[i] ? (int32_t)(i % n) : L_NONE; dirty[i] = core[i]; }
 }
 
-// One warp per (eps, row): push L[u] to the eps-prefix of a core row.
+// One warp per (eps, row): push L[u] to the eps-prefix of a core row.  Only rows whose label changed since
+// their last push are "dirty" and do any work: after the first sweep the frontier is a small part of the graph,
+// so a sweep costs one flag byte per row instead of the row's k indices.
 __global__ void __launch_bounds__(R_WARPS * 32)
 label_prop_kernel(const int32_t* __restrict__ idx, long long n, int k,
                   const int32_t* __restrict__ prefix_len, const uint8_t* __restrict__ core,
-                  int n_eps, int32_t* __restrict__ L, int* __restrict__ changed) {
+                  int n_eps, int32_t* __restrict__ L, uint8_t* __restrict__ dirty, int* __restrict__ changed) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * R_WARPS + (threadIdx.x >> 5);
   if (wid >= n * n_eps) return;
+  if (!dirty[wid]) return;                       // non-core rows are never dirty
   const long long e = wid / n, u = wid % n;
-  if (!core[wid]) return;
   int32_t* Le = L + e * n;
-  const int32_t lu = Le[u];
+  uint8_t* De = dirty + e * n;
+  // clear first, then read the label: a concurrent improvement of L[u] either is seen by the read below or
+  // sets the flag again after this clear
+  if (lane == 0) De[u] = 0;
+  __threadfence();
+  int32_t lu = ((volatile int32_t*)Le)[u];
+  lu = __shfl_sync(0xffffffffu, lu, 0);          // the value read by the lane that cleared the flag
+  // pointer jumping: L[x] = y means core y reaches x, and L[y] reaches y, so L[y] reaches x as well; following
+  // the chain to its root before pushing makes the number of sweeps logarithmic in the path length
+  {
+    int32_t root = lu;
+    for (int hop = 0; hop < 64; ++hop) { const int32_t nx = ((volatile int32_t*)Le)[root]; if (nx >= root) break; root = nx; }
+    root = __shfl_sync(0xffffffffu, root, 0);
+    if (root < lu) { if (lane == 0) atomicMin(&Le[u], root); lu = root; }
+  }
   const int plen = prefix_len[wid];
   bool any = false;
   for (int c = lane; c < plen; c += 32) {
     const int32_t j = idx[u * k + c];
-    if (Le[j] > lu) { atomicMin(&Le[j], lu); any = true; }
+    if (Le[j] > lu) {
+      const int32_t old = atomicMin(&Le[j], lu);
+      if (old > lu) { if (core[e * n + j]) De[j] = 1; any = true; }
+    }
   }
   if (__any_sync(0xffffffffu, any) && lane == 0) *changed = 1;
 }
@@ -128,6 +147,7 @@ extern "C" size_t sbk_dbscan_labels_workspace_bytes(int64_t n, int32_t n_eps) {
   a.take<long long>(total + 1);      // seed_off
   a.take<long long>(scan_workspace_elems((long long)total));
   a.take<int>(64);
+  a.take<uint8_t>(total);            // dirty
   return a.off + 256;
 }
 
@@ -143,18 +163,19 @@ extern "C" int sbk_dbscan_labels(const int32_t* idx, int64_t n, int32_t k,
   long long* seed_off = a.take<long long>((size_t)total + 1);
   long long* bsum = a.take<long long>(scan_workspace_elems(total));
   int* changed = a.take<int>(64);
+  uint8_t* dirty = a.take<uint8_t>((size_t)total);
   if (!a.ok()) { set_error("dbscan labels: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   const unsigned eb = (unsigned)((total + 255) / 256);
-  label_init_kernel<<<eb, 256, 0, stream>>>(core, total, n, L);
+  label_init_kernel<<<eb, 256, 0, stream>>>(core, total, n, L, dirty);
   SBK_LAUNCH_CHECK();
   const unsigned wb = (unsigned)((total + R_WARPS - 1) / R_WARPS);
   // Propagate to the fixpoint.  The host polls `changed` every few sweeps; the
   // number of sweeps is bounded by the longest shortest path (+ polling slack).
-  const int sweeps_per_poll = 4;
+  const int sweeps_per_poll = 2;
   for (long long it = 0;; ++it) {
     SBK_CUDA_CHECK(cudaMemsetAsync(changed, 0, sizeof(int), stream));
     for (int s = 0; s < sweeps_per_poll; ++s) {
-      label_prop_kernel<<<wb, R_WARPS * 32, 0, stream>>>(idx, n, k, prefix_len, core, n_eps, L, changed);
+      label_prop_kernel<<<wb, R_WARPS * 32, 0, stream>>>(idx, n, k, prefix_len, core, n_eps, L, dirty, changed);
       SBK_LAUNCH_CHECK();
     }
     int h = 0;
