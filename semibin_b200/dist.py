@@ -30,9 +30,11 @@ def world_info(group=None):
     return 0, 1
 
 
-def all_gather_rows(local, n_total, group=None):
+def all_gather_rows(local, n_total, group=None, out=None):
     """Gather row blocks of possibly different heights (differ by at most one
-    row) into the full [n_total, ...] tensor on every rank."""
+    row) into the full [n_total, ...] tensor on every rank.  Equal blocks go
+    straight into the result (`out`, if given, is reused) with one collective and
+    no staging copy."""
     import torch
     dist = _dist()
     rank, world = world_info(group)
@@ -40,6 +42,11 @@ def all_gather_rows(local, n_total, group=None):
         return local
     sizes = [row_block(n_total, r, world) for r in range(world)]
     max_rows = max(hi - lo for lo, hi in sizes)
+    if all(hi - lo == max_rows for lo, hi in sizes):
+        if out is None:
+            out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[:local.shape[0]] = local
     out = torch.empty((world * max_rows,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)

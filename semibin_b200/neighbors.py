@@ -52,11 +52,12 @@ def release_workspace():
     _ws_cache.clear()
 
 
-def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=False):
+def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=False, out=None):
     """Exact Euclidean kNN of rows [q_begin, q_end) of X among all rows of X
     (self excluded by index).  X: CUDA tensor [N, D] float32/float64.
     Returns (dist, idx): dist float32 (float64 for float64 input) [n, k],
-    idx int32 [n, k], both CUDA tensors, rows ordered by (distance, index)."""
+    idx int32 [n, k], both CUDA tensors, rows ordered by (distance, index).
+    `out=(dist, idx)` reuses caller-owned CUDA tensors of those shapes/dtypes (no allocation in the call)."""
     import torch
     _lib.require_cuda()
     lib = _lib.load()
@@ -77,8 +78,15 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
     if ws_bytes == 0:
         raise ValueError(_lib.last_error())
     ws = _workspace(ws_bytes, X.device)
-    out_d = torch.empty((n_q, k), dtype=X.dtype, device=X.device)
-    out_i = torch.empty((n_q, k), dtype=torch.int32, device=X.device)
+    if out is not None:
+        out_d, out_i = out
+        if (tuple(out_d.shape) != (n_q, k) or tuple(out_i.shape) != (n_q, k) or out_d.dtype != X.dtype
+                or out_i.dtype != torch.int32 or not out_d.is_contiguous() or not out_i.is_contiguous()
+                or out_d.device != X.device or out_i.device != X.device):
+            raise ValueError('out must be contiguous (dist, idx) CUDA tensors of shape [n, k], dtypes (X.dtype, int32)')
+    else:
+        out_d = torch.empty((n_q, k), dtype=X.dtype, device=X.device)
+        out_i = torch.empty((n_q, k), dtype=torch.int32, device=X.device)
     stats = _lib.KnnStats()
     rc = lib.sbk_knn(_lib.ptr(X), dtype, N, D, X.stride(0), q_begin, q_end, k,
                      _lib.ptr(out_d), _lib.ptr(out_i), _lib.ptr(ws), ws.numel(), a,
