@@ -547,21 +547,24 @@ tc_kernel(const TcArgs p) {
     }
     // FILTER: this thread's candidate segment (row = thread, column quarter = warp): (column, score) pairs
     const int seg_cap = p.cand_cap >> 2;
-    uint2* seg = nullptr; uint2* wr = nullptr; uint2* wr_lim = nullptr;
+    uint2* seg = nullptr;
+    int cnt = 0;                                                // candidates in the segment so far
+    const int cnt_lim = seg_cap - 32;                           // a 32-column chunk is appended only if it fits entirely
     bool overflow = false;
     if ((MODE == TC_FILTER || MODE == TC_PROBE_NOAPPEND) && row_ok) {
       thr = p.thr[slot];
       seg = p.cand + slot * (long long)p.cand_cap + (long long)w4 * seg_cap;
-      int c0 = 0;
-      if (p.bt0 > 0) c0 = p.cand_count[slot * 4 + w4];        // continue the segment of the earlier reference chunks
-      overflow = c0 > seg_cap;
-      wr = seg + min(c0, seg_cap);
-      wr_lim = seg + seg_cap - 32;                            // a 32-column chunk is appended only if it fits entirely
+      if (p.bt0 > 0) cnt = p.cand_count[slot * 4 + w4];         // continue the segment of the earlier reference chunks
+      overflow = cnt > seg_cap;
+      cnt = min(cnt, seg_cap);
     }
     int probe_hits = 0;
+    // first tile column of this warp's quarter; loop-carried so the append path finds it in a register
+    uint32_t jcol = (uint32_t)(p.bt0 * TC_BN + w4 * 64) - (uint32_t)TC_BN;
 
     for (long long t = 0; t < n_tiles; ++t) {
       const int as = (int)(t & 1);
+      jcol += (uint32_t)TC_BN;
       mbar_wait(&tfull_bar[as], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN + w4 * 64);
@@ -573,20 +576,18 @@ tc_kernel(const TcArgs p) {
       }
       uint32_t va[32], vb[32];
       if (MODE == TC_FILTER || MODE == TC_PROBE_NOAPPEND) {
-        // software pipeline: the second 32 columns are in flight (TMEM -> registers) while the first 32 are reduced
+        // Both 32-column halves go to registers and the accumulator stage is released BEFORE any of it is
+        // reduced: the MMA issuer waits for the slowest of the pair's 32 epilogue warps, so whatever a warp
+        // does between "accumulator ready" and its release is on the tensor pipe's critical path.
         tmem_ld32(taddr, va);
-        tmem_ld_wait();
         tmem_ld32(taddr + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t* v = hh ? vb : va;
-          if (hh == 1) {
-            tmem_ld_wait();
-            // the accumulator stage is free as soon as its values sit in registers
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
-          }
           // minima of the four groups of 8 columns, then of the chunk: three-input min instructions, no branches
           float m8[4];
 #pragma unroll
@@ -596,17 +597,24 @@ tc_kernel(const TcArgs p) {
             m8[g] = fminf(fminf(a0, a1), fminf(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7])));
           }
           const float mn = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
-          if (mn <= thr) {                       // rare: about one lane in every other warp-chunk
-            if (MODE == TC_PROBE_NOAPPEND) { ++probe_hits; continue; }
-            if (wr > wr_lim) { overflow = true; continue; }     // segment (nearly) full: the row goes to the exact filter
-            const uint32_t j0 = (uint32_t)((p.bt0 + t) * TC_BN + w4 * 64 + hh * 32);
+          const bool hit = mn <= thr;            // about one lane in every other warp-chunk
+          // The append path is WARP-UNIFORM: votes decide which 8-column groups are walked and every lane walks
+          // them with its stores predicated.  (As per-lane branches the hitting lanes diverged by group and the
+          // path cost ~145 issue slots per entry with one active thread: 40 % of the kernel's instructions.)
+          if (__any_sync(0xffffffffu, hit)) {
+            if (MODE == TC_PROBE_NOAPPEND) { probe_hits += hit ? 1 : 0; continue; }
+            const bool full = cnt > cnt_lim;     // segment (nearly) full: the row goes to the exact filter
+            overflow |= hit && full;
+            const bool can = hit && !full;
+            const uint32_t j0 = jcol + hh * 32;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (m8[g] <= thr) {
+              const bool hg = can && (m8[g] <= thr);
+              if (__any_sync(0xffffffffu, hg)) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                  // one 8-byte store and a pointer bump per passing column; no capacity test here
-                  if (__uint_as_float(v[8 * g + c]) <= thr) { *wr = make_uint2(j0 + 8 * g + c, v[8 * g + c]); ++wr; }
+                  // one 8-byte store and a counter bump per passing column; no capacity test here
+                  if (hg && __uint_as_float(v[8 * g + c]) <= thr) { seg[cnt] = make_uint2(j0 + 8 * g + c, v[8 * g + c]); ++cnt; }
                 }
               }
             }
@@ -642,7 +650,7 @@ tc_kernel(const TcArgs p) {
     // ---- per-row results ----
     if (MODE == TC_FILTER) {
       // a count above the segment capacity marks the segment as overflowed (the rerank sends the row to the exact filter)
-      if (row_ok) p.cand_count[slot * 4 + w4] = overflow ? seg_cap + 1 : (int)(wr - seg);
+      if (row_ok) p.cand_count[slot * 4 + w4] = overflow ? seg_cap + 1 : cnt;
     }
     if ((MODE == TC_PROBE_NOAPPEND || MODE == TC_PROBE_LDONLY) && row_ok && probe_hits == 0x7fffffff) p.cand_count[slot * 4 + w4] = 1;
     if (MODE == TC_SAMPLE) {
