@@ -219,7 +219,7 @@ __device__ __forceinline__ void rr_distances(const T* __restrict__ X, long long 
 //                (NULL -> +inf, i.e. the list is a guaranteed superset)
 //   fail_rows / n_fail : rows whose certificate failed are appended here (output left untouched)
 template <typename T, typename OutT, bool REGQ>
-__global__ void __launch_bounds__(RR_THREADS, REGQ ? 3 : 2)
+__global__ void __launch_bounds__(RR_THREADS, REGQ ? 4 : 2)
 rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ rows, long long q_begin,
               const uint32_t* __restrict__ cand_idx, const uint2* __restrict__ cand_pair,
@@ -237,6 +237,8 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   uint32_t* cid = id + pmax;                                 // [ncand_cap]  all candidates (tensor path only)
   float* cval = reinterpret_cast<float*>(cid + ncand_cap);   // [ncand_cap]  lower bounds L
   __shared__ uint32_t hist[512];
+  __shared__ __align__(16) uint32_t s_khi[2 * RR_THREADS];   // rank sort: high words of the survivors' d2
+  __shared__ uint16_t s_own[2 * RR_THREADS];                 // rank sort: who claimed each position
   __shared__ uint32_t s_prefix, s_remaining;
   __shared__ int s_drop, s_m, s_m2;
   __shared__ unsigned long long s_dmax;
@@ -397,11 +399,16 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   if (tid == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
 
   if (m <= 2 * RR_THREADS) {
-    // ---- rank sort: every thread counts how many survivors precede its own in (d2, index) order and drops
-    // its pair at that position.  O(m^2 / threads) broadcast reads but only two block barriers, against the
-    // ~40 of a bitonic network (the rerank is barrier- and latency-bound, not issue-bound).  Only the first
-    // k+1 positions are needed; (d2, index) pairs are distinct, +inf padding of the exact path ranks last.
+    // ---- rank sort: every thread counts how many survivors precede its own and drops its pair at that
+    // position: two or three block barriers against the ~40 of a bitonic network.  Only the first k+1
+    // positions are needed.  Fast pass: compare the HIGH WORDS of the d2 bit patterns only (d2 >= 0, so
+    // the pattern is monotone; one broadcast 16-byte load and two integer instructions per pair instead of
+    // two FP64 compares, an index compare and their selects).  Equal high words give equal counts, i.e. two
+    // survivors claim the same position: detected through the `s_own` table, and only such rows (a few %)
+    // repeat the count with the full (d2, index) comparison.  +inf padding of the exact path ranks last.
     __syncthreads();
+    for (int c = tid; c < ((m + 3) & ~3); c += RR_THREADS)
+      s_khi[c] = c < m ? (uint32_t)__double2hiint(key[c]) : 0x7ff00000u;   // pad: never "less"
     double kt[2]; uint32_t it[2]; int rk[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -409,23 +416,60 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       rk[u] = -1;
       if (c < m) { kt[u] = key[c]; it[u] = id[c]; rk[u] = 0; }
     }
+    __syncthreads();
     if (rk[0] == 0) {
+      const uint32_t h0 = (uint32_t)__double2hiint(kt[0]);
+      const uint4* kh4 = reinterpret_cast<const uint4*>(s_khi);
       if (rk[1] == 0) {
-#pragma unroll 4
-        for (int j = 0; j < m; ++j) {
-          const double kj = key[j]; const uint32_t ij = id[j];
-          rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
-          rk[1] += (kj < kt[1] || (kj == kt[1] && ij < it[1])) ? 1 : 0;
+        const uint32_t h1 = (uint32_t)__double2hiint(kt[1]);
+        uint32_t r0 = 0, r1 = 0;
+#pragma unroll 2
+        for (int j = 0; j < (m + 3) / 4; ++j) {
+          const uint4 hj = kh4[j];                 // high words < 2^31: the borrow of (hj - h) is "hj < h"
+          r0 += ((hj.x - h0) >> 31) + ((hj.y - h0) >> 31) + ((hj.z - h0) >> 31) + ((hj.w - h0) >> 31);
+          r1 += ((hj.x - h1) >> 31) + ((hj.y - h1) >> 31) + ((hj.z - h1) >> 31) + ((hj.w - h1) >> 31);
         }
+        rk[0] = (int)r0; rk[1] = (int)r1;
       } else {
-#pragma unroll 4
-        for (int j = 0; j < m; ++j) {
-          const double kj = key[j]; const uint32_t ij = id[j];
-          rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
+        uint32_t r0 = 0;
+#pragma unroll 2
+        for (int j = 0; j < (m + 3) / 4; ++j) {
+          const uint4 hj = kh4[j];
+          r0 += ((hj.x - h0) >> 31) + ((hj.y - h0) >> 31) + ((hj.z - h0) >> 31) + ((hj.w - h0) >> 31);
         }
+        rk[0] = (int)r0;
       }
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (rk[u] >= 0 && rk[u] < k1) s_own[rk[u]] = (uint16_t)(tid + u * RR_THREADS);
     __syncthreads();
+    bool clash = false;
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      clash |= (rk[u] >= 0 && rk[u] < k1 && s_own[rk[u]] != (uint16_t)(tid + u * RR_THREADS));
+    if (__syncthreads_or(clash ? 1 : 0)) {
+      // rare: full comparison (key/id are still untouched)
+#pragma unroll
+      for (int u = 0; u < 2; ++u) if (rk[u] >= 0) rk[u] = 0;
+      if (rk[0] == 0) {
+        if (rk[1] == 0) {
+#pragma unroll 4
+          for (int j = 0; j < m; ++j) {
+            const double kj = key[j]; const uint32_t ij = id[j];
+            rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
+            rk[1] += (kj < kt[1] || (kj == kt[1] && ij < it[1])) ? 1 : 0;
+          }
+        } else {
+#pragma unroll 4
+          for (int j = 0; j < m; ++j) {
+            const double kj = key[j]; const uint32_t ij = id[j];
+            rk[0] += (kj < kt[0] || (kj == kt[0] && ij < it[0])) ? 1 : 0;
+          }
+        }
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       if (rk[u] >= 0 && rk[u] < k1) { key[rk[u]] = kt[u]; id[rk[u]] = it[u]; }
