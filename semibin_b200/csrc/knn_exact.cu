@@ -16,9 +16,9 @@
 namespace sbk {
 
 static constexpr int XF_THREADS = 256;
-static constexpr int XF_QT = 8;          // query rows per CTA
-
-template <typename T>
+// query rows per CTA: 8 (each streamed reference row is reused for 8 queries), or 1 for the handful of rows
+// the tensor path hands back (the 7 idle query slots cost 8x the FP64 work and 4x the shared-memory reads)
+template <typename T, int XF_QT>
 __global__ void __launch_bounds__(XF_THREADS)
 exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
                     const int32_t* __restrict__ rows, long long q_begin, long long n_q,
@@ -28,9 +28,9 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* qs = reinterpret_cast<double*>(smem_raw);                 // [d][QT]
   double* key = qs + (size_t)d * XF_QT;                             // [QT][cap]
-  uint32_t* id = reinterpret_cast<uint32_t*>(key + (size_t)XF_QT * cap);   // [QT][cap]
+  double* thr = key + (size_t)XF_QT * cap;                          // [QT]
+  uint32_t* id = reinterpret_cast<uint32_t*>(thr + XF_QT);          // [QT][cap]
   int* cnt = reinterpret_cast<int*>(id + (size_t)XF_QT * cap);      // [QT]
-  double* thr = reinterpret_cast<double*>(cnt + XF_QT);             // [QT] (8B aligned: QT*4 = 32)
 
   const int tid = threadIdx.x;
   const long long slot0 = (long long)blockIdx.x * XF_QT;
@@ -93,13 +93,18 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           if (u < nc) {
-            const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)(c0 + u) * XF_QT);
+            if (XF_QT == 1) {
+              const double t0 = qs[c0 + u] - yv[u];
+              acc[0] = fma(t0, t0, acc[0]);
+            } else {
+              const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)(c0 + u) * XF_QT);
 #pragma unroll
-            for (int h = 0; h < XF_QT / 2; ++h) {
-              double2 qq = q2[h];
-              double t0 = qq.x - yv[u], t1 = qq.y - yv[u];
-              acc[2 * h] = fma(t0, t0, acc[2 * h]);
-              acc[2 * h + 1] = fma(t1, t1, acc[2 * h + 1]);
+              for (int h = 0; h < XF_QT / 2; ++h) {
+                double2 qq = q2[h];
+                double t0 = qq.x - yv[u], t1 = qq.y - yv[u];
+                acc[2 * h] = fma(t0, t0, acc[2 * h]);
+                acc[2 * h + 1] = fma(t1, t1, acc[2 * h + 1]);
+              }
             }
           }
         }
@@ -143,9 +148,11 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
 
 int exact_filter_cap(int k1) { return (int)pow2ceil((uint32_t)(k1 + XF_THREADS)); }
 
+static constexpr int XF_QT_MAX = 8;
+static constexpr long long XF_FEW_ROWS = 32;     // up to this many query rows: one row per CTA
 size_t exact_filter_smem(int d, int k1) {
   int cap = exact_filter_cap(k1);
-  return (size_t)d * XF_QT * 8 + (size_t)XF_QT * cap * 12 + XF_QT * 4 + XF_QT * 8 + 16;
+  return (size_t)d * XF_QT_MAX * 8 + (size_t)XF_QT_MAX * cap * 12 + XF_QT_MAX * 4 + XF_QT_MAX * 8 + 16;
 }
 
 int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long long ld,
@@ -156,16 +163,17 @@ int launch_exact_filter(const void* X, int dtype, long long n_ref, int d, long l
   int cap = exact_filter_cap(k1);
   size_t smem = exact_filter_smem(d, k1);
   if (smem > 227 * 1024) { set_error("exact filter: k=%d d=%d needs %zu B shared memory", k1 - 1, d, smem); return SBK_ERR_INVALID; }
-  dim3 grid((unsigned)((n_q + XF_QT - 1) / XF_QT), (unsigned)n_split);
-  if (dtype == SBK_F32) {
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(exact_filter_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    exact_filter_kernel<float><<<grid, XF_THREADS, smem, stream>>>((const float*)X, n_ref, d, ld, rows, q_begin, n_q,
-                                                                  n_split, k1, cap, cand_idx, cand_stride, cand_count);
-  } else {
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(exact_filter_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    exact_filter_kernel<double><<<grid, XF_THREADS, smem, stream>>>((const double*)X, n_ref, d, ld, rows, q_begin, n_q,
-                                                                    n_split, k1, cap, cand_idx, cand_stride, cand_count);
-  }
+#define SBK_XF_LAUNCH(T, QT)                                                                                           \
+  do {                                                                                                                 \
+    dim3 grid((unsigned)((n_q + QT - 1) / QT), (unsigned)n_split);                                                     \
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(exact_filter_kernel<T, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    exact_filter_kernel<T, QT><<<grid, XF_THREADS, smem, stream>>>((const T*)X, n_ref, d, ld, rows, q_begin, n_q,      \
+                                                                   n_split, k1, cap, cand_idx, cand_stride, cand_count); \
+  } while (0)
+  const bool few = n_q <= XF_FEW_ROWS;
+  if (dtype == SBK_F32) { if (few) SBK_XF_LAUNCH(float, 1); else SBK_XF_LAUNCH(float, 8); }
+  else { if (few) SBK_XF_LAUNCH(double, 1); else SBK_XF_LAUNCH(double, 8); }
+#undef SBK_XF_LAUNCH
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }

@@ -97,7 +97,7 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
     return out_d, out_i
 
 
-def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=2, algo='auto'):
+def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto'):
     """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
     host tensors (pinned ones are allocated when none are passed).  The query rows are processed in
     `n_blocks` row blocks; the device->host copy of a finished block runs on a second stream while the
