@@ -178,7 +178,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
     int h = tm.begin(&st.ms_prepare);
     rc = tc_prepare(X, dtype, n_ref, d, ld, s.plan, s.chunk, w.tc, w.tc_bytes, &tcs, stream);
     tm.end(h);
-    st.n_launches += 5;
+    st.n_launches += 3;
     if (rc) return rc;
     tm.on = (stats != nullptr);
     st.sample_size = s.plan.sample_size; st.cand_capacity = s.plan.cand_cap;
@@ -199,7 +199,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
-                         nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 2;
       if (rc) return rc;
@@ -209,9 +209,9 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       tm.end(h);
       if (rc) return rc;
       h = tm.begin(&st.ms_filter);
-      int nfl = 0;
-      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, w.cand_pair, w.cand_count, &nfl, stream);
-      st.n_filter_launches += nfl; st.n_launches += nfl - 1;
+      int nfl = 0, nrf = 0;
+      rc = tc_filter_chunk(&tcs, s.plan, row0, cn, k, w.cand_pair, w.cand_count, w.bound, &nfl, &nrf, stream);
+      st.n_filter_launches += nfl; st.n_launches += nfl + nrf - 1;
       if (getenv("SBK_TC_PROBE") && atoi(getenv("SBK_TC_PROBE")) > 0) {   // profiling aid: time the filter variants only
         tm.end(h); SBK_CUDA_CHECK(cudaStreamSynchronize(stream)); st.n_chunks++; continue;
       }
@@ -219,7 +219,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
       if (rc) return rc;
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
-                         w.bound, tcs.nrm, tcs.norms4, tcs.scale, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 3;
       if (rc) return rc;
@@ -243,7 +243,7 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
         if (rc) return rc;
         // n_fail doubles as the (unused) failure sink of the fallback rerank
         rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
-                           w.fb_count, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
+                           w.fb_count, nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
         if (rc) return rc;
       }
       tm.end(hfb);

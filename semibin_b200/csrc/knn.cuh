@@ -15,7 +15,7 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   const int32_t* rows, long long q_begin, long long n_slots,
                   const uint32_t* cand_idx, const uint2* cand_pair, long long cand_stride, int n_seg,
                   const int32_t* cand_count, const double* bound, const double* nrm, const float4* norms4,
-                  const double* scale, int k,
+                  const double* scale, const int32_t* orig, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream);
@@ -64,11 +64,12 @@ __host__ __device__ static inline double tc_pair_upper_slack(const float4& ni, c
   return 2.02 * G + 2.02 * J + (double)ni.w + 2.4e-7 * ((double)nj.x + (double)nj.y + (double)ni.z + (double)ni.y) + 4e-7;
 }
 struct TcState {
-  __half* a_tiles; __half* b_tiles; __half* s_tiles;
+  __half* a_tiles; __half* b_tiles;
   double* centre; double* colsum; double* scale; double* nrm;
-  float4* norms4; TcScalars* sc; int32_t* sample_rows; float* thr;
+  float4* norms4; TcScalars* sc; int32_t* orig; float* thr;   // orig[p] = row staged at reference position p
   unsigned long long* maxabs;
   int nstage; int cg; long long n_ref; int d;   // cg: CTAs per MMA (tcgen05 cta_group)
+  long long perm_mult, perm_off, perm_minv;     // reference position p holds row (p * perm_mult + perm_off) mod n_ref
 };
 
 TcPlan tc_make_plan(long long n_ref, int d, int k);
@@ -83,8 +84,10 @@ int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
                     cudaStream_t stream);
 // Filter pass over all references: fills 4 segments of cand_cap/4 (column, score) pairs per slot,
 // cand_count[slot*4 + segment].
-int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
-                    uint2* cand, int32_t* cand_count, int* n_launches, cudaStream_t stream);
+// Candidate columns are reference POSITIONS (st->orig maps them to rows); the thresholds (and `bound`) are
+// tightened between launches from the candidates seen so far.
+int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, int k,
+                    uint2* cand, int32_t* cand_count, double* bound, int* n_launches, int* n_refines, cudaStream_t stream);
 int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
 int tc_debug_norms(TcState* st, const TcPlan& p, long long n, float* norms4_out, double* nrm_out, int32_t* info,
                    cudaStream_t stream);

@@ -222,6 +222,8 @@ __device__ __forceinline__ void rr_distances(const T* __restrict__ X, long long 
 //                     dmax = max d2 over T  >=  the (k+1)-th smallest exact d2 of the row
 //                  2. a candidate outside T can only matter if its lower bound allows d2 <= dmax, i.e.
 //                     L_ij <= S^2 dmax - nrm_i + sigma_i; those are evaluated too, the rest are dropped
+//   orig       : tensor path: candidate columns are reference POSITIONS of the staged (permuted) order; orig maps
+//                them to rows when a candidate becomes a survivor
 //   nrm / norms4 / scale : exact ||z_i||^2, (.., .., .., sigma_i) and S of the staging (tensor path)
 //   bound      : per slot, every reference NOT in the candidate list is known to have d2 > bound
 //                (NULL -> +inf, i.e. the list is a guaranteed superset)
@@ -234,7 +236,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               long long cand_stride, int n_seg, const int32_t* __restrict__ cand_count,
               const double* __restrict__ bound, const double* __restrict__ nrm,
               const float4* __restrict__ norms4, const double* __restrict__ scale,
-              int k, int ncand_cap, int pmax,
+              const int32_t* __restrict__ orig, int k, int ncand_cap, int pmax,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
               unsigned long long* __restrict__ totals) {
@@ -344,7 +346,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     }
     const uint32_t kth_ord = prefix | 0xffu;     // every candidate sharing the (k+1)-th's top 24 bits is in T
     for (int c = tid; c < n; c += RR_THREADS) {
-      if (f2ord(cval[c]) <= kth_ord) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
+      if (f2ord(cval[c]) <= kth_ord) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = (uint32_t)orig[cid[c]]; }
     }
     __syncthreads();
     const int m1 = s_m;                          // >= k+1 (more only on equal lower bounds)
@@ -370,7 +372,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
       const double cut = S * S * dmax * (1.0 + 1e-12) - nrm[row] * (1.0 - 1e-12) + (double)norms4[row].w + 1e-300;
       for (int c = tid; c < n; c += RR_THREADS) {
         const float l = cval[c];
-        if (f2ord(l) > kth_ord && (double)l <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = cid[c]; }
+        if (f2ord(l) > kth_ord && (double)l <= cut) { const int p = atomicAdd(&s_m, 1); if (p < pmax) id[p] = (uint32_t)orig[cid[c]]; }
       }
     }
     __syncthreads();
@@ -524,10 +526,11 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   const int32_t* rows, long long q_begin, long long n_slots,
                   const uint32_t* cand_idx, const uint2* cand_pair, long long cand_stride, int n_seg,
                   const int32_t* cand_count, const double* bound, const double* nrm, const float4* norms4,
-                  const double* scale, int k,
+                  const double* scale, const int32_t* orig, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream) {
+  if (cand_pair && !orig) { set_error("rerank: tensor-path candidates need the position -> row map"); return SBK_ERR_INVALID; }
   if (n_slots <= 0) return SBK_OK;
   // tensor path: all candidates staged (ncand_cap), survivors of the two-phase cut sorted in a
   // buffer of pmax entries; exact path: every candidate is a survivor
@@ -543,7 +546,7 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T, T, REGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     rerank_kernel<T, T, REGQ><<<grid, RR_THREADS, smem, stream>>>(                                                      \
         (const T*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale, \
-        k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);                                \
+        orig, k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);                                \
   } while (0)
   if (dtype == SBK_F32) {
     if (d <= RegQuery<float>::MAX_D) SBK_RR_LAUNCH(float, true); else SBK_RR_LAUNCH(float, false);

@@ -259,27 +259,38 @@ __global__ void tc_centre_kernel(const double* __restrict__ colsum, const double
   }
 }
 
-// One thread per staged row.  `src_rows` (optional) gathers a sample.
+// One thread per staged row.
 //   b_tiles : reference-side operand, tiles of `brows` rows:  -2*zh | n_hi n_mid n_lo | (-2*zh_c, -2*zl_c) per split column | 0
 //   a_tiles : query-side operand, tiles of TC_BM rows:        zh  |  1    1     1   | (  zl_c ,   zh_c ) per split column | 0
-//             (NULL for samples)
 // tile layout (FP16 elements): [kpad/8 chunks][R rows][8]  -> core matrices of 8 rows x 16 B
+// The REFERENCE side is stored in a pseudo-random order: row i goes to position p with i = (p * mult + off) mod n
+// (golden-ratio stride, a bijection since gcd(mult, n) = 1).  Any prefix of the staged references is then an
+// unbiased sample of all of them, whatever the order the caller's rows came in: the first `sample_size`
+// positions ARE the threshold sample, and the candidates of the first reference chunks refine the thresholds
+// for the later ones (tc_refine_kernel).  orig[p] = i maps a candidate position back to its row.
 template <typename T>
 __global__ void __launch_bounds__(128)
-tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
-                const int32_t* __restrict__ src_rows, long long n_staged,
+tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld, long long n_staged,
+                long long perm_minv, long long perm_off,
                 const double* __restrict__ centre, const double* __restrict__ scale, int kpad, int brows,
-                __half* __restrict__ b_tiles, __half* __restrict__ a_tiles,
+                __half* __restrict__ b_tiles, __half* __restrict__ a_tiles, int32_t* __restrict__ orig,
                 double* __restrict__ nrm, float4* __restrict__ norms4,
                 const TcScalars* __restrict__ sc) {
   const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
   if (row >= n_staged) return;
-  const long long bt = row / brows, br = row % brows;       // brows = reference rows per staged tile (256, or 128 for CTA pairs)
+  const bool real = row < n;
+  // position of this row on the reference side (padding rows keep their place behind the n real ones)
+  long long pos = row;
+  if (real) {
+    long long t = row - perm_off; if (t < 0) t += n;
+    pos = (long long)(((unsigned long long)t * (unsigned long long)perm_minv) % (unsigned long long)n);
+  }
+  orig[pos] = real ? (int32_t)row : 0x7fffffff;
+  const long long bt = pos / brows, br = pos % brows;       // brows = reference rows per staged tile (256, or 128 for CTA pairs)
   __half* bdst = b_tiles + bt * (long long)brows * kpad + br * 8;
-  __half* adst = nullptr;
-  if (a_tiles) { const long long at = row / TC_BM, ar = row % TC_BM; adst = a_tiles + at * (long long)TC_BM * kpad + ar * 8; }
-  const long long src = src_rows ? (long long)src_rows[row] : row;
-  const bool real = src_rows ? true : (row < n);
+  const long long at = row / TC_BM, ar = row % TC_BM;
+  __half* adst = a_tiles + at * (long long)TC_BM * kpad + ar * 8;
+  const long long src = row;
   const double S = scale[0];
   double n2 = 0.0, d2 = 0.0, zh2 = 0.0;
   const int nchunk = kpad / 8;
@@ -364,15 +375,87 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld,
       adst[(long long)(c1 >> 3) * TC_BM * 8 + (c1 & 7)] = __float2half_ru(real ? na : 0.f);
     }
   }
-  if (real && !src_rows) {
+  if (real) {
     nrm[row] = n2;
     norms4[row] = make_float4(nz, nd, na, l2f);
   }
 }
 
-__global__ void tc_sample_rows_kernel(int32_t* __restrict__ rows, int m, long long n, long long mult, long long off) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < m) rows[i] = (int32_t)(((long long)i * mult + off) % n);   // mult coprime to n -> no repeats for m <= n
+// Threshold and certificate bound of one query row from tau, an upper bound (with the planned confidence) of the
+// row's k+1 smallest LOWER bounds.  Their exact scores may be up to the per-pair slack higher: estimate that
+// slack for references at the threshold distance (norms of such neighbours from the triangle inequality); a
+// poor estimate only costs a fallback, the certificate is what guarantees exactness.
+__device__ __forceinline__ void tc_threshold(float tau, const float4 ni, double ni2, int kpad, int d, double S,
+                                             float* thr_out, double* bound_out) {
+  const double c_acc = tc_c_acc(kpad);
+  const double rho = sqrt(fmax(0.0, (double)tau + ni2));
+  const double zj = (double)ni.x + rho;
+  const double ratio = fmax(ni.x > 0.f ? (double)ni.y / (double)ni.x : 0.0, 1.220703125e-4);
+  float4 nj; nj.x = (float)zj; nj.y = (float)(ratio * zj + 6e-8 * sqrt((double)d)); nj.z = (float)zj; nj.w = ni.w;
+  const double margin = 1.05 * tc_pair_upper_slack(ni, nj, c_acc);
+  const float thr_f = __double2float_ru((double)tau + margin);
+  *thr_out = thr_f;
+  // every non-emitted j has L_ij > thr  =>  S^2 d2_ij - n_i = e_ij >= L_ij - ||l_i||^2 > thr - ||l_i||^2
+  *bound_out = ((double)thr_f - (double)ni.w + ni2) / (S * S) * (1.0 - 1e-13);
+}
+
+__device__ __forceinline__ uint32_t tc_f2ord(float f) {          // order-preserving float -> uint32
+  const uint32_t b = __float_as_uint(f);
+  return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float tc_ord2f(uint32_t u) {
+  return __uint_as_float(u ^ ((u >> 31) ? 0x80000000u : 0xffffffffu));
+}
+
+// Threshold refinement between filter launches.  After the first launches the candidate lists hold EVERY
+// reference with L <= thr among the first `fraction` of the (pseudo-randomly ordered) references: a sample
+// several times the size of the threshold sample.  The r-th smallest lower bound seen so far, r from the
+// binomial tail of "how many of the row's k nearest fall into the part seen", bounds the k+1 smallest lower
+// bounds of the row with the planned confidence: the threshold of the remaining launches drops to it (plus the
+// usual slack), which roughly halves the candidates they emit.  One warp per query row; rows with more than
+// 256 candidates so far, an overflowed segment or fewer than r candidates keep their threshold.
+static constexpr int TC_REFINE_MAX = 256;
+__global__ void __launch_bounds__(256)
+tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
+                 long long row_lo, long long n_rows, int r_stat,
+                 const float4* __restrict__ norms4, const double* __restrict__ nrm, const double* __restrict__ scale,
+                 int kpad, int d, float* __restrict__ thr, double* __restrict__ bound) {
+  const long long slot = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (slot >= n_rows) return;
+  const int seg_cap = cand_cap >> 2;
+  int c[4], n = 0; bool bad = false;
+#pragma unroll
+  for (int sgm = 0; sgm < 4; ++sgm) { c[sgm] = cand_count[slot * 4 + sgm]; bad |= c[sgm] > seg_cap; n += c[sgm]; }
+  if (bad || n < r_stat || n > TC_REFINE_MAX) return;
+  uint32_t key[TC_REFINE_MAX / 32];
+  const uint2* base = cand + slot * (long long)cand_cap;
+#pragma unroll
+  for (int u = 0; u < TC_REFINE_MAX / 32; ++u) {
+    int e = lane + 32 * u;
+    key[u] = 0xffffffffu;
+    if (e < n) {
+      int sgm = 0;
+      while (e >= c[sgm]) { e -= c[sgm]; ++sgm; }           // n <= sum of the four counts
+      key[u] = tc_f2ord(__uint_as_float(base[(long long)sgm * seg_cap + e].y));
+    }
+  }
+  // r-th smallest key = the largest v with #(keys < v) < r, built bit by bit
+  uint32_t res = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t t = res | (1u << bit);
+    int cnt = 0;
+#pragma unroll
+    for (int u = 0; u < TC_REFINE_MAX / 32; ++u) cnt += key[u] < t ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt < r_stat) res = t;
+  }
+  if (lane == 0) {
+    const long long grow = row_lo + slot;
+    float thr_new; double bound_new;
+    tc_threshold(tc_ord2f(res), norms4[grow], nrm[grow], kpad, d, scale[0], &thr_new, &bound_new);
+    if (thr_new < thr[slot]) { thr[slot] = thr_new; bound[slot] = bound_new; }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -394,7 +477,7 @@ struct TcArgs {
   // FILTER
   uint2* cand; int32_t* cand_count; int cand_cap;   // (column, score) pairs: 4 segments of cand_cap/4 per row
   // DUMP
-  float* dump; long long dump_ld;
+  float* dump; long long dump_ld; const int32_t* orig;
 };
 
 template <int CG> __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -635,13 +718,14 @@ tc_kernel(const TcArgs p) {
           gmin[c] = fminf(gmin[c], fminf(__uint_as_float(va[c]), __uint_as_float(vb[c])));
       } else if (MODE == TC_PROBE_LDONLY) {
         if (va[0] == 0x7fc12345u && vb[31] == 0x7fc12345u) ++probe_hits;   // keeps the loads alive
-      } else {   // TC_DUMP
+      } else {   // TC_DUMP: positions -> original columns
         if (row_ok) {
           const long long j0 = (p.bt0 + t) * TC_BN + w4 * 64;
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
-            p.dump[slot * p.dump_ld + j0 + c] = __uint_as_float(va[c]);
-            p.dump[slot * p.dump_ld + j0 + 32 + c] = __uint_as_float(vb[c]);
+            const int32_t o0 = p.orig[j0 + c], o1 = p.orig[j0 + 32 + c];
+            if (o0 != 0x7fffffff) p.dump[slot * p.dump_ld + o0] = __uint_as_float(va[c]);
+            if (o1 != 0x7fffffff) p.dump[slot * p.dump_ld + o1] = __uint_as_float(vb[c]);
           }
         }
       }
@@ -673,23 +757,10 @@ tc_kernel(const TcArgs p) {
           if (cnt_eq == 0) break;                                   // fewer distinct values than r
           taken += cnt_eq; last = m; tau = m;
         }
-        // tau bounds the k+1 smallest LOWER bounds; their exact scores may be up to the per-pair
-        // slack higher.  Estimate that slack for references at the threshold distance (norms of
-        // such neighbours from the triangle inequality); a poor estimate only costs a fallback,
-        // the certificate below is what guarantees exactness.
-        const float4 ni = p.norms4[grow];
-        const double ni2 = p.nrm[grow];
-        const double c_acc = tc_c_acc(kpad);
-        const double rho = sqrt(fmax(0.0, (double)tau + ni2));
-        const double zj = (double)ni.x + rho;
-        const double ratio = fmax(ni.x > 0.f ? (double)ni.y / (double)ni.x : 0.0, 1.220703125e-4);
-        float4 nj; nj.x = (float)zj; nj.y = (float)(ratio * zj + 6e-8 * sqrt((double)p.d)); nj.z = (float)zj; nj.w = ni.w;
-        const double margin = 1.05 * tc_pair_upper_slack(ni, nj, c_acc);
-        const float thr_f = __double2float_ru((double)tau + margin);
-        const double S = p.scale[0];
+        float thr_f; double bound_f;
+        tc_threshold(tau, p.norms4[grow], p.nrm[grow], kpad, p.d, p.scale[0], &thr_f, &bound_f);
         p.thr[slot] = thr_f;
-        // every non-emitted j has L_ij > thr  =>  S^2 d2_ij - n_i = e_ij >= L_ij - ||l_i||^2 > thr - ||l_i||^2
-        p.bound[slot] = ((double)thr_f - (double)ni.w + ni2) / (S * S) * (1.0 - 1e-13);
+        p.bound[slot] = bound_f;
       }
     }
   }
@@ -777,14 +848,13 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
   (void)n_a;   // A tiles are staged by the same kernel that walks the n_b padded rows
   st->a_tiles = a.take<__half>((size_t)n_b * p.kpad_alloc);
   st->b_tiles = a.take<__half>((size_t)n_b * p.kpad_alloc);
-  st->s_tiles = a.take<__half>((size_t)p.sample_size * p.kpad_alloc);
   st->centre = a.take<double>(4096);
   st->colsum = a.take<double>(2 * 4096);     // column sums, then column sums of squares
   st->scale = a.take<double>(8);
   st->nrm = a.take<double>((size_t)n_b);
   st->norms4 = a.take<float4>((size_t)n_b);
   st->sc = a.take<TcScalars>(2);
-  st->sample_rows = a.take<int32_t>((size_t)p.sample_size);
+  st->orig = a.take<int32_t>((size_t)n_b);
   st->thr = a.take<float>((size_t)chunk + TC_BM);
   st->maxabs = a.take<unsigned long long>(8);
 }
@@ -818,6 +888,18 @@ static long long coprime_multiplier(long long n) {
   auto gcd = [](long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; };
   while (gcd(m, n) != 1) ++m;
   return m;
+}
+
+// a^-1 mod n for gcd(a, n) = 1 (extended Euclid)
+static long long mod_inverse(long long a, long long n) {
+  long long t = 0, nt = 1, r = n, nr = a % n;
+  while (nr != 0) {
+    const long long q = r / nr;
+    long long tmp = t - q * nt; t = nt; nt = tmp;
+    tmp = r - q * nr; r = nr; nr = tmp;
+  }
+  if (t < 0) t += n;
+  return t;
 }
 
 int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
@@ -854,25 +936,17 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   st->cg = tc_cta_group();
   st->nstage = tc_pick_stages(p.kpad, st->cg);
   if (p.kpad > p.kpad_alloc || st->nstage == 0) { set_error("tensor kNN: operand width %d exceeds the staged capacity", p.kpad); return SBK_ERR_INTERNAL; }
+  // pseudo-random (golden-ratio stride) order of the reference side: position p holds row (p * mult + off) mod n
+  st->perm_mult = coprime_multiplier(n_ref);
+  st->perm_off = n_ref / 3;
+  st->perm_minv = mod_inverse(st->perm_mult, n_ref);
   const unsigned sb = (unsigned)((n_b + 127) / 128);
   if (dtype == SBK_F32)
-    tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad, TC_BN / st->cg,
-                                                   st->b_tiles, st->a_tiles, st->nrm, st->norms4, st->sc);
+    tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, n_b, st->perm_minv, st->perm_off, st->centre, st->scale,
+                                                   p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc);
   else
-    tc_stage_kernel<double><<<sb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, nullptr, n_b, st->centre, st->scale, p.kpad, TC_BN / st->cg,
-                                                    st->b_tiles, st->a_tiles, st->nrm, st->norms4, st->sc);
-  SBK_LAUNCH_CHECK();
-  // pseudo-random (golden-ratio stride) sample without repeats
-  const long long mult = coprime_multiplier(n_ref);
-  tc_sample_rows_kernel<<<(p.sample_size + 255) / 256, 256, 0, stream>>>(st->sample_rows, p.sample_size, n_ref, mult, n_ref / 3);
-  SBK_LAUNCH_CHECK();
-  const unsigned ssb = (unsigned)((p.sample_size + 127) / 128);
-  if (dtype == SBK_F32)
-    tc_stage_kernel<float><<<ssb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
-                                                    p.kpad, TC_BN / st->cg, st->s_tiles, nullptr, nullptr, nullptr, st->sc);
-  else
-    tc_stage_kernel<double><<<ssb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, st->sample_rows, p.sample_size, st->centre, st->scale,
-                                                     p.kpad, TC_BN / st->cg, st->s_tiles, nullptr, nullptr, nullptr, st->sc);
+    tc_stage_kernel<double><<<sb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, n_b, st->perm_minv, st->perm_off, st->centre, st->scale,
+                                                    p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc);
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
@@ -917,12 +991,19 @@ int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
   TcArgs a; long long n_mtiles;
   tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
   a.bound = bound;
-  a.b_tiles = st->s_tiles; a.n_btiles = p.sample_size / TC_BN;
+  a.b_tiles = st->b_tiles; a.n_btiles = p.sample_size / TC_BN;   // the first staged references are the sample
   return tc_launch<TC_SAMPLE>(a, n_mtiles, st->cg, stream);
 }
 
-int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows,
-                    uint2* cand, int32_t* cand_count, int* n_launches, cudaStream_t stream) {
+// smallest r with P(Binomial(n, p) >= r) <= eps
+static int binom_quantile(int n, double p, double eps) {
+  int r = (int)(n * p);
+  while (r <= n && binom_tail_ge(n, p, r) > eps) ++r;
+  return r;
+}
+
+int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, int k,
+                    uint2* cand, int32_t* cand_count, double* bound, int* n_launches, int* n_refines, cudaStream_t stream) {
   TcArgs a; long long n_mtiles;
   tc_chunk_args(st, p, row0, n_rows, a, n_mtiles);
   a.cand = cand; a.cand_count = cand_count;
@@ -934,15 +1015,29 @@ int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
   const long long per = std::max<long long>(1, TC_L2_CHUNK_BYTES / (long long)p.stage_bytes);
   const long long n_launch = (p.n_tiles + per - 1) / per;
   const long long even = (p.n_tiles + n_launch - 1) / n_launch;
-  for (long long b0 = 0; b0 < p.n_tiles; b0 += even) {
+  static const int probe = getenv("SBK_TC_PROBE") ? atoi(getenv("SBK_TC_PROBE")) : 0;
+  static const int refine = getenv("SBK_TC_REFINE") ? atoi(getenv("SBK_TC_REFINE")) : 1;
+  int li = 0;
+  for (long long b0 = 0; b0 < p.n_tiles; b0 += even, ++li) {
     a.bt0 = b0; a.n_btiles = std::min(even, p.n_tiles - b0);
-    static const int probe = getenv("SBK_TC_PROBE") ? atoi(getenv("SBK_TC_PROBE")) : 0;
     int rc = probe == 3 ? tc_launch<TC_PROBE_NOLD>(a, n_mtiles, st->cg, stream)
            : probe == 4 ? tc_launch<TC_PROBE_LDONLY>(a, n_mtiles, st->cg, stream)
            : probe == 5 ? tc_launch<TC_PROBE_NOAPPEND>(a, n_mtiles, st->cg, stream)
                         : tc_launch<TC_FILTER>(a, n_mtiles, st->cg, stream);
     if (rc) return rc;
     if (n_launches) ++*n_launches;
+    // threshold refinement from the candidates seen so far (after launches 1, 2 and 4; later ones gain little)
+    const long long seen = std::min<long long>(st->n_ref, (b0 + a.n_btiles) * TC_BN);
+    if (refine && probe == 0 && b0 + even < p.n_tiles && (li == 0 || li == 1 || li == 3)) {
+      const double f = (double)seen / (double)st->n_ref;
+      const int r = binom_quantile(k, f, 2e-6) + 1;       // +1: the row itself is always among the seen or unseen k+1
+      if (r <= TC_REFINE_MAX / 2) {
+        tc_refine_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, row0, n_rows, r,
+                                                                          st->norms4, st->nrm, st->scale, p.kpad, st->d, st->thr, bound);
+        SBK_LAUNCH_CHECK();
+        if (n_refines) ++*n_refines;
+      }
+    }
   }
   return SBK_OK;
 }
@@ -952,7 +1047,7 @@ int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long
   a.a_tiles = st->a_tiles; a.b_tiles = st->b_tiles; a.n_btiles = p.n_tiles;
   a.kpad = p.kpad; a.nstage = st->nstage;
   a.tile_m0 = 0; a.row_lo = 0; a.row_hi = n_q;
-  a.dump = out; a.dump_ld = out_ld;
+  a.dump = out; a.dump_ld = out_ld; a.orig = st->orig;
   return tc_launch<TC_DUMP>(a, (n_q + TC_BM - 1) / TC_BM, st->cg, stream);
 }
 
