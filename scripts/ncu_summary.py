@@ -32,5 +32,7 @@ for rep in sys.argv[1:]:
         d = dict(zip(hdr, r))
         print(f'== {rep} :: {d.get("Kernel Name", "?")[:100]}  grid={d.get("Grid Size")} block={d.get("Block Size")}')
         for kname in KEYS:
-            if kname in d:
-                print(f'  {kname:95s} {d[kname]:>18s} {units[hdr.index(kname)]}')
+            # some raw-page columns carry a section prefix ("TPC.TriageCompute.sm__pipe_tensor_...")
+            hit = [h for h in hdr if h == kname or h.endswith('.' + kname)]
+            for h in hit[:1]:
+                print(f'  {kname:95s} {d[h]:>18s} {units[hdr.index(h)]}')

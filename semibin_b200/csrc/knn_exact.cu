@@ -64,44 +64,48 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
     for (int qi = 0; qi < XF_QT; ++qi) acc[qi] = 0.0;
     if (valid) {
       const T* y = X + j * ld;
-      // 16 columns per step: the loads of a step are independent (memory-level parallelism),
-      // 16-byte vector loads when the row is aligned
+      // STEP columns per step: the loads of a step are independent (memory-level parallelism), 16-byte vector
+      // loads when the row is aligned.  With a single query row per CTA the arithmetic is negligible and the loop
+      // is pure load latency: 48 (24) columns in flight per thread instead of 16.
+      constexpr int STEP = XF_QT == 1 ? (sizeof(T) == 4 ? 48 : 24) : 16;
+      constexpr int VEC = 16 / sizeof(T);
       const bool vec_ok = ((((uintptr_t)y) & 15) == 0);
-      for (int c0 = 0; c0 < d; c0 += 16) {
-        double yv[16];
-        const int nc = min(16, d - c0);
-        if (vec_ok && nc == 16) {
+      for (int c0 = 0; c0 < d; c0 += STEP) {
+        T yv[STEP];
+        const int nc = min(STEP, d - c0);
+        if (vec_ok && nc == STEP) {
           if (sizeof(T) == 4) {
             const float4* y4 = reinterpret_cast<const float4*>(y + c0);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < STEP / VEC; ++u) {
               const float4 f = __ldg(y4 + u);
-              yv[4 * u] = (double)f.x; yv[4 * u + 1] = (double)f.y; yv[4 * u + 2] = (double)f.z; yv[4 * u + 3] = (double)f.w;
+              yv[4 * u] = (T)f.x; yv[4 * u + 1] = (T)f.y; yv[4 * u + 2] = (T)f.z; yv[4 * u + 3] = (T)f.w;
             }
           } else {
             const double2* y2 = reinterpret_cast<const double2*>(y + c0);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+            for (int u = 0; u < STEP / VEC; ++u) {
               const double2 f = __ldg(y2 + u);
-              yv[2 * u] = f.x; yv[2 * u + 1] = f.y;
+              yv[2 * u] = (T)f.x; yv[2 * u + 1] = (T)f.y;
             }
           }
         } else {
 #pragma unroll
-          for (int u = 0; u < 16; ++u) yv[u] = (u < nc) ? (double)__ldg(y + c0 + u) : 0.0;
+          for (int u = 0; u < STEP; ++u) yv[u] = (u < nc) ? __ldg(y + c0 + u) : (T)0;
         }
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
+        for (int u = 0; u < STEP; ++u) {
           if (u < nc) {
+            const double yu = (double)yv[u];
             if (XF_QT == 1) {
-              const double t0 = qs[c0 + u] - yv[u];
+              const double t0 = qs[c0 + u] - yu;
               acc[0] = fma(t0, t0, acc[0]);
             } else {
               const double2* q2 = reinterpret_cast<const double2*>(qs + (size_t)(c0 + u) * XF_QT);
 #pragma unroll
               for (int h = 0; h < XF_QT / 2; ++h) {
                 double2 qq = q2[h];
-                double t0 = qq.x - yv[u], t1 = qq.y - yv[u];
+                double t0 = qq.x - yu, t1 = qq.y - yu;
                 acc[2 * h] = fma(t0, t0, acc[2 * h]);
                 acc[2 * h + 1] = fma(t1, t1, acc[2 * h + 1]);
               }

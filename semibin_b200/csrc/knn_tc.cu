@@ -70,10 +70,10 @@ enum TcMode { TC_SAMPLE = 0, TC_FILTER = 1, TC_DUMP = 2,
               TC_PROBE_NOAPPEND = 5 };// filter epilogue without the candidate append (min tree + threshold test only)
 
 // bytes of the reference-tile ring; at least the SAMPLE epilogue's scratch
-// ([TC_NGROUP][TC_BM] floats) which reuses it once the pipeline has drained
+// ([TC_BM][TC_NGROUP + 1] floats) which reuses it once the pipeline has drained
 __host__ __device__ static inline size_t tc_ring_bytes(int kpad, int nstage, int cg) {
   const size_t ring = (size_t)nstage * (TC_BN / cg) * kpad * 2;
-  const size_t scratch = (size_t)TC_NGROUP * TC_BM * 4;
+  const size_t scratch = (size_t)(TC_NGROUP + 1) * TC_BM * 4;
   return ring > scratch ? ring : scratch;
 }
 
@@ -705,6 +705,22 @@ tc_kernel(const TcArgs p) {
         }
         continue;
       }
+      if (MODE == TC_SAMPLE) {
+        // one 32-column half at a time: with both halves AND the 32 running minima live the kernel exceeds its
+        // 96 registers and spills the minima every tile (50 local-memory accesses per warp and tile)
+        tmem_ld32(taddr, va);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(va[c]));
+        tmem_ld32(taddr + 32, va);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(va[c]));
+        continue;
+      }
       tmem_ld32(taddr, va);
       tmem_ld32(taddr + 32, vb);
       tmem_ld_wait();
@@ -712,11 +728,7 @@ tc_kernel(const TcArgs p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
-      if (MODE == TC_SAMPLE) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          gmin[c] = fminf(gmin[c], fminf(__uint_as_float(va[c]), __uint_as_float(vb[c])));
-      } else if (MODE == TC_PROBE_LDONLY) {
+      if (MODE == TC_PROBE_LDONLY) {
         if (va[0] == 0x7fc12345u && vb[31] == 0x7fc12345u) ++probe_hits;   // keeps the loads alive
       } else {   // TC_DUMP: positions -> original columns
         if (row_ok) {
@@ -741,26 +753,35 @@ tc_kernel(const TcArgs p) {
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
       // all MMAs have retired (last tfull observed by every epilogue warp) -> the B ring
       // is free: use it as scratch
-      float* gm = reinterpret_cast<float*>(sB);                    // [TC_NGROUP][TC_BM]
+      float* gm = reinterpret_cast<float*>(sB);                    // [TC_BM rows][TC_NGROUP + 1]: conflict-free both ways
 #pragma unroll
-      for (int c = 0; c < 32; ++c) gm[(w4 * 32 + c) * TC_BM + r_in_tile] = gmin[c];
+      for (int c = 0; c < 32; ++c) gm[r_in_tile * (TC_NGROUP + 1) + w4 * 32 + c] = gmin[c];
       asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-      if (w4 == 0 && row_ok) {
-        // r-th smallest of the TC_NGROUP group minima (selection by repeated min)
-        float last = -INFINITY; int taken = 0; float tau = INFINITY;
-        while (taken < p.order_stat) {
-          float m = INFINITY; int cnt_eq = 0;
-          for (int g = 0; g < TC_NGROUP; ++g) {
-            const float x = gm[g * TC_BM + r_in_tile];
-            if (x > last) { if (x < m) { m = x; cnt_eq = 1; } else if (x == m) ++cnt_eq; }
-          }
-          if (cnt_eq == 0) break;                                   // fewer distinct values than r
-          taken += cnt_eq; last = m; tau = m;
+      // r-th smallest of each row's TC_NGROUP group minima: one warp per row (8 rows per warp), four ordered keys
+      // per lane, the answer built bit by bit from warp-wide counts (32 short steps instead of r serial scans
+      // of all groups by one thread, which cost more than the sample's MMAs)
+      for (int rr = 0; rr < TC_BM / TC_EPI_WARPS; ++rr) {
+        const int r_sel = warp * (TC_BM / TC_EPI_WARPS) + rr;
+        const long long grow_sel = tile_m * TC_BM + r_sel;
+        if (grow_sel < p.row_lo || grow_sel >= p.row_hi) continue;  // warp-uniform
+        uint32_t key[TC_NGROUP / 32];
+#pragma unroll
+        for (int u = 0; u < TC_NGROUP / 32; ++u) key[u] = tc_f2ord(gm[r_sel * (TC_NGROUP + 1) + lane + 32 * u]);
+        uint32_t res = 0;                                            // largest v with #(keys < v) < r
+        for (int bit = 31; bit >= 0; --bit) {
+          const uint32_t tv = res | (1u << bit);
+          int cnt = 0;
+#pragma unroll
+          for (int u = 0; u < TC_NGROUP / 32; ++u) cnt += key[u] < tv ? 1 : 0;
+          cnt = __reduce_add_sync(0xffffffffu, cnt);
+          if (cnt < p.order_stat) res = tv;
         }
-        float thr_f; double bound_f;
-        tc_threshold(tau, p.norms4[grow], p.nrm[grow], kpad, p.d, p.scale[0], &thr_f, &bound_f);
-        p.thr[slot] = thr_f;
-        p.bound[slot] = bound_f;
+        if (lane == 0) {
+          float thr_f; double bound_f;
+          tc_threshold(tc_ord2f(res), p.norms4[grow_sel], p.nrm[grow_sel], kpad, p.d, p.scale[0], &thr_f, &bound_f);
+          p.thr[grow_sel - p.row_lo] = thr_f;
+          p.bound[grow_sel - p.row_lo] = bound_f;
+        }
       }
     }
   }
