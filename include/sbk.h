@@ -163,6 +163,27 @@ int sbk_dbscan_labels(const int32_t* idx, int64_t n, int32_t k,
                       const int32_t* prefix_len, const uint8_t* core, int32_t n_eps,
                       long long* labels, void* workspace, size_t ws_bytes, void* cuda_stream);
 
+size_t sbk_integrate_workspace_bytes(int64_t n, int32_t n_results);
+
+/* Long-read ensemble integration: the greedy bin extraction of
+ * SemiBin/long_read_cluster.py:12-49 (get_best_bin) and :122-150 (the loop and the final labels).
+ *   labels       : long long[n_results * n], DBSCAN labels of every result (-1 = noise), device
+ *   lengths      : long long[n], contig lengths (len(contig_dict[name])), device
+ *   marker_masks : uint64[n * mask_words], bit m set iff the contig carries marker m (each marker at
+ *                  most once per contig, markers.py:63), device
+ *   n_markers    : the recall denominator (107, long_read_cluster.py:35)
+ *   out_labels   : long long[n], index of the extraction that took the contig, or -1, device
+ *   n_extracted  : host int, number of bins extracted
+ * Every bin of every result is scored as in :26-46 (length >= minfasta, at least one marker, contamination
+ * step, F1 in the reference's floating-point operation order, ties to the smaller length and then to the
+ * bin met LAST), the winner's contigs are retired from all results and the loop repeats until the
+ * remaining length is below minfasta, one contig is left (it becomes a bin) or no bin qualifies.
+ * Synchronises `cuda_stream`. */
+int sbk_integrate(const long long* labels, int32_t n_results, int64_t n, const long long* lengths,
+                  const unsigned long long* marker_masks, int32_t mask_words, int32_t n_markers,
+                  int64_t minfasta, long long* out_labels, int32_t* n_extracted,
+                  void* workspace, size_t ws_bytes, void* cuda_stream);
+
 /* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
  * MMA pipeline as the tensor filter and returns the accumulator values
  *   L[i,j] <= S^2 d2_ij - nrm_i + norms4[i].w      (i < n_q, j < n_ref <= 65536)

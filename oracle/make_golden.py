@@ -136,10 +136,36 @@ def cal_kl():
     np.savez_compressed(os.path.join(OUT, 'cal_kl.npz'), **out)
 
 
+def integrate():
+    """long_read_cluster.py:12-49,122-150 run with the reference's own get_best_bin."""
+    from collections import defaultdict
+    from oracle import integrate as oi
+    out = {}
+
+    def run(labels, lengths, markers, minfasta):
+        n = labels.shape[1]
+        names = [f'c{i}' for i in range(n)]
+        cd = {nm: 'A' * int(l) for nm, l in zip(names, lengths)}
+        c2m = defaultdict(list, {nm: [f'm{j}' for j in m] for nm, m in zip(names, markers) if len(m)})
+        ext, lab = oi.reference_loop([l.tolist() for l in labels], c2m, names, cd, minfasta)
+        return np.asarray(lab, dtype=np.int64)
+
+    for seed in range(24):
+        labels, lengths, markers, minfasta = oi.random_case(seed)
+        out[f'rand{seed}'] = run(labels, lengths, markers, minfasta)
+    for n, seed, minfasta in ((1500, 5, 20000), (2500, 6, 200000)):
+        labels, lengths, markers = oi.synth_case(n, seed)
+        out[f'synth{n}'] = run(labels, lengths, markers, minfasta)
+    np.savez_compressed(os.path.join(OUT, 'integrate.npz'), **out)
+
+
 if __name__ == '__main__':
     warnings.simplefilter('ignore')
     os.makedirs(OUT, exist_ok=True)
     import sklearn
     assert sklearn.__version__.startswith('1.9'), sklearn.__version__
-    for fn in (bin_data, ties, synth_knn, synth_edges, synth_dbscan, cal_kl):
+    only = sys.argv[1:]
+    for fn in (bin_data, ties, synth_knn, synth_edges, synth_dbscan, cal_kl, integrate):
+        if only and fn.__name__ not in only:
+            continue
         fn(); print('wrote', fn.__name__)

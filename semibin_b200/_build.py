@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libsbk.so')
-SOURCES = ['api.cu', 'knn_exact.cu', 'knn_tc.cu', 'edges.cu', 'radius.cu', 'scan.cu']
+SOURCES = ['api.cu', 'knn_exact.cu', 'knn_tc.cu', 'edges.cu', 'radius.cu', 'scan.cu', 'integrate.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 

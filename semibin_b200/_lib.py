@@ -57,6 +57,9 @@ SIGNATURES = {
     'sbk_dbscan_labels_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_dbscan_labels': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sbk_integrate_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
+    'sbk_integrate': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                C.c_int64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
     'sbk_debug_tc_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_debug_tc_scores': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

@@ -8,8 +8,13 @@ SemiBin/long_read_cluster.py:51-161.
         all eps values in one pass (the 12-value loop of :115-120)
     long_read_labels(embedding, depth, lengths, ...) -> [12 label vectors]
         features concat (:75-81) + kNN graph (:108-113) + sweep (:115-120)
-    cluster_long_read(...)   reference signature; the consumer part (marker genes,
-        get_best_bin, write_bins) is delegated to the reference package.
+    integrate_labels(labels, lengths, markers, minfasta) -> (contig_labels, n_bins)
+        the greedy ensemble integration (get_best_bin + extraction loop, :12-49, :122-150)
+    integrate_bins(dbscan_results, contig2marker, contig_list, contig_dict, minfasta) -> extracted
+        same, on the reference's own Python objects (lists / dicts of names)
+    cluster_long_read(...)   reference signature: the body of :51-161 with the kNN graph, the
+        DBSCAN sweep and the integration loop on the GPU; marker-gene search and bin
+        writing are the reference package's (out of scope).
 """
 import ctypes as C
 import numpy as np
@@ -159,18 +164,128 @@ class _SweepCache:
         return self.res[eps]
 
 
+N_MARKERS = 107            # recall denominator, long_read_cluster.py:35
+
+
+def marker_masks(markers, n=None):
+    """list (per contig) of marker ids -> uint64 [N, words] bit masks (ids < 256)."""
+    n = len(markers) if n is None else n
+    top = max((int(np.max(m)) for m in markers if len(m)), default=0)
+    words = top // 64 + 1
+    if words > 4:
+        raise ValueError(f'{top + 1} distinct markers: at most 256 are supported')
+    masks = np.zeros((n, words), dtype=np.uint64)
+    rows = np.repeat(np.arange(n), [len(m) for m in markers])
+    if len(rows):
+        ids = np.concatenate([np.asarray(m, dtype=np.int64) for m in markers if len(m)])
+        np.bitwise_or.at(masks, (rows, ids // 64), np.uint64(1) << (ids % 64).astype(np.uint64))
+    return masks
+
+
+def integrate_labels(labels, lengths, markers, minfasta, n_markers=N_MARKERS):
+    """Greedy ensemble integration on the GPU.  labels: [R, N] int64 (CUDA tensor or array; -1 noise),
+    lengths: [N] ints, markers: per-contig marker-id lists or a uint64 [N, words] mask array.
+    Returns (contig_labels np.int64 [N] with -1 = unbinned, number of bins), identical to
+    long_read_cluster.py:122-150."""
+    import torch
+    _lib.require_cuda()
+    lib = _lib.load()
+    if not isinstance(labels, torch.Tensor):
+        labels = torch.from_numpy(np.ascontiguousarray(np.asarray(labels, dtype=np.int64)))
+    labels = labels.to(device='cuda', dtype=torch.int64).contiguous()
+    R, N = labels.shape
+    masks = markers if isinstance(markers, np.ndarray) and markers.dtype == np.uint64 else marker_masks(markers, N)
+    if masks.shape[0] != N:
+        raise ValueError('one marker list per contig expected')
+    md = torch.from_numpy(np.ascontiguousarray(masks).view(np.int64)).cuda()
+    ld = torch.from_numpy(np.ascontiguousarray(np.asarray(lengths, dtype=np.int64))).cuda()
+    out = torch.empty((N,), dtype=torch.int64, device='cuda')
+    ws_bytes = lib.sbk_integrate_workspace_bytes(N, R)
+    if ws_bytes == 0:
+        raise ValueError(f'integrate: unsupported shape R={R}, N={N}')
+    ws = _workspace(ws_bytes, labels.device)
+    n_ext = C.c_int32(0)
+    rc = lib.sbk_integrate(_lib.ptr(labels), R, N, _lib.ptr(ld), _lib.ptr(md), masks.shape[1], int(n_markers),
+                           int(minfasta), _lib.ptr(out), C.byref(n_ext), _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc)
+    return out.cpu().numpy(), int(n_ext.value)
+
+
+def integrate_bins(dbscan_results, contig2marker, contig_list, contig_dict, minfasta):
+    """The reference's objects in, `extracted` (list of lists of contig names, in extraction order, names in
+    contig_list order) out: long_read_cluster.py:122-143."""
+    names = list(contig_list)
+    marker_id = {}
+    per_contig = []
+    for name in names:
+        ms = contig2marker[name] if name in contig2marker else []
+        per_contig.append(np.array(sorted({marker_id.setdefault(m, len(marker_id)) for m in ms}), dtype=np.int64))
+    lengths = np.array([len(contig_dict[name]) for name in names], dtype=np.int64)
+    labels = np.asarray([np.asarray(r, dtype=np.int64) for r in dbscan_results])
+    lab, n_ext = integrate_labels(labels, lengths, per_contig, minfasta)
+    extracted = [[] for _ in range(n_ext)]
+    for name, l in zip(names, lab):
+        if l >= 0:
+            extracted[l].append(name)
+    return extracted
+
+
 def cluster_long_read(logger, model, data, device, is_combined, n_sample, out, contig_dict, *,
                       binned_length, args, minfasta):
-    """Reference signature (long_read_cluster.py:51-53).  Runs the reference's
-    own function with its two hot call sites -- `kneighbors_graph` (:108) and
-    `dbscan` (:117) -- bound to the GPU implementations; marker-gene scoring,
-    get_best_bin and bin writing stay the reference's code (out of scope)."""
-    import SemiBin.long_read_cluster as ref
-    from .neighbors import kneighbors_graph
-    saved = (ref.kneighbors_graph, ref.dbscan)
-    ref.kneighbors_graph, ref.dbscan = kneighbors_graph, _SweepCache()
-    try:
-        return ref.cluster_long_read(logger, model, data, device, is_combined, n_sample, out, contig_dict,
-                                     binned_length=binned_length, args=args, minfasta=minfasta)
-    finally:
-        ref.kneighbors_graph, ref.dbscan = saved
+    """Reference signature and behaviour (long_read_cluster.py:51-161).  The embedding forward, the marker-gene
+    search (estimate_seeds / get_marker) and write_bins are the reference package's own functions; the kNN
+    graph (:108-113), the 12 DBSCAN runs (:115-120) and the integration loop (:122-150) run on the GPU."""
+    import os
+    import shutil
+    import tempfile
+    import pandas as pd
+    import torch
+    from SemiBin.utils import write_bins, norm_abundance
+    from SemiBin.markers import estimate_seeds, get_marker
+    contig_list = data.index.tolist()
+    if not is_combined:                                                          # :57-65
+        train_data_input = data.values[:, 0:136]
+    else:
+        train_data_input = data.values
+        if norm_abundance(train_data_input):
+            from sklearn.preprocessing import normalize
+            norm = np.sum(train_data_input, axis=0)
+            train_data_input = train_data_input / norm
+            train_data_input = normalize(train_data_input, axis=1, norm='l1')
+    with torch.no_grad():                                                        # :67-70
+        model.eval()
+        x = torch.from_numpy(train_data_input).to(device)
+        embedding = model.embedding(x.float()).detach().cpu().numpy()
+    length_weight = np.array([len(contig_dict[name]) for name in contig_list])  # :72-73
+    depth = None if is_combined else data.values[:, 136:len(data.values[0])].astype(np.float32)
+    with tempfile.TemporaryDirectory() as tdir:                                  # :83-99
+        cfasta = os.path.join(tdir, 'concatenated.fna')
+        with open(cfasta, 'wt') as concat_out:
+            for h in contig_list:
+                concat_out.write(f'>{h}\n{contig_dict[h]}\n')
+        estimate_seeds(cfasta, binned_length, args.num_process, output=out, orf_finder=args.orf_finder,
+                       prodigal_output_faa=args.prodigal_output_faa)
+        contig2marker = get_marker(os.path.join(out, 'markers.hmmout'), orf_finder=args.orf_finder,
+                                   min_contig_len=binned_length, fasta_path=cfasta, contig_to_marker=True)
+    output_bin_path = os.path.join(out, 'output_bins')                           # :101-105
+    if os.path.exists(output_bin_path):
+        logger.warning(f'Previous output directory `{output_bin_path}` found. Over-writing it.')
+        shutil.rmtree(output_bin_path)
+    os.makedirs(output_bin_path, exist_ok=True)
+    logger.debug('Running DBSCAN.')
+    dbscan_results = long_read_labels(embedding, depth, length_weight, n_sample=n_sample, is_combined=is_combined)
+    logger.debug('Integrating results.')
+    extracted = integrate_bins(dbscan_results, contig2marker if len(contig2marker) else {}, contig_list, contig_dict,
+                               minfasta)
+    contig2ix = {}                                                               # :145-150
+    for i, cs in enumerate(extracted):
+        for c in cs:
+            contig2ix[c] = i
+    namelist = data.index.tolist()
+    contig_labels = [contig2ix.get(c, -1) for c in namelist]
+    written = write_bins(namelist, contig_labels, output_bin_path, contig_dict, minfasta=minfasta,
+                         output_tag=args.output_tag, output_compression=args.output_compression)
+    logger.info(f'Number of bins: {len(written)}')
+    written.to_csv(os.path.join(out, 'bins_info.tsv'), index=False, sep='\t')
+    pd.DataFrame({'contig': namelist, 'bin': contig_labels}).to_csv(os.path.join(out, 'contig_bins.tsv'), index=False,
+                                                                    sep='\t')

@@ -100,3 +100,32 @@ def tie_grid(n, d=24, seed=3, dtype=np.float32, n_dup=0):
     if n_dup:
         x[-n_dup:] = x[0]
     return np.ascontiguousarray(x)
+
+
+def marker_table(genome, lengths, seed=20240, n_markers=107, completeness=(0.4, 1.0), dup_rate=0.03):
+    """Single-copy marker genes per contig for the long-read ensemble step
+    (SemiBin/long_read_cluster.py:12-49 consumes contig -> [marker names]).  Every
+    genome carries a random subset of the `n_markers` markers (its completeness),
+    each placed on one of its contigs with probability proportional to length; a
+    few markers are duplicated on a second contig (contamination).  Returns a list
+    of sorted int arrays, one per contig (each marker at most once per contig, as
+    SemiBin/markers.py:63 guarantees)."""
+    rng = np.random.default_rng(seed + 11)
+    n = len(genome)
+    per_contig = [[] for _ in range(n)]
+    order = np.argsort(genome, kind='stable')
+    bounds = np.flatnonzero(np.diff(genome[order])) + 1
+    for members in np.split(order, bounds):
+        frac = rng.uniform(*completeness)
+        present = np.flatnonzero(rng.random(n_markers) < frac)
+        w = lengths[members].astype(np.float64)
+        w /= w.sum()
+        home = rng.choice(members, size=len(present), p=w)
+        for m, c in zip(present, home):
+            per_contig[c].append(int(m))
+        dup = present[rng.random(len(present)) < dup_rate]
+        for m in dup:
+            c = int(rng.choice(members, p=w))
+            if int(m) not in per_contig[c]:
+                per_contig[c].append(int(m))
+    return [np.array(sorted(v), dtype=np.int32) for v in per_contig]

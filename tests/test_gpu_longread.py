@@ -51,3 +51,58 @@ def test_dbscan_csr_input_and_50k():
     for lab in labs:
         u = np.unique(lab[lab >= 0])
         assert (u == np.arange(len(u))).all()
+
+
+def test_integrate_golden(golden):
+    """Ensemble integration (long_read_cluster.py:12-49,122-150) against outputs of the reference's own loop."""
+    from oracle import integrate as oi
+    from semibin_b200.long_read import integrate_labels
+    g = golden('integrate')
+    for seed in range(24):
+        labels, lengths, markers, minfasta = oi.random_case(seed)
+        lab, n_ext = integrate_labels(labels, lengths, markers, minfasta)
+        np.testing.assert_array_equal(lab, g[f'rand{seed}'])
+        assert n_ext == int(g[f'rand{seed}'].max()) + 1
+    for n, seed, minfasta in ((1500, 5, 20000), (2500, 6, 200000)):
+        labels, lengths, markers = oi.synth_case(n, seed)
+        lab, _ = integrate_labels(labels, lengths, markers, minfasta)
+        np.testing.assert_array_equal(lab, g[f'synth{n}'])
+
+
+def test_integrate_reference_objects_and_edge_cases():
+    from collections import defaultdict
+    from oracle import integrate as oi
+    from semibin_b200.long_read import integrate_bins, integrate_labels
+    labels, lengths, markers, minfasta = oi.random_case(7)
+    names = [f'c{i}' for i in range(labels.shape[1])]
+    cd = {nm: 'A' * int(l) for nm, l in zip(names, lengths)}
+    c2m = defaultdict(list, {nm: [f'm{j}' for j in m] for nm, m in zip(names, markers) if len(m)})
+    ext = integrate_bins([l.tolist() for l in labels], c2m, names, cd, minfasta)
+    ref, _ = oi.integrate_restated(labels, lengths, markers, minfasta)
+    got = np.full(len(names), -1)
+    for b, members in enumerate(ext):
+        assert members == sorted(members, key=names.index)
+        got[[names.index(m) for m in members]] = b
+    np.testing.assert_array_equal(got, ref)
+    lab, n = integrate_labels(np.zeros((2, 3), np.int64), [10, 10, 10], [np.array([0])] * 3, 100)
+    assert n == 0 and (lab == -1).all()
+    lab, n = integrate_labels(np.zeros((2, 1), np.int64), [500], [np.array([], np.int32)], 100)
+    assert n == 1 and lab[0] == 0
+    lab, n = integrate_labels(np.zeros((1, 4), np.int64), [500] * 4, [np.array([], np.int32)] * 4, 100)
+    assert n == 0
+
+
+def test_integrate_20k_against_restatement():
+    """Full hot path at 20k contigs: GPU kNN + sweep + integration vs the CPU restatement on the same labels."""
+    from oracle import integrate as oi
+    from semibin_b200.long_read import long_read_labels, integrate_labels
+    n = 20000
+    X, L = synth.long_read_case(n, n_sample=1, seed=77)
+    _, genome = synth.embeddings(n, 77, return_genome=True)
+    markers = synth.marker_table(genome, L, seed=77)
+    labs = long_read_labels(X, None, L, n_sample=1, is_combined=True, n_neighbors=100)
+    labels = np.stack(labs)
+    got, n_got = integrate_labels(labels, L, markers, 200000)
+    ref, n_ref = oi.integrate_restated(labels, L, markers, 200000)
+    assert n_got == n_ref and n_ref > 20
+    np.testing.assert_array_equal(got, ref)

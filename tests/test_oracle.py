@@ -163,3 +163,31 @@ def test_live_sklearn_agrees():
     rd, ri = knn.knn_sklearn(X, 30, q_begin=100, q_end=400)
     d, i = knn.knn_restated(X, 30, q_begin=100, q_end=400)
     compare.assert_knn_parity(rd, ri, d, i, rtol=0)
+
+
+def test_integrate_restated_matches_reference_loop(golden):
+    """long_read_cluster.py:12-49,122-150: the restatement against outputs of the reference's own
+    get_best_bin loop (oracle/make_golden.py::integrate)."""
+    from oracle import integrate as oi
+    g = golden('integrate')
+    for seed in range(24):
+        labels, lengths, markers, minfasta = oi.random_case(seed)
+        lab, n_ext = oi.integrate_restated(labels, lengths, markers, minfasta)
+        np.testing.assert_array_equal(lab, g[f'rand{seed}'])
+        assert n_ext == int(g[f'rand{seed}'].max()) + 1
+    labels, lengths, markers = oi.synth_case(1500, 5)
+    lab, _ = oi.integrate_restated(labels, lengths, markers, 20000)
+    np.testing.assert_array_equal(lab, g['synth1500'])
+
+
+def test_integrate_edge_cases():
+    from oracle import integrate as oi
+    # total length below minfasta: nothing is extracted (long_read_cluster.py:123)
+    lab, n = oi.integrate_restated(np.zeros((2, 3), np.int64), [10, 10, 10], [np.array([0])] * 3, 100)
+    assert n == 0 and (lab == -1).all()
+    # a single contig that is long enough becomes a bin without any marker (:124-126)
+    lab, n = oi.integrate_restated(np.zeros((2, 1), np.int64), [500], [np.array([], np.int32)], 100)
+    assert n == 1 and lab[0] == 0
+    # no bin with a marker: loop ends (:133-134)
+    lab, n = oi.integrate_restated(np.zeros((1, 4), np.int64), [500] * 4, [np.array([], np.int32)] * 4, 100)
+    assert n == 0
