@@ -95,6 +95,16 @@ def long_read(n, S, k=200, cpu_check=False):
     res['n_clusters'] = [int(labels[e].max().item()) + 1 for e in range(12)]
     res['stats'] = {k2: st[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')}
     res['total_ms'] = res['knn_ms'] + res['sweep_ms'] + res['labels_ms']
+    # N2: ensemble integration (long_read_cluster.py:12-49,122-150) on the 12 label vectors
+    _, genome = synth.embeddings(n, 20244, return_genome=True)
+    markers = lr.marker_masks(synth.marker_table(genome, L, seed=20244), n)
+    minfasta = 200000
+    lr.integrate_labels(labels, L, markers, minfasta)
+    t0 = time.perf_counter()
+    lab, n_bins = lr.integrate_labels(labels, L, markers, minfasta)
+    res['integrate_ms'] = (time.perf_counter() - t0) * 1e3
+    res['integrate_bins'] = n_bins
+    res['integrate_binned_contigs'] = int((lab >= 0).sum())
     if cpu_check:
         from oracle import dbscan as od
         nb = min(n, 50000)
@@ -115,6 +125,20 @@ def long_read(n, S, k=200, cpu_check=False):
             for eps in (0.05, 0.3, 0.55):
                 dbscan(G, eps=eps, min_samples=5, metric='precomputed', sample_weight=Ls)
         res['cpu_dbscan_50k_s_per_eps'] = (time.perf_counter() - t0) / 3
+        # the reference's integration loop is O(bins * R * N) interpreter work: time the restatement (faster than
+        # the reference's own loop) on a 20k-contig problem and check the GPU result against it
+        from oracle import integrate as oi
+        Xs, Ls = sy.long_read_case(20000, n_sample=S, seed=20246)
+        _, gs = sy.embeddings(20000, 20246, return_genome=True)
+        ms = sy.marker_table(gs, Ls, seed=20246)
+        labs = np.stack(lr.long_read_labels(Xs, None, Ls, n_sample=S, is_combined=True))
+        t0 = time.perf_counter()
+        ref, nref = oi.integrate_restated(labs, Ls, ms, 200000)
+        res['cpu_integrate_20k_s'] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        got, ngot = lr.integrate_labels(labs, Ls, ms, 200000)
+        res['gpu_integrate_20k_ms'] = (time.perf_counter() - t0) * 1e3
+        res['integrate_parity_20k'] = bool(nref == ngot and (ref == got).all())
     return res
 
 
