@@ -128,6 +128,21 @@ def build_edge_list(embedding, features, depth, *, max_edges, max_node, is_combi
     return out
 
 
+def add_edges_contiguous(graph, X, Y):
+    """Hand-off #1 to igraph without the reference's per-edge Python tuples (cluster.py:150 builds up to 1e8
+    of them): the endpoints go in as ONE contiguous int64 [E, 2] buffer (python-igraph reads a 2-D memoryview of
+    its integer type directly); an igraph build without that path gets the same pairs as nested lists, built by
+    numpy in C.  Edge order and endpoints are unchanged."""
+    pairs = np.empty((len(X), 2), dtype=np.int64)
+    pairs[:, 0] = X
+    pairs[:, 1] = Y
+    try:
+        graph.add_edges(memoryview(pairs))
+    except (TypeError, ValueError):
+        graph.add_edges(pairs.tolist())
+    return pairs
+
+
 def run_embed_infomap(logger, model, data, *, device, max_edges, max_node, is_combined, n_sample,
                       contig_dict, num_process: int, random_seed):
     """Drop-in for SemiBin.cluster.run_embed_infomap (same arguments, same
@@ -156,7 +171,7 @@ def run_embed_infomap(logger, model, data, *, device, max_edges, max_node, is_co
     logger.debug(f'Number of edges in clustering graph: {len(X)}')
     g = Graph()
     g.add_vertices(np.arange(num_contigs))
-    g.add_edges(list(zip(X.tolist(), Y.tolist())))
+    add_edges_contiguous(g, X, Y)                                # cluster.py:150-157 without the tuple list
     length_weight = np.array([len(contig_dict[name]) for name in data.index])
     logger.debug(f'Running infomap with {num_process} processes...')
     result = g.community_infomap(edge_weights=V, vertex_weights=length_weight, trials=NR_INFOMAP_TRIALS)

@@ -69,3 +69,27 @@ def test_sharded_knn_gloo_world2(tmp_path):
         np.testing.assert_array_equal(z['c'], [3, 30])
         np.testing.assert_array_equal(z['gx'], [0, 1, 2, 501, 502, 503, 504])
         np.testing.assert_array_equal(z['gv'], np.array([0, 1, 2, 501, 502, 503, 504]) * 0.5)
+
+
+def test_igraph_handoff_contiguous_buffer():
+    """cluster.py:150-157: the edge list reaches igraph as one [E,2] buffer (or, for an igraph without the
+    memoryview path, as the same pairs in nested lists); order and endpoints unchanged."""
+    from semibin_b200.cluster import add_edges_contiguous
+
+    class NewGraph:
+        def add_edges(self, es):
+            assert isinstance(es, memoryview) and es.ndim == 2 and es.shape[1] == 2 and es.format in ('l', 'q')
+            self.got = np.asarray(es).copy()
+
+    class OldGraph:
+        def add_edges(self, es):
+            if isinstance(es, memoryview):
+                raise TypeError('only sequences of pairs')
+            self.got = np.asarray(es)
+
+    X = np.array([0, 0, 3], dtype=np.int32)
+    Y = np.array([1, 5, 4], dtype=np.int32)
+    for G in (NewGraph, OldGraph):
+        g = G()
+        add_edges_contiguous(g, X, Y)
+        np.testing.assert_array_equal(g.got, np.stack([X, Y], axis=1))
