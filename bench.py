@@ -294,9 +294,11 @@ def run_ours(args):
                        'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
             'clocks': sampler.summary(),
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
+                    # whole-job bytes: every embedding row is uploaded once (each rank its own row block, the rest
+                    # arrives over NVLink) and every result row is downloaded once (by the rank that computed it)
                     'h2d_bytes_per_step': int(X_host.numel() * 4),
-                    'd2h_bytes_per_step': int(out_d_host.numel() * 4 + out_i_host.numel() * 4),
-                    'api': 'semibin_b200.neighbors.knn_host: pinned host embedding in, (dist f32, idx i32) row block out in pinned host memory; row blocks downloaded while the next block is computed'},
+                    'd2h_bytes_per_step': int(n * k * 8),
+                    'api': 'semibin_b200.neighbors.knn_host: pinned host embedding in (row block per rank, all-gathered over NVLink when N>1), (dist f32, idx i32) row block out in pinned host memory; row blocks downloaded while the next block is computed'},
             'gpu_launches': int(sum(s['n_launches'] for s in stats)),
             'roofline': roofline,
             'stages_ms': stage_ms,

@@ -97,11 +97,15 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
     return out_d, out_i
 
 
-def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto'):
+def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto',
+             group=None, shard_upload=True):
     """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
     host tensors (pinned ones are allocated when none are passed).  The query rows are processed in
     `n_blocks` row blocks; the device->host copy of a finished block runs on a second stream while the
     next block is computed, so only the upload and the last block's download are exposed.
+    Under torch.distributed (one process per GPU, every rank holding the same host matrix) each rank uploads
+    only its own row block of X and the blocks are all-gathered over NVLink (`shard_upload`), instead of every
+    rank pulling the whole matrix through the host's PCIe links.
     Returns (dist, idx) host tensors [n, k]."""
     import torch
     _lib.require_cuda()
@@ -116,7 +120,13 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
         out_dist = torch.empty((n_q, k), dtype=X_host.dtype).pin_memory()
     if out_idx is None:
         out_idx = torch.empty((n_q, k), dtype=torch.int32).pin_memory()
-    Xd = X_host.cuda(non_blocking=True)
+    from . import dist as sdist
+    rank, world = sdist.world_info(group)
+    if world > 1 and shard_upload:
+        lo, hi = sdist.row_block(N, rank, world)
+        Xd = sdist.all_gather_rows(X_host[lo:hi].cuda(non_blocking=True), N, group)
+    else:
+        Xd = X_host.cuda(non_blocking=True)
     compute = torch.cuda.current_stream()
     copy = _copy_stream(Xd.device)
     n_blocks = max(1, min(int(n_blocks), (n_q + 65535) // 65536))

@@ -3,9 +3,12 @@ describes: "replace these call sites / monkey-patch these names").
 
     import semibin_b200.patch; semibin_b200.patch.install()
 
-After install(), `SemiBin.cluster.run_embed_infomap` is the fused GPU version
-and `SemiBin.long_read_cluster`'s `kneighbors_graph` / `dbscan` names resolve to
-the libsbk-backed drop-ins; `uninstall()` restores the originals.
+After install(), `SemiBin.cluster.run_embed_infomap` is the fused GPU version,
+`SemiBin.long_read_cluster.cluster_long_read` is the GPU version (kNN graph,
+12-eps DBSCAN sweep and the get_best_bin extraction loop on the device; main.py
+imports the name at call time, :1170) and `SemiBin.long_read_cluster`'s
+`kneighbors_graph` / `dbscan` / `get_best_bin`-free call sites resolve to the
+libsbk-backed drop-ins; `uninstall()` restores the originals.
 """
 _saved = {}
 
@@ -16,10 +19,12 @@ def install():
     from . import cluster, long_read, neighbors
     if _saved:
         return
-    _saved.update(run_embed_infomap=rc.run_embed_infomap, kneighbors_graph=rl.kneighbors_graph, dbscan=rl.dbscan)
+    _saved.update(run_embed_infomap=rc.run_embed_infomap, kneighbors_graph=rl.kneighbors_graph, dbscan=rl.dbscan,
+                  cluster_long_read=rl.cluster_long_read)
     rc.run_embed_infomap = cluster.run_embed_infomap
     rl.kneighbors_graph = neighbors.kneighbors_graph
     rl.dbscan = long_read._SweepCache()
+    rl.cluster_long_read = long_read.cluster_long_read
 
 
 def uninstall():
@@ -30,4 +35,5 @@ def uninstall():
     rc.run_embed_infomap = _saved['run_embed_infomap']
     rl.kneighbors_graph = _saved['kneighbors_graph']
     rl.dbscan = _saved['dbscan']
+    rl.cluster_long_read = _saved['cluster_long_read']
     _saved.clear()
