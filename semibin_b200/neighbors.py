@@ -129,7 +129,9 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
         Xd = X_host.cuda(non_blocking=True)
     compute = torch.cuda.current_stream()
     copy = _copy_stream(Xd.device)
-    n_blocks = max(1, min(int(n_blocks), (n_q + 65535) // 65536))
+    # a row block should fill the GPU for many waves (74 CTA pairs x 256 rows each): small blocks pay the staging
+    # twice and lose a partial wave per filter launch, which costs more than the download they would hide
+    n_blocks = max(1, min(int(n_blocks), n_q // 200000))
     step = ((n_q + n_blocks - 1) // n_blocks + 255) // 256 * 256
     keep = []
     for b0 in range(0, n_q, step):
