@@ -113,6 +113,18 @@ int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
 /* sbk_knn synchronises `cuda_stream` before it returns (it reads back the
  * certificate-failure count to size the fallback launch). */
 
+/* sbk_knn with the result also delivered to HOST memory (the buffers kneighbors_graph hands to scipy,
+ * cluster.py:94-105): the query rows are processed in chunks of `chunk_rows` (0 = the default chunking) and
+ * every finished chunk is copied to host_dist / host_idx (pinned memory for an asynchronous copy) on
+ * `copy_stream` while the next chunk is computed; rows recomputed by the exact fallback are copied again at
+ * the end.  out_dist / out_idx are still the full device outputs.  Both streams are synchronised on return. */
+int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                   int64_t q_begin, int64_t q_end, int32_t k,
+                   void* out_dist, int32_t* out_idx,
+                   void* host_dist, int32_t* host_idx, int64_t chunk_rows,
+                   void* workspace, size_t ws_bytes, int algo,
+                   sbk_knn_stats* stats, void* cuda_stream, void* copy_stream);
+
 /* Number of thresholds of the max_node search (cluster.py:118-125). */
 #define SBK_MAX_THRESHOLDS 32
 

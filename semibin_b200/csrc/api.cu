@@ -68,13 +68,13 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
   return s;
 }
 
-static void carve(Arena& a, const KnnShape& s, long long n_ref, int k, KnnWs& w) {
+static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, int k, KnnWs& w) {
   const int k1 = k + 1;
   w.cand_idx = s.algo == SBK_KNN_TENSOR ? nullptr : a.take<uint32_t>((size_t)s.chunk * s.cand_stride);
   w.cand_pair = s.algo == SBK_KNN_TENSOR ? a.take<uint2>((size_t)s.chunk * s.cand_stride) : nullptr;
   w.cand_count = a.take<int32_t>((size_t)s.chunk * 4);
   w.bound = a.take<double>((size_t)s.chunk);
-  w.fail_rows = a.take<int32_t>((size_t)s.chunk + (size_t)s.fb_rows + 1);
+  w.fail_rows = a.take<int32_t>((size_t)n_q + (size_t)s.fb_rows + 1);     // all failing rows of the call, then the fallback's own sink
   w.n_fail = a.take<int>(64);
   w.cand_total = a.take<unsigned long long>(8);   // [0] candidates emitted, [1] candidates reranked in FP64
   w.fb_idx = a.take<uint32_t>((size_t)s.fb_rows * s.fb_split * k1);
@@ -145,16 +145,19 @@ extern "C" size_t sbk_knn_workspace_bytes(int dtype, int64_t n_ref, int32_t d, i
   KnnShape s = knn_shape(dtype, n_ref, d, n_query, k, algo);
   Arena a(nullptr, 0);
   KnnWs w;
-  carve(a, s, n_ref, k, w);
+  carve(a, s, n_ref, std::min<int64_t>(n_query, n_ref), k, w);
   return a.off + 1024;
 }
 
-extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
-                       int64_t q_begin, int64_t q_end, int32_t k,
-                       void* out_dist, int32_t* out_idx,
-                       void* workspace, size_t ws_bytes, int algo,
-                       sbk_knn_stats* stats, void* cuda_stream) {
-  cudaStream_t stream = (cudaStream_t)cuda_stream;
+// Host sink of sbk_knn_stream: finished query chunks are copied to host memory on `copy_stream` while the
+// next chunk is computed.
+struct HostSink { void* dist; int32_t* idx; long long chunk_rows; cudaStream_t copy_stream; };
+
+static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                    int64_t q_begin, int64_t q_end, int32_t k,
+                    void* out_dist, int32_t* out_idx,
+                    void* workspace, size_t ws_bytes, int algo,
+                    sbk_knn_stats* stats, cudaStream_t stream, const HostSink* sink) {
   int rc = knn_check(dtype, n_ref, d, q_begin, q_end, k);
   if (rc) return rc;
   if (ld < d) { set_error("knn: ld=%lld < d=%d", (long long)ld, d); return SBK_ERR_INVALID; }
@@ -162,15 +165,17 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
   const long long n_q = q_end - q_begin;
   const int k1 = k + 1;
   KnnShape s = knn_shape(dtype, n_ref, d, n_q, k, algo);
+  if (sink && sink->chunk_rows > 0)             // smaller chunks only: the workspace was sized for the default
+    s.chunk = std::min<long long>(s.chunk, std::max<long long>(256, sink->chunk_rows / 256 * 256));
   Arena a(workspace, ws_bytes);
   KnnWs w;
-  carve(a, s, n_ref, k, w);
+  carve(a, s, n_ref, n_q, k, w);
   if (!a.ok() || workspace == nullptr) { set_error("knn: workspace %zu B < required %zu B", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   sbk_knn_stats st; memset(&st, 0, sizeof(st));
   st.algo_used = s.algo;
   const size_t esz = dtype == SBK_F32 ? 4 : 8;
   SBK_CUDA_CHECK(cudaMemsetAsync(w.cand_total, 0, 8 * sizeof(unsigned long long), stream));
-  SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail, 0, 64 * sizeof(int), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail, 0, 64 * sizeof(int), stream));      // [0] failing rows of the whole call
 
   StageTimer tm(stream, stats != nullptr);
   TcState tcs; memset(&tcs, 0, sizeof(tcs));
@@ -185,29 +190,32 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
     st.order_stat = s.plan.order_stat; st.kpad = s.plan.kpad; st.n_split_cols = s.plan.n_split;
   }
 
+  // The chunk loop never waits for the GPU: rows whose certificate fails are collected over the whole call
+  // (their output rows stay untouched) and recomputed once at the end.
+  std::vector<cudaEvent_t> events;
+  auto drop_events = [&]() { for (cudaEvent_t e : events) cudaEventDestroy(e); events.clear(); };
   for (long long c0 = 0; c0 < n_q; c0 += s.chunk) {
     const long long cn = std::min(s.chunk, n_q - c0);
     const long long row0 = q_begin + c0;
     void* od = (char*)out_dist + (size_t)c0 * k * esz;
     int32_t* oi = out_idx + (size_t)c0 * k;
-    SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail, 0, sizeof(int), stream));
     if (s.algo == SBK_KNN_EXACT) {
       int h = tm.begin(&st.ms_exact_filter);
       rc = launch_exact_filter(X, dtype, n_ref, d, ld, nullptr, row0, cn, s.n_split, k1,
                                w.cand_idx, s.cand_stride, w.cand_count, stream);
       tm.end(h);
-      if (rc) return rc;
+      if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
                          nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 2;
-      if (rc) return rc;
+      if (rc) { drop_events(); return rc; }
     } else {
       int h = tm.begin(&st.ms_sample);
       rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, stream);
       tm.end(h);
-      if (rc) return rc;
+      if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_filter);
       int nfl = 0, nrf = 0;
       rc = tc_filter_chunk(&tcs, s.plan, row0, cn, k, w.cand_pair, w.cand_count, w.bound, &nfl, &nrf, stream);
@@ -216,45 +224,76 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
         tm.end(h); SBK_CUDA_CHECK(cudaStreamSynchronize(stream)); st.n_chunks++; continue;
       }
       tm.end(h);
-      if (rc) return rc;
+      if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                          w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
       tm.end(h);
       st.n_launches += 3;
-      if (rc) return rc;
+      if (rc) { drop_events(); return rc; }
     }
-    int h_fail = 0;
-    SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fail, w.n_fail, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
-    if (h_fail > 0) {
-      if (s.algo == SBK_KNN_EXACT) {
-        set_error("knn: exact filter produced an incomplete candidate list for %d rows", h_fail);
-        return SBK_ERR_INTERNAL;
-      }
-      st.n_fallback_rows += h_fail;
-      // rows whose certificate failed: exact FP64 filter over all references
-      int hfb = tm.begin(&st.ms_fallback);
-      for (int f0 = 0; f0 < h_fail; f0 += (int)s.fb_rows) {
-        st.n_launches += 2;
-        const int fn = std::min<int>((int)s.fb_rows, h_fail - f0);
-        rc = launch_exact_filter(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, s.fb_split, k1,
-                                 w.fb_idx, (long long)s.fb_split * k1, w.fb_count, stream);
-        if (rc) return rc;
-        // n_fail doubles as the (unused) failure sink of the fallback rerank
-        rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
-                           w.fb_count, nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows + s.chunk, w.n_fail + 1, nullptr, stream);
-        if (rc) return rc;
-      }
-      tm.end(hfb);
+    if (sink) {                                  // download this chunk while the next one is computed
+      cudaEvent_t ev;
+      SBK_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      events.push_back(ev);
+      SBK_CUDA_CHECK(cudaEventRecord(ev, stream));
+      SBK_CUDA_CHECK(cudaStreamWaitEvent(sink->copy_stream, ev, 0));
+      SBK_CUDA_CHECK(cudaMemcpyAsync((char*)sink->dist + (size_t)c0 * k * esz, od, (size_t)cn * k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
+      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx + (size_t)c0 * k, oi, (size_t)cn * k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
     }
     st.n_chunks++;
+  }
+  int h_fail = 0;
+  SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fail, w.n_fail, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+  std::vector<int32_t> h_rows;
+  if (h_fail > 0) {
+    if (s.algo == SBK_KNN_EXACT) {
+      drop_events();
+      set_error("knn: exact filter produced an incomplete candidate list for %d rows", h_fail);
+      return SBK_ERR_INTERNAL;
+    }
+    st.n_fallback_rows += h_fail;
+    // rows whose certificate failed: exact FP64 filter over all references
+    int hfb = tm.begin(&st.ms_fallback);
+    for (int f0 = 0; f0 < h_fail; f0 += (int)s.fb_rows) {
+      st.n_launches += 2;
+      const int fn = std::min<int>((int)s.fb_rows, h_fail - f0);
+      rc = launch_exact_filter(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, s.fb_split, k1,
+                               w.fb_idx, (long long)s.fb_split * k1, w.fb_count, stream);
+      if (rc) { drop_events(); return rc; }
+      // n_fail[1] counts rows the fallback itself could not resolve (none are expected)
+      rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
+                         w.fb_count, nullptr, nullptr, nullptr, nullptr, nullptr, k, out_dist, out_idx, q_begin,
+                         w.fail_rows + n_q, w.n_fail + 1, nullptr, stream);
+      if (rc) { drop_events(); return rc; }
+    }
+    tm.end(hfb);
+    if (sink) {
+      h_rows.resize((size_t)h_fail);
+      SBK_CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), w.fail_rows, (size_t)h_fail * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    }
   }
   unsigned long long h_total[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int h_fb_fail = 0;
   SBK_CUDA_CHECK(cudaMemcpyAsync(h_total, w.cand_total, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fb_fail, w.n_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (sink) {
+    // the recomputed rows replace what the chunk downloads carried for them (copies on one stream stay ordered)
+    if (h_fail > 4096) {
+      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->dist, out_dist, (size_t)n_q * k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
+      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx, out_idx, (size_t)n_q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
+    } else {
+      for (int f = 0; f < h_fail; ++f) {
+        const size_t r = (size_t)(h_rows[f] - q_begin);
+        SBK_CUDA_CHECK(cudaMemcpyAsync((char*)sink->dist + r * k * esz, (char*)out_dist + r * k * esz, (size_t)k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
+        SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx + r * k, out_idx + r * k, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
+      }
+    }
+    SBK_CUDA_CHECK(cudaStreamSynchronize(sink->copy_stream));
+  }
+  drop_events();
   if (h_fb_fail > 0) { set_error("knn: exact fallback left %d rows unresolved", h_fb_fail); return SBK_ERR_INTERNAL; }
   st.n_candidates = (long long)h_total[0];
   st.n_reranked = (long long)h_total[1];
@@ -263,6 +302,28 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
   tm.collect();
   if (stats) *stats = st;
   return SBK_OK;
+}
+
+extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                       int64_t q_begin, int64_t q_end, int32_t k,
+                       void* out_dist, int32_t* out_idx,
+                       void* workspace, size_t ws_bytes, int algo,
+                       sbk_knn_stats* stats, void* cuda_stream) {
+  return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
+                  (cudaStream_t)cuda_stream, nullptr);
+}
+
+extern "C" int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                              int64_t q_begin, int64_t q_end, int32_t k,
+                              void* out_dist, int32_t* out_idx,
+                              void* host_dist, int32_t* host_idx, int64_t chunk_rows,
+                              void* workspace, size_t ws_bytes, int algo,
+                              sbk_knn_stats* stats, void* cuda_stream, void* copy_stream) {
+  if (!host_dist || !host_idx) { set_error("knn_stream: host output buffers required"); return SBK_ERR_INVALID; }
+  if (copy_stream == cuda_stream) { set_error("knn_stream: the copy stream must differ from the compute stream"); return SBK_ERR_INVALID; }
+  HostSink sink; sink.dist = host_dist; sink.idx = host_idx; sink.chunk_rows = chunk_rows; sink.copy_stream = (cudaStream_t)copy_stream;
+  return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
+                  (cudaStream_t)cuda_stream, &sink);
 }
 
 extern "C" size_t sbk_debug_tc_workspace_bytes(int64_t n_ref, int32_t d) {

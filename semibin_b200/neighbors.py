@@ -98,28 +98,38 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
 
 
 def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto',
-             group=None, shard_upload=True):
+             group=None, shard_upload=True, min_block_rows=200000, return_stats=False):
     """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
-    host tensors (pinned ones are allocated when none are passed).  The query rows are processed in
-    `n_blocks` row blocks; the device->host copy of a finished block runs on a second stream while the
-    next block is computed, so only the upload and the last block's download are exposed.
+    host tensors (pinned ones are allocated when none are passed).  One library call (`sbk_knn_stream`): the
+    query rows are processed in `n_blocks` chunks and the device->host copy of a finished chunk runs on a
+    second stream while the next chunk is computed, so only the upload and the last chunk's download are
+    exposed; the reference operands are staged once.
     Under torch.distributed (one process per GPU, every rank holding the same host matrix) each rank uploads
     only its own row block of X and the blocks are all-gathered over NVLink (`shard_upload`), instead of every
     rank pulling the whole matrix through the host's PCIe links.
     Returns (dist, idx) host tensors [n, k]."""
     import torch
     _lib.require_cuda()
+    lib = _lib.load()
     if isinstance(X_host, np.ndarray):
         X_host = torch.from_numpy(np.ascontiguousarray(X_host))
-    N = X_host.shape[0]
+    if X_host.dtype not in (torch.float32, torch.float64):
+        X_host = X_host.float()
+    X_host = X_host.contiguous()
+    N, D = X_host.shape
     if q_end is None:
         q_end = N
     n_q = q_end - q_begin
     k = int(n_neighbors)
+    if k < 1 or k >= N:
+        raise ValueError(f'Expected n_neighbors < n_samples_fit, but n_neighbors = {k}, n_samples_fit = {N}')
     if out_dist is None:
         out_dist = torch.empty((n_q, k), dtype=X_host.dtype).pin_memory()
     if out_idx is None:
         out_idx = torch.empty((n_q, k), dtype=torch.int32).pin_memory()
+    if (tuple(out_dist.shape) != (n_q, k) or tuple(out_idx.shape) != (n_q, k) or out_dist.dtype != X_host.dtype
+            or out_idx.dtype != torch.int32 or not out_dist.is_contiguous() or not out_idx.is_contiguous()):
+        raise ValueError('out_dist / out_idx must be contiguous host tensors [n, k] of dtypes (X.dtype, int32)')
     from . import dist as sdist
     rank, world = sdist.world_info(group)
     if world > 1 and shard_upload:
@@ -127,25 +137,25 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
         Xd = sdist.all_gather_rows(X_host[lo:hi].cuda(non_blocking=True), N, group)
     else:
         Xd = X_host.cuda(non_blocking=True)
-    compute = torch.cuda.current_stream()
     copy = _copy_stream(Xd.device)
-    # a row block should fill the GPU for many waves (74 CTA pairs x 256 rows each): small blocks pay the staging
-    # twice and lose a partial wave per filter launch, which costs more than the download they would hide
-    n_blocks = max(1, min(int(n_blocks), n_q // 200000))
-    step = ((n_q + n_blocks - 1) // n_blocks + 255) // 256 * 256
-    keep = []
-    for b0 in range(0, n_q, step):
-        b1 = min(n_q, b0 + step)
-        d, i = knn(Xd, k, q_begin=q_begin + b0, q_end=q_begin + b1, algo=algo)
-        ev = torch.cuda.Event()
-        ev.record(compute)
-        copy.wait_event(ev)
-        with torch.cuda.stream(copy):
-            out_dist[b0:b1].copy_(d, non_blocking=True)
-            out_idx[b0:b1].copy_(i, non_blocking=True)
-        keep.append((d, i))              # keep the device blocks alive until their copies have run
-    copy.synchronize()
-    return out_dist, out_idx
+    # a chunk should fill the GPU for many waves (74 CTA pairs x 256 rows each): small chunks lose a partial wave
+    # per filter launch, which costs more than the download they would hide
+    n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
+    chunk = ((n_q + n_blocks - 1) // n_blocks + 255) // 256 * 256
+    dtype = _lib.SBK_F32 if Xd.dtype == torch.float32 else _lib.SBK_F64
+    a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
+    ws_bytes = lib.sbk_knn_workspace_bytes(dtype, N, D, n_q, k, a)
+    if ws_bytes == 0:
+        raise ValueError(_lib.last_error())
+    ws = _workspace(ws_bytes, Xd.device)
+    dev_d = torch.empty((n_q, k), dtype=Xd.dtype, device=Xd.device)
+    dev_i = torch.empty((n_q, k), dtype=torch.int32, device=Xd.device)
+    stats = _lib.KnnStats()
+    rc = lib.sbk_knn_stream(_lib.ptr(Xd), dtype, N, D, Xd.stride(0), q_begin, q_end, k, _lib.ptr(dev_d), _lib.ptr(dev_i),
+                            out_dist.data_ptr(), out_idx.data_ptr(), chunk, _lib.ptr(ws), ws.numel(), a,
+                            C.byref(stats), _lib.stream_ptr(), copy.cuda_stream)
+    _lib.check(rc)
+    return (out_dist, out_idx, stats.as_dict()) if return_stats else (out_dist, out_idx)
 
 
 _copy_streams = {}

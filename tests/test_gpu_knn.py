@@ -147,5 +147,27 @@ def test_knn_host_blocks_equal_device_call():
     X = synth.embeddings(150000, seed=77)
     Xd = torch.from_numpy(X).cuda()
     d0, i0 = knn(Xd, 50, q_begin=1000, q_end=141000)
-    hd, hi = knn_host(torch.from_numpy(X).pin_memory(), 50, q_begin=1000, q_end=141000, n_blocks=3)
+    hd, hi = knn_host(torch.from_numpy(X).pin_memory(), 50, q_begin=1000, q_end=141000, n_blocks=3, min_block_rows=1)
     assert torch.equal(hd, d0.cpu()) and torch.equal(hi, i0.cpu())
+
+
+def test_clustered_row_order_320k():
+    """Rows sorted by genome (neighbours adjacent in index, as contigs of one assembly are): the reference side is
+    staged in a pseudo-random order, so the threshold sample and the between-launch refinement stay unbiased.
+    Sampled rows against live sklearn; almost no row may need the exact fallback."""
+    sk = pytest.importorskip('sklearn.neighbors')
+    N, k = 320000, 100
+    X, genome = synth.embeddings(N, seed=9, return_genome=True)
+    X = np.ascontiguousarray(X[np.argsort(genome, kind='stable')])
+    d, i, st = _gpu_knn(X, k, 'auto', return_stats=True)
+    assert st['algo_used'] == 2 and st['n_filter_launches'] >= 2
+    assert st['n_fallback_rows'] < 0.002 * N, st
+    rows = np.sort(np.random.default_rng(6).choice(N, 256, replace=False))
+    nn = sk.NearestNeighbors(n_neighbors=k + 1, algorithm='brute').fit(X)
+    rd, ri = nn.kneighbors(X[rows])
+    for t, r in enumerate(rows):
+        m = ri[t] != r
+        if m.all():
+            m[0] = False
+        compare.assert_knn_parity(rd[t][m][None], ri[t][m][None], d[r][None], i[r][None], rtol=1e-6)
+    assert (np.diff(d, axis=1) >= 0).all() and (i != np.arange(N)[:, None]).all()
