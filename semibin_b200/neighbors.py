@@ -138,10 +138,15 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
     else:
         Xd = X_host.cuda(non_blocking=True)
     copy = _copy_stream(Xd.device)
-    # a chunk should fill the GPU for many waves (74 CTA pairs x 256 rows each): small chunks lose a partial wave
-    # per filter launch, which costs more than the download they would hide
+    # Chunks are whole WAVES of the filter grid (one CTA pair per 256 query rows, one pair per two SMs): a chunk
+    # that ends mid-wave idles most SMs for the tail of each of its filter launches.  The last chunk is the small
+    # remainder, so the download that nothing can hide is short.
     n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
-    chunk = ((n_q + n_blocks - 1) // n_blocks + 255) // 256 * 256
+    wave_rows = (torch.cuda.get_device_properties(Xd.device).multi_processor_count // 2) * 256
+    chunk = n_q
+    if n_blocks > 1:
+        waves = n_q / wave_rows
+        chunk = max(1, int(np.ceil(waves / (n_blocks - 0.7)))) * wave_rows
     dtype = _lib.SBK_F32 if Xd.dtype == torch.float32 else _lib.SBK_F64
     a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
     ws_bytes = lib.sbk_knn_workspace_bytes(dtype, N, D, n_q, k, a)
