@@ -171,3 +171,23 @@ def test_clustered_row_order_320k():
             m[0] = False
         compare.assert_knn_parity(rd[t][m][None], ri[t][m][None], d[r][None], i[r][None], rtol=1e-6)
     assert (np.diff(d, axis=1) >= 0).all() and (i != np.arange(N)[:, None]).all()
+
+
+def test_stream_with_fallback_rows():
+    """Rows the tensor path cannot certify (hundreds of exact duplicates: more than a candidate segment holds of one
+    value, and the 'self not among the k+1 nearest' corner of neighbors/_base.py:946-950) are recomputed by the
+    exact filter at the END of the call; the host-buffer path must carry the recomputed rows, not the chunk
+    downloads made before."""
+    import torch
+    from semibin_b200.neighbors import knn, knn_host
+    X = synth.embeddings(40000, seed=123)
+    X[100:1100] = X[7]                                   # 1001 identical rows, k = 50
+    Xd = torch.from_numpy(X).cuda()
+    d0, i0 = knn(Xd, 50, algo='exact')
+    d1, i1, st = knn(Xd, 50, algo='tensor', return_stats=True)
+    assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    hd, hi, sth = knn_host(torch.from_numpy(X).pin_memory(), 50, algo='tensor', n_blocks=4, min_block_rows=1,
+                           return_stats=True)
+    assert sth['n_chunks'] >= 2
+    assert torch.equal(hd, d0.cpu()) and torch.equal(hi, i0.cpu())
+    print('fallback rows', st['n_fallback_rows'], sth['n_fallback_rows'])
