@@ -26,36 +26,31 @@ radius_sweep_kernel(const float* __restrict__ dist, const int32_t* __restrict__ 
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * R_WARPS + (threadIdx.x >> 5);
   if (r >= n_rows) return;
-  const double wself = weight ? weight[row_begin + r] : 1.0;
-  // eight eps values per pass over the row (the second pass re-reads it from L1): with all sixteen counters and
-  // FP64 weight sums live the kernel needed 81 registers and ran at a quarter of the SM's warps
-  constexpr int EB = 8;
-  for (int e0 = 0; e0 < n_eps; e0 += EB) {
-    int cnt[EB];
-    double ws[EB];
+  int cnt[R_MAX_EPS];
+  double ws[R_MAX_EPS];
 #pragma unroll
-    for (int e = 0; e < EB; ++e) { cnt[e] = 0; ws[e] = 0.0; }
-    for (int c = lane; c < k; c += 32) {
-      const double d = (double)dist[r * k + c];
-      const double wj = weight ? weight[idx[r * k + c]] : 1.0;
+  for (int e = 0; e < R_MAX_EPS; ++e) { cnt[e] = 0; ws[e] = 0.0; }
+  for (int c = lane; c < k; c += 32) {
+    const double d = (double)dist[r * k + c];
+    const double wj = weight ? weight[idx[r * k + c]] : 1.0;
 #pragma unroll
-      for (int e = 0; e < EB; ++e) {
-        if (e0 + e < n_eps && d <= eps.v[e0 + e]) { cnt[e] += 1; ws[e] += wj; }
-      }
+    for (int e = 0; e < R_MAX_EPS; ++e) {
+      if (e < n_eps && d <= eps.v[e]) { cnt[e] += 1; ws[e] += wj; }
     }
+  }
+  const double wself = weight ? weight[row_begin + r] : 1.0;
 #pragma unroll
-    for (int e = 0; e < EB; ++e) {
-      if (e0 + e >= n_eps) break;
-      int c = cnt[e]; double s = ws[e];
+  for (int e = 0; e < R_MAX_EPS; ++e) {
+    if (e >= n_eps) break;
+    int c = cnt[e]; double s = ws[e];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-      }
-      if (lane == 0) {
-        prefix_len[(long long)(e0 + e) * n_rows + r] = c;
-        core[(long long)(e0 + e) * n_rows + r] = (wself + s >= min_samples) ? 1 : 0;
-      }
+    for (int o = 16; o > 0; o >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+    }
+    if (lane == 0) {
+      prefix_len[(long long)e * n_rows + r] = c;
+      core[(long long)e * n_rows + r] = (wself + s >= min_samples) ? 1 : 0;
     }
   }
 }
