@@ -171,6 +171,57 @@ def scaling_case(n, k=200, check_rows=512):
     return res
 
 
+def short_read_sharded(n, S, combined, k=200, max_node=1):
+    """C3 across the GPUs of one box (launch under torchrun): row-block kNN graphs, intersection and weights per
+    rank, one all-reduce (threshold counts) and one gather (edge blocks).  Rank 0 prints the line; the edge list
+    is checksummed so that runs at different GPU counts can be compared."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from semibin_b200 import synth, dist as sdist
+    rank = int(os.environ.get('RANK', 0)); world = int(os.environ.get('WORLD_SIZE', 1))
+    torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))))
+    emb, feat, depth, L = synth.short_read_case(n, n_sample=S, seed=20243)
+    if combined:
+        f = np.concatenate([feat, depth[:, 0::2].astype(np.float64) / 100.0], axis=1)
+        f = f / np.sum(f, axis=0)
+        feat = f / np.abs(f).sum(axis=1, keepdims=True)
+    E = torch.from_numpy(emb).cuda()
+    F = torch.from_numpy(np.ascontiguousarray(feat)).cuda()
+    Dp = torch.from_numpy(depth).cuda()
+    kw = dict(max_edges=k, max_node=max_node, is_combined=combined, n_sample=S)
+    sdist.build_edge_list_sharded(E, F, Dp, **kw)              # warm-up
+    times, times_dev = [], []
+    for mode, acc in ((False, times_dev), ('view', times)):
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = sdist.build_edge_list_sharded(E, F, Dp, to_host=mode, **kw)
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            acc.append(float(t.item()) * 1e3)
+    X, Y, V = out
+    h = hashlib.sha256()
+    for a in (X, Y, V):
+        h.update(np.ascontiguousarray(a).tobytes())
+    res = dict(n=n, S=S, combined=combined, k=k, n_gpus=world, edge_list_ms=min(times), edge_list_ms_all=times,
+               edge_list_on_device_ms=min(times_dev), edge_list_on_device_ms_all=times_dev,
+               n_edges=int(len(X)), sha256=h.hexdigest()[:16],
+               what='embedding, feature and depth matrices resident on every GPU; timed: both kNN graphs (row block per rank), '
+                    'intersect + max_node threshold (all-reduce) + KL weights, NCCL gather of the edge blocks, '
+                    '(edge_list_ms only) download of the edge list to every rank through pinned buffers')
+    if world > 1:
+        dist.destroy_process_group()
+    return res if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', default='C2')
@@ -186,6 +237,10 @@ def main():
         r = long_read(a.n or 500000, 1, cpu_check=a.cpu_check)
     elif a.config == 'C5':
         r = scaling_case(a.n or 4000000)
+    elif a.config == 'C3dist':
+        r = short_read_sharded(a.n or 1000000, 10, a.combined)
+        if r is None:
+            return
     else:
         raise SystemExit('unknown config')
     r['config'] = a.config
