@@ -103,22 +103,6 @@ def gather_edges(X, Y, V, group=None):
     return tuple(outs)
 
 
-_pinned = {}
-
-
-def _to_host(t, tag):
-    """Device tensor -> numpy through a cached pinned staging buffer (pageable copies of the 0.5 GB edge list
-    run at a fraction of the PCIe rate and dominated the multi-GPU edge-list build)."""
-    import torch
-    n = t.numel()
-    buf = _pinned.get((tag, t.dtype))
-    if buf is None or buf.numel() < n:
-        buf = torch.empty((max(n, 1),), dtype=t.dtype).pin_memory()
-        _pinned[(tag, t.dtype)] = buf
-    buf[:n].copy_(t.reshape(-1), non_blocking=True)
-    return buf, n
-
-
 def build_edge_list_sharded(embedding, features, depth, *, max_edges, max_node, is_combined, n_sample,
                             group=None, algo='auto', to_host='all'):
     """Multi-GPU version of cluster.build_edge_list: kNN graphs, intersection
@@ -151,8 +135,4 @@ def build_edge_list_sharded(embedding, features, depth, *, max_edges, max_node, 
         return X, Y, V
     if to_host == 'rank0' and rank != 0:
         return None
-    if to_host == 'view':
-        staged = [_to_host(t, tag) for t, tag in ((X, 'x'), (Y, 'y'), (V, 'v'))]
-        torch.cuda.current_stream().synchronize()
-        return tuple(buf[:m].numpy() for buf, m in staged)
-    return X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()
+    return cluster.edges_to_host(X, Y, V, 'view' if to_host == 'view' else 'copy')
