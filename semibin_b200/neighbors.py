@@ -98,7 +98,7 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
 
 
 def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto',
-             group=None, shard_upload=True, min_block_rows=200000, return_stats=False):
+             group=None, shard_upload=True, min_block_rows=None, return_stats=False):
     """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
     host tensors (pinned ones are allocated when none are passed).  One library call (`sbk_knn_stream`): the
     query rows are processed in `n_blocks` chunks and the device->host copy of a finished chunk runs on a
@@ -139,10 +139,12 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
         Xd = X_host.cuda(non_blocking=True)
     copy = _copy_stream(Xd.device)
     # Chunks are whole WAVES of the filter grid (one CTA pair per 256 query rows, one pair per two SMs): a chunk
-    # that ends mid-wave idles most SMs for the tail of each of its filter launches.  The last chunk is the small
-    # remainder, so the download that nothing can hide is short.
-    n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
+    # that ends mid-wave idles most SMs for the tail of each of its filter launches, whole-wave chunks cost no
+    # extra waves at all.  The last chunk is the small remainder, so the download that nothing can hide is short.
     wave_rows = (torch.cuda.get_device_properties(Xd.device).multi_processor_count // 2) * 256
+    if min_block_rows is None:
+        min_block_rows = 2 * wave_rows
+    n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
     chunk = n_q
     if n_blocks > 1:
         waves = n_q / wave_rows
