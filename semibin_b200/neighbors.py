@@ -97,6 +97,20 @@ def knn(X, n_neighbors, *, q_begin=0, q_end=None, algo='auto', return_stats=Fals
     return out_d, out_i
 
 
+def plan_chunk_rows(n_q, n_blocks, wave_rows, min_block_rows=None):
+    """Rows per chunk of the streamed host path.  Chunks are whole WAVES of the filter grid (one CTA pair per 256
+    query rows, one pair per two SMs -> `wave_rows` rows per wave): a chunk that ends mid-wave idles most SMs for
+    the tail of each of its filter launches, whole-wave chunks cost no extra waves at all.  The last chunk is the
+    small remainder, so the download that nothing can hide is short.  Returns n_q when the rows are not split."""
+    if min_block_rows is None:
+        min_block_rows = 2 * wave_rows
+    n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
+    if n_blocks <= 1:
+        return n_q
+    waves = n_q / wave_rows
+    return max(1, int(np.ceil(waves / (n_blocks - 0.7)))) * wave_rows
+
+
 def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_idx=None, n_blocks=4, algo='auto',
              group=None, shard_upload=True, min_block_rows=None, return_stats=False):
     """Host-buffer form of knn(): X_host is a (preferably pinned) host tensor / array, the result lands in
@@ -138,17 +152,8 @@ def knn_host(X_host, n_neighbors, *, q_begin=0, q_end=None, out_dist=None, out_i
     else:
         Xd = X_host.cuda(non_blocking=True)
     copy = _copy_stream(Xd.device)
-    # Chunks are whole WAVES of the filter grid (one CTA pair per 256 query rows, one pair per two SMs): a chunk
-    # that ends mid-wave idles most SMs for the tail of each of its filter launches, whole-wave chunks cost no
-    # extra waves at all.  The last chunk is the small remainder, so the download that nothing can hide is short.
     wave_rows = (torch.cuda.get_device_properties(Xd.device).multi_processor_count // 2) * 256
-    if min_block_rows is None:
-        min_block_rows = 2 * wave_rows
-    n_blocks = max(1, min(int(n_blocks), n_q // max(1, int(min_block_rows))))
-    chunk = n_q
-    if n_blocks > 1:
-        waves = n_q / wave_rows
-        chunk = max(1, int(np.ceil(waves / (n_blocks - 0.7)))) * wave_rows
+    chunk = plan_chunk_rows(n_q, n_blocks, wave_rows, min_block_rows)
     dtype = _lib.SBK_F32 if Xd.dtype == torch.float32 else _lib.SBK_F64
     a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
     ws_bytes = lib.sbk_knn_workspace_bytes(dtype, N, D, n_q, k, a)

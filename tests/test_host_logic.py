@@ -93,3 +93,36 @@ def test_igraph_handoff_contiguous_buffer():
         g = G()
         add_edges_contiguous(g, X, Y)
         np.testing.assert_array_equal(g.got, np.stack([X, Y], axis=1))
+
+
+def test_plan_chunk_rows_whole_waves():
+    """Streamed host path: chunks are whole waves of the filter grid, the last chunk is the short remainder, and the
+    total number of waves never grows."""
+    from semibin_b200.neighbors import plan_chunk_rows
+    wave = 74 * 256
+    for n_q in (1000000, 500000, 125000, 250000, 4000000):
+        c = plan_chunk_rows(n_q, 4, wave)
+        assert c % wave == 0 and c % 256 == 0
+        n_chunks = -(-n_q // c)
+        assert 2 <= n_chunks <= 4
+        last = n_q - (n_chunks - 1) * c
+        assert 0 < last <= c
+        waves_split = (n_chunks - 1) * (c // wave) + -(-last // wave)
+        assert waves_split == -(-n_q // wave)
+    assert plan_chunk_rows(30000, 4, wave) == 30000                  # under two waves: not split
+    assert plan_chunk_rows(140000, 3, wave, min_block_rows=1) == 4 * wave
+
+
+def test_marker_masks_and_features():
+    from semibin_b200.long_read import marker_masks, long_read_features
+    m = marker_masks([np.array([0, 5]), np.array([], dtype=int), np.array([64, 70, 106])])
+    assert m.dtype == np.uint64 and m.shape == (3, 2)
+    assert m[0, 0] == (1 << 0) | (1 << 5) and m[0, 1] == 0 and not m[1].any()
+    assert m[2, 0] == 0 and m[2, 1] == (1 << 0) | (1 << 6) | (1 << 42)
+    with pytest.raises(ValueError):
+        marker_masks([np.array([300])])
+    emb = np.ones((4, 100), np.float32)
+    depth = np.array([[2.0, 9.0, 0.0, 1.0]] * 4, np.float32)         # [mean_0, var_0, mean_1, var_1]
+    x = long_read_features(emb, depth, 2, False)                     # long_read_cluster.py:75-81
+    assert x.shape == (4, 102) and x.dtype == np.float32
+    np.testing.assert_allclose(x[0, 100:], np.log(np.clip(np.array([2.0, 0.0], np.float32), 1e-6, None)))
