@@ -230,62 +230,69 @@ def integrate_bins(dbscan_results, contig2marker, contig_list, contig_dict, minf
     return extracted
 
 
+def _network_input(table, is_combined):
+    """What the embedding network is fed (long_read_cluster.py:57-65): the 136 k-mer columns, or in combined
+    mode all columns, column- then row-normalised when the reference's norm_abundance() asks for it."""
+    if not is_combined:
+        return table[:, :136]
+    from SemiBin.utils import norm_abundance
+    if not norm_abundance(table):
+        return table
+    scaled = table / table.sum(axis=0)
+    return scaled / np.abs(scaled).sum(axis=1, keepdims=True)        # == sklearn normalize(axis=1, norm='l1')
+
+
+def _markers_per_contig(names, contig_dict, out, binned_length, args):
+    """Marker genes of every contig through the reference's own tooling (ORF finder + hmmsearch,
+    long_read_cluster.py:83-99); returns its contig -> [marker names] mapping."""
+    import os
+    import tempfile
+    from SemiBin.markers import estimate_seeds, get_marker
+    with tempfile.TemporaryDirectory() as scratch:
+        fasta = os.path.join(scratch, 'concatenated.fna')
+        with open(fasta, 'wt') as fh:
+            fh.writelines(f'>{name}\n{contig_dict[name]}\n' for name in names)
+        estimate_seeds(fasta, binned_length, args.num_process, output=out, orf_finder=args.orf_finder,
+                       prodigal_output_faa=args.prodigal_output_faa)
+        found = get_marker(os.path.join(out, 'markers.hmmout'), orf_finder=args.orf_finder,
+                           min_contig_len=binned_length, fasta_path=fasta, contig_to_marker=True)
+    return found if len(found) else {}
+
+
 def cluster_long_read(logger, model, data, device, is_combined, n_sample, out, contig_dict, *,
                       binned_length, args, minfasta):
-    """Reference signature and behaviour (long_read_cluster.py:51-161).  The embedding forward, the marker-gene
-    search (estimate_seeds / get_marker) and write_bins are the reference package's own functions; the kNN
-    graph (:108-113), the 12 DBSCAN runs (:115-120) and the integration loop (:122-150) run on the GPU."""
+    """Drop-in for SemiBin.long_read_cluster.cluster_long_read (:51-161): same arguments, same files written
+    (`output_bins/`, `bins_info.tsv`, `contig_bins.tsv`).  The kNN graph (:108-113), the 12 DBSCAN runs
+    (:115-120) and the bin extraction loop (:122-150) run on the GPU; the embedding forward is the reference
+    model's, marker search and write_bins are the reference package's own functions."""
     import os
     import shutil
-    import tempfile
     import pandas as pd
     import torch
-    from SemiBin.utils import write_bins, norm_abundance
-    from SemiBin.markers import estimate_seeds, get_marker
-    contig_list = data.index.tolist()
-    if not is_combined:                                                          # :57-65
-        train_data_input = data.values[:, 0:136]
-    else:
-        train_data_input = data.values
-        if norm_abundance(train_data_input):
-            from sklearn.preprocessing import normalize
-            norm = np.sum(train_data_input, axis=0)
-            train_data_input = train_data_input / norm
-            train_data_input = normalize(train_data_input, axis=1, norm='l1')
-    with torch.no_grad():                                                        # :67-70
+    from SemiBin.utils import write_bins
+    names = list(data.index)
+    table = data.values
+    with torch.no_grad():                                            # :67-70
         model.eval()
-        x = torch.from_numpy(train_data_input).to(device)
-        embedding = model.embedding(x.float()).detach().cpu().numpy()
-    length_weight = np.array([len(contig_dict[name]) for name in contig_list])  # :72-73
-    depth = None if is_combined else data.values[:, 136:len(data.values[0])].astype(np.float32)
-    with tempfile.TemporaryDirectory() as tdir:                                  # :83-99
-        cfasta = os.path.join(tdir, 'concatenated.fna')
-        with open(cfasta, 'wt') as concat_out:
-            for h in contig_list:
-                concat_out.write(f'>{h}\n{contig_dict[h]}\n')
-        estimate_seeds(cfasta, binned_length, args.num_process, output=out, orf_finder=args.orf_finder,
-                       prodigal_output_faa=args.prodigal_output_faa)
-        contig2marker = get_marker(os.path.join(out, 'markers.hmmout'), orf_finder=args.orf_finder,
-                                   min_contig_len=binned_length, fasta_path=cfasta, contig_to_marker=True)
-    output_bin_path = os.path.join(out, 'output_bins')                           # :101-105
-    if os.path.exists(output_bin_path):
-        logger.warning(f'Previous output directory `{output_bin_path}` found. Over-writing it.')
-        shutil.rmtree(output_bin_path)
-    os.makedirs(output_bin_path, exist_ok=True)
+        net_in = torch.from_numpy(np.ascontiguousarray(_network_input(table, is_combined))).to(device)
+        embedding = model.embedding(net_in.float()).detach().cpu().numpy()
+    lengths = np.fromiter((len(contig_dict[name]) for name in names), dtype=np.int64, count=len(names))
+    depth = None if is_combined else table[:, 136:].astype(np.float32)
+    contig2marker = _markers_per_contig(names, contig_dict, out, binned_length, args)
+    bin_dir = os.path.join(out, 'output_bins')                       # :101-105
+    if os.path.exists(bin_dir):
+        logger.warning(f'Previous output directory `{bin_dir}` found. Over-writing it.')
+        shutil.rmtree(bin_dir)
+    os.makedirs(bin_dir, exist_ok=True)
     logger.debug('Running DBSCAN.')
-    dbscan_results = long_read_labels(embedding, depth, length_weight, n_sample=n_sample, is_combined=is_combined)
+    label_stack = long_read_labels(embedding, depth, lengths, n_sample=n_sample, is_combined=is_combined)
     logger.debug('Integrating results.')
-    extracted = integrate_bins(dbscan_results, contig2marker if len(contig2marker) else {}, contig_list, contig_dict,
-                               minfasta)
-    contig2ix = {}                                                               # :145-150
-    for i, cs in enumerate(extracted):
-        for c in cs:
-            contig2ix[c] = i
-    namelist = data.index.tolist()
-    contig_labels = [contig2ix.get(c, -1) for c in namelist]
-    written = write_bins(namelist, contig_labels, output_bin_path, contig_dict, minfasta=minfasta,
-                         output_tag=args.output_tag, output_compression=args.output_compression)
+    extracted = integrate_bins(label_stack, contig2marker, names, contig_dict, minfasta)
+    bin_of = {name: b for b, members in enumerate(extracted) for name in members}     # :145-150
+    contig_labels = [bin_of.get(name, -1) for name in names]
+    written = write_bins(names, contig_labels, bin_dir, contig_dict, minfasta=minfasta, output_tag=args.output_tag,
+                         output_compression=args.output_compression)
     logger.info(f'Number of bins: {len(written)}')
     written.to_csv(os.path.join(out, 'bins_info.tsv'), index=False, sep='\t')
-    pd.DataFrame({'contig': namelist, 'bin': contig_labels}).to_csv(os.path.join(out, 'contig_bins.tsv'), index=False,
-                                                                    sep='\t')
+    pd.DataFrame({'contig': names, 'bin': contig_labels}).to_csv(os.path.join(out, 'contig_bins.tsv'), index=False,
+                                                                 sep='\t')
