@@ -126,3 +126,26 @@ def test_marker_masks_and_features():
     x = long_read_features(emb, depth, 2, False)                     # long_read_cluster.py:75-81
     assert x.shape == (4, 102) and x.dtype == np.float32
     np.testing.assert_allclose(x[0, 100:], np.log(np.clip(np.array([2.0, 0.0], np.float32), 1e-6, None)))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own scikit-learn path on the host cores): one JSON line with the
+    keys the driver reads."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--contigs', '3000',
+                          '--neighbors', '20', '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'kNN-graph contigs/sec' and line['unit'] == 'contigs/s'
+    assert line['higher_is_better'] is True and line['value'] > 0 and line['n_gpus'] == 1
+    assert line['cpu_baseline']['kind'] == 'reference' and line['cpu_baseline']['cores'] >= 1
+    assert line['cpu_baseline']['value'] == line['value'] == line['e2e']['value']
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
+    # ranks other than 0 print nothing and exit 0 under torchrun
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--contigs', '3000',
+                          '--neighbors', '20', '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ''
