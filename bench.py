@@ -303,7 +303,8 @@ def run_ours(args):
             'roofline': roofline,
             'stages_ms': stage_ms,
             'knn_stats': {kk: stats[-1][kk] for kk in ('algo_used', 'n_chunks', 'n_filter_launches', 'n_fallback_rows', 'n_candidates',
-                                                       'n_reranked', 'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
+                                                       'n_reranked', 'n_retry_rows', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate',
+                                                       'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
         }
         if world == 1 and not args.no_cpu_baseline:
             Xn = X_host.numpy()

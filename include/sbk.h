@@ -85,9 +85,16 @@ typedef struct sbk_knn_stats {
   int64_t n_fail_certificate;    /* (k+1)-th exact distance not below the exclusion bound */
   int32_t n_split_cols;          /* high-energy columns given an FP16 hi+lo representation */
   int32_t reserved2;
+  int64_t n_retry_rows;          /* rows with more survivors than the warp rerank sorts -> block-per-row rerank */
 } sbk_knn_stats;
 
 int sbk_version(void);
+/* sha256 prefix (32 hex digits) of the sources this binary was compiled from; the Python binding recomputes it
+ * from the tree and refuses a stale binary. */
+const char* sbk_source_hash(void);
+/* 1 in the profiling build (libsbk_probe.so, -DSBK_ENABLE_PROBES: environment switches alter the pipeline and
+ * results may be meaningless), 0 in the product library, which never reads the environment. */
+int sbk_probes_enabled(void);
 const char* sbk_last_error(void);
 /* Number of CUDA devices visible (0 when none / no driver). */
 int sbk_device_count(void);

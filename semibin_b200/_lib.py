@@ -7,7 +7,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libsbk.so')
+# SBK_LIB_VARIANT=probe selects the profiling build (libsbk_probe.so); nothing else does
+PROBES = os.environ.get('SBK_LIB_VARIANT', '') == 'probe'
+LIB_PATH = os.path.join(HERE, 'libsbk_probe.so' if PROBES else 'libsbk.so')
 
 SBK_F32, SBK_F64 = 0, 1
 KNN_AUTO, KNN_EXACT, KNN_TENSOR = 0, 1, 2
@@ -25,7 +27,7 @@ class KnnStats(C.Structure):
                 ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float),
                 ('n_reranked', C.c_int64), ('n_fail_overflow', C.c_int64), ('n_fail_few', C.c_int64),
                 ('n_fail_survivors', C.c_int64), ('n_fail_certificate', C.c_int64),
-                ('n_split_cols', C.c_int32), ('reserved2', C.c_int32)]
+                ('n_split_cols', C.c_int32), ('reserved2', C.c_int32), ('n_retry_rows', C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
@@ -40,6 +42,8 @@ _lib = None
 # name -> (restype, argtypes); every symbol include/sbk.h declares
 SIGNATURES = {
     'sbk_version': (C.c_int, []),
+    'sbk_source_hash': (C.c_char_p, []),
+    'sbk_probes_enabled': (C.c_int, []),
     'sbk_last_error': (C.c_char_p, []),
     'sbk_device_count': (C.c_int, []),
     'sbk_knn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int]),
@@ -83,6 +87,15 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    # a binary that was not built from the sources in this tree is refused (stale prebuilt .so)
+    from . import _build
+    want = _build.source_hash(PROBES)
+    got = lib.sbk_source_hash().decode('ascii', 'replace')
+    if got != want:
+        raise SbkError(f'{LIB_PATH} was built from other sources (embedded hash {got}, tree {want}): rebuild with '
+                       '`python -m semibin_b200._build`')
+    if bool(lib.sbk_probes_enabled()) != PROBES:
+        raise SbkError(f'{LIB_PATH}: probe build flag does not match SBK_LIB_VARIANT')
     _lib = lib
     return lib
 

@@ -25,16 +25,27 @@ static constexpr int KNN_MAX_K = 1023;
 static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk (exact path)
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
 
+// Profiling switches exist only in the probe build (-DSBK_ENABLE_PROBES, libsbk_probe.so): the product library
+// never reads the environment, so a stray variable cannot change or corrupt a result.
+#ifdef SBK_ENABLE_PROBES
+static int probe_mode() { static const int v = getenv("SBK_TC_PROBE") ? atoi(getenv("SBK_TC_PROBE")) : 0; return v; }
+static bool probe_block_rerank() { static const int v = getenv("SBK_RERANK_BLOCK") ? atoi(getenv("SBK_RERANK_BLOCK")) : 0; return v != 0; }
+#else
+static constexpr bool probe_block_rerank() { return false; }
+#endif
+
 struct KnnWs {
   uint32_t* cand_idx; uint2* cand_pair; int32_t* cand_count; double* bound;   // exact path: columns; tensor path: (column, score)
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
+  uint32_t* tlist; int32_t* tcount; int32_t* retry;     // tensor path: survivor lists of tc_select, rows handed back by the warp rerank
   void* tc;                                             // tensor-path staging area
   size_t tc_bytes;
 };
 
 struct KnnShape {
   int algo; long long chunk; long long cand_stride; int n_split; long long fb_rows; int fb_split;
+  int tcap; long long retry_cap;                        // warp rerank: survivor capacity per row (0 = block rerank), retry list length
   TcPlan plan;
 };
 
@@ -64,6 +75,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     s.fb_split = 32;                                  // few rows x all references: parallelise over references
     if (n_ref / 2048 < s.fb_split) s.fb_split = (int)std::max<long long>(1, n_ref / 2048);
     while (s.fb_split > 1 && (size_t)s.fb_split * k1 * 12 > 150 * 1024) s.fb_split /= 2;
+    s.tcap = rerank_warp_supported(dtype, d, k) ? rerank_warp_cap(k) : 0;
+    s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 8) : 0;
   }
   return s;
 }
@@ -76,9 +89,12 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, i
   w.bound = a.take<double>((size_t)s.chunk);
   w.fail_rows = a.take<int32_t>((size_t)n_q + (size_t)s.fb_rows + 1);     // all failing rows of the call, then the fallback's own sink
   w.n_fail = a.take<int>(64);
-  w.cand_total = a.take<unsigned long long>(8);   // [0] candidates emitted, [1] candidates reranked in FP64
+  w.cand_total = a.take<unsigned long long>(16);  // [0] candidates emitted, [1] reranked in FP64, [2..5] failure classes; [8..] same, retry launches
   w.fb_idx = a.take<uint32_t>((size_t)s.fb_rows * s.fb_split * k1);
   w.fb_count = a.take<int32_t>((size_t)s.fb_rows + 1);
+  w.tlist = a.take<uint32_t>((size_t)s.chunk * s.tcap);
+  w.tcount = a.take<int32_t>((size_t)s.chunk + 1);
+  w.retry = a.take<int32_t>((size_t)s.retry_cap + 1);
   w.tc = nullptr; w.tc_bytes = 0;
   if (s.algo == SBK_KNN_TENSOR) {
     w.tc_bytes = tc_workspace_bytes(s.plan, n_ref, s.chunk);
@@ -116,7 +132,21 @@ struct StageTimer {
 
 using namespace sbk;
 
+#ifndef SBK_SOURCE_HASH_STR
+#define SBK_SOURCE_HASH_STR "SBK_SOURCE_HASH=unknown"
+#endif
+// "SBK_SOURCE_HASH=<sha256 prefix of the sources this binary was built from>" (semibin_b200/_build.py)
+static const char g_source_hash[] = SBK_SOURCE_HASH_STR;
+
 extern "C" int sbk_version(void) { return SBK_VERSION; }
+extern "C" const char* sbk_source_hash(void) { return g_source_hash + 16; }
+extern "C" int sbk_probes_enabled(void) {
+#ifdef SBK_ENABLE_PROBES
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* sbk_last_error(void) { return g_err; }
 
 extern "C" int sbk_device_count(void) {
@@ -174,7 +204,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   sbk_knn_stats st; memset(&st, 0, sizeof(st));
   st.algo_used = s.algo;
   const size_t esz = dtype == SBK_F32 ? 4 : 8;
-  SBK_CUDA_CHECK(cudaMemsetAsync(w.cand_total, 0, 8 * sizeof(unsigned long long), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(w.cand_total, 0, 16 * sizeof(unsigned long long), stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail, 0, 64 * sizeof(int), stream));      // [0] failing rows of the whole call
 
   StageTimer tm(stream, stats != nullptr);
@@ -220,16 +250,31 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       int nfl = 0, nrf = 0;
       rc = tc_filter_chunk(&tcs, s.plan, row0, cn, k, w.cand_pair, w.cand_count, w.bound, &nfl, &nrf, stream);
       st.n_filter_launches += nfl; st.n_launches += nfl + nrf - 1;
-      if (getenv("SBK_TC_PROBE") && atoi(getenv("SBK_TC_PROBE")) > 0) {   // profiling aid: time the filter variants only
+#ifdef SBK_ENABLE_PROBES
+      if (probe_mode() > 0) {                    // profiling build only: time the filter variants, results are meaningless
         tm.end(h); SBK_CUDA_CHECK(cudaStreamSynchronize(stream)); st.n_chunks++; continue;
       }
+#endif
       tm.end(h);
       if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_rerank);
-      rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
-                         w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+      if (s.tcap > 0 && !probe_block_rerank()) {
+        // final selection (thr / bound tightened from the complete lists) -> warp-per-row rerank of the survivors ->
+        // block-per-row rerank of the few rows with more survivors than a warp sorts (device-side list, no host sync)
+        SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
+        rc = tc_select_chunk(&tcs, s.plan, row0, cn, k, w.cand_pair, w.cand_count, w.bound, w.tlist, w.tcount, s.tcap, w.cand_total, stream);
+        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.tlist, w.tcount, s.tcap, w.bound, k, od, oi, row0,
+                                         w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap, w.cand_total, stream);
+        if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+                                    w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total + 8, stream,
+                                    w.retry, w.n_fail + 2, (int)s.retry_cap);
+        st.n_launches += 4;
+      } else {
+        rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+                           w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+        st.n_launches += 3;
+      }
       tm.end(h);
-      st.n_launches += 3;
       if (rc) { drop_events(); return rc; }
     }
     if (sink) {                                  // download this chunk while the next one is computed
@@ -274,7 +319,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       SBK_CUDA_CHECK(cudaMemcpyAsync(h_rows.data(), w.fail_rows, (size_t)h_fail * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     }
   }
-  unsigned long long h_total[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long h_total[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int h_fb_fail = 0;
   SBK_CUDA_CHECK(cudaMemcpyAsync(h_total, w.cand_total, sizeof(h_total), cudaMemcpyDeviceToHost, stream));
   SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fb_fail, w.n_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -296,9 +341,10 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   drop_events();
   if (h_fb_fail > 0) { set_error("knn: exact fallback left %d rows unresolved", h_fb_fail); return SBK_ERR_INTERNAL; }
   st.n_candidates = (long long)h_total[0];
-  st.n_reranked = (long long)h_total[1];
-  st.n_fail_overflow = (long long)h_total[2]; st.n_fail_few = (long long)h_total[3];
-  st.n_fail_survivors = (long long)h_total[4]; st.n_fail_certificate = (long long)h_total[5];
+  st.n_reranked = (long long)(h_total[1] + h_total[9]);
+  st.n_fail_overflow = (long long)(h_total[2] + h_total[10]); st.n_fail_few = (long long)(h_total[3] + h_total[11]);
+  st.n_fail_survivors = (long long)(h_total[4] + h_total[12]); st.n_fail_certificate = (long long)(h_total[5] + h_total[13]);
+  st.n_retry_rows = (long long)h_total[6];
   tm.collect();
   if (stats) *stats = st;
   return SBK_OK;

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "knn.cuh"
 #include <algorithm>
+#include <stdlib.h>
 
 namespace sbk {
 
@@ -122,8 +123,16 @@ exact_filter_kernel(const T* __restrict__ X, long long n_ref, int d, long long l
       }
     }
     __syncthreads();
+    // every thread snapshots the counts BETWEEN two barriers: a warp that finds nothing to prune must not run
+    // ahead into the next batch's atomicAdd while a slower warp still reads cnt[] (it could then enter the sort,
+    // which contains barriers, alone)
+    int n_snap[XF_QT];
+#pragma unroll
+    for (int qi = 0; qi < XF_QT; ++qi) n_snap[qi] = cnt[qi];
+    __syncthreads();
+#pragma unroll
     for (int qi = 0; qi < XF_QT; ++qi) {
-      int n = cnt[qi];                               // uniform across the block
+      int n = n_snap[qi];                            // uniform across the block
       if (n > cap - XF_THREADS) {
         n = min(n, cap);
         for (int t = n + tid; t < cap; t += XF_THREADS) { key[(size_t)qi * cap + t] = INF; id[(size_t)qi * cap + t] = 0xffffffffu; }
@@ -243,7 +252,8 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               const int32_t* __restrict__ orig, int k, int ncand_cap, int pmax,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
-              unsigned long long* __restrict__ totals) {
+              unsigned long long* __restrict__ totals,
+              const int32_t* __restrict__ slot_list, const int* __restrict__ n_list, int list_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* q = reinterpret_cast<double*>(smem_raw);           // [d]
   double* key = q + ((d + 1) & ~1);                          // [pmax]  survivors: exact d2
@@ -258,7 +268,11 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   __shared__ unsigned long long s_dmax;
 
   const int tid = threadIdx.x;
-  const long long slot = blockIdx.x;
+  long long slot = blockIdx.x;
+  if (slot_list) {                               // retry mode: the slots the warp kernel handed back (device-side count)
+    if ((int)blockIdx.x >= min(*n_list, list_cap)) return;
+    slot = slot_list[blockIdx.x];
+  }
   const long long row = rows ? (long long)rows[slot] : (q_begin + slot);
   const int k1 = k + 1;
   const int seg_cap = (int)(cand_stride / n_seg);
@@ -391,12 +405,16 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     // nearest: compact [m1, m) down to those within dmax (keeps the sort at 256 entries for almost every row)
     {
       double kk[4]; uint32_t ii[4]; int nk = 0;
+      bool lost = false;                           // pmax = 2048 (k >= 512): a thread may own up to 6 entries of [m1, m)
       const double dmax = __longlong_as_double((long long)s_dmax);
       for (int c = m1 + tid; c < m; c += RR_THREADS) {
         const double v = key[c];
-        if (v <= dmax && nk < 4) { kk[nk] = v; ii[nk] = id[c]; ++nk; }
+        if (v <= dmax) { if (nk < 4) { kk[nk] = v; ii[nk] = id[c]; ++nk; } else lost = true; }
       }
-      __syncthreads();
+      if (__syncthreads_or(lost ? 1 : 0)) {        // never drop a survivor silently: the exact filter takes the row
+        if (tid == 0) { int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[4], 1ull); }
+        return;
+      }
       if (nk) {
         const int p0 = atomicAdd(&s_m2, nk);
 #pragma unroll
@@ -522,6 +540,211 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
   }
 }
 
+// ---------------------------------------------------------------------------
+// warp-per-row rerank of the survivor lists of tc_select_kernel (tensor path, the common case)
+// ---------------------------------------------------------------------------
+// One warp owns one query row from the first gather to the last store: no block barriers, 24+ rows in flight
+// per SM, the gathers of two candidate groups outstanding per lane.  The row's survivors T (k+1 plus the few
+// whose lower bound sits inside the slack, already mapped to rows) are evaluated in FP64 by groups of LPC lanes
+// (RegQuery: the lane's slice of the query lives in registers), the squared distances are parked in 2 KB of
+// shared memory per warp, then sorted by (d2, row) in REGISTERS by a bitonic network over the warp (32 * EPL
+// elements, EPL per lane, blocked: strides below EPL are register-to-register, the others one shuffle per word).
+// d2 >= 0, so its bit pattern orders like the value and (pattern, row) compares as integers.
+// Certificate, self removal and sklearn's rounding recipe as in rerank_kernel.
+static constexpr int RW_WARPS = 8;
+__device__ __forceinline__ bool rw_less(unsigned long long ka, uint32_t ia, unsigned long long kb, uint32_t ib) {
+  return (ka < kb) | ((ka == kb) & (ia < ib));      // bitwise on purpose: no short-circuit branches
+}
+// One compare-exchange layer (SIZE, STRIDE) of the bitonic network over NEL = 32 * EPL elements, element index
+// i = lane * EPL + u; templates so that every register index is a compile-time constant.
+template <int EPL, int SIZE, int STRIDE>
+struct RwLayer {
+  static __device__ __forceinline__ void run(unsigned long long (&kt)[EPL], uint32_t (&it)[EPL], int lane) {
+    if (STRIDE >= EPL) {
+      constexpr int lmask = STRIDE / EPL > 0 ? STRIDE / EPL : 1;
+      const bool lower = (lane & lmask) == 0;
+      const bool up = ((lane * EPL) & SIZE) == 0;                  // SIZE > STRIDE >= EPL: the bit lies in the lane part
+#pragma unroll
+      for (int u = 0; u < EPL; ++u) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, kt[u], lmask);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, it[u], lmask);
+        // keep the minimum (lower == up) or the maximum; identical pairs (padding) may be exchanged freely
+        const bool take = rw_less(ok, oi, kt[u], it[u]) == (lower == up);
+        kt[u] = take ? ok : kt[u]; it[u] = take ? oi : it[u];
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < EPL; ++u) {
+        if ((u & STRIDE) == 0) {
+          constexpr int vmask = STRIDE < EPL ? STRIDE : 0;
+          const int v = u | vmask;
+          const bool up = (((lane * EPL + u) & SIZE) == 0);
+          const bool swap = rw_less(kt[v], it[v], kt[u], it[u]) == up;
+          const unsigned long long lo_k = swap ? kt[v] : kt[u], hi_k = swap ? kt[u] : kt[v];
+          const uint32_t lo_i = swap ? it[v] : it[u], hi_i = swap ? it[u] : it[v];
+          kt[u] = lo_k; kt[v] = hi_k; it[u] = lo_i; it[v] = hi_i;
+        }
+      }
+    }
+    RwLayer<EPL, SIZE, STRIDE / 2>::run(kt, it, lane);
+  }
+};
+template <int EPL, int SIZE>
+struct RwLayer<EPL, SIZE, 0> {
+  static __device__ __forceinline__ void run(unsigned long long (&)[EPL], uint32_t (&)[EPL], int) {}
+};
+template <int EPL, int SIZE>
+struct RwSort {
+  static __device__ __forceinline__ void run(unsigned long long (&kt)[EPL], uint32_t (&it)[EPL], int lane) {
+    RwLayer<EPL, SIZE, SIZE / 2>::run(kt, it, lane);
+    RwSort<EPL, SIZE * 2>::run(kt, it, lane);
+  }
+};
+template <> struct RwSort<2, 128> { static __device__ __forceinline__ void run(unsigned long long (&)[2], uint32_t (&)[2], int) {} };
+template <> struct RwSort<4, 256> { static __device__ __forceinline__ void run(unsigned long long (&)[4], uint32_t (&)[4], int) {} };
+template <> struct RwSort<8, 512> { static __device__ __forceinline__ void run(unsigned long long (&)[8], uint32_t (&)[8], int) {} };
+template <> struct RwSort<16, 1024> { static __device__ __forceinline__ void run(unsigned long long (&)[16], uint32_t (&)[16], int) {} };
+
+template <typename T, int EPL, int MINB>
+__global__ void __launch_bounds__(RW_WARPS * 32, MINB)
+rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_begin, long long n_rows,
+                   const uint32_t* __restrict__ tlist, const int32_t* __restrict__ tcount, int tcap,
+                   const double* __restrict__ bound, int k,
+                   T* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
+                   int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
+                   int32_t* __restrict__ retry_slots, int* __restrict__ n_retry, int retry_cap,
+                   unsigned long long* __restrict__ totals) {
+  constexpr int NEL = 32 * EPL;
+  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC;
+  __shared__ double s_key[RW_WARPS][NEL];
+  __shared__ uint32_t s_id[RW_WARPS][NEL];
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const long long slot = (long long)blockIdx.x * RW_WARPS + wp;
+  if (slot >= n_rows) return;
+  const long long row = q_begin + slot;
+  const int m = tcount[slot];
+  const int k1 = k + 1;
+  if (m < 0 || m > NEL) {
+    if (lane == 0) {
+      bool to_fail = true;
+      if (m == TS_WIDE || m > NEL) {
+        const int p = atomicAdd(n_retry, 1);
+        if (p < retry_cap) { retry_slots[p] = (int32_t)slot; to_fail = false; if (totals) atomicAdd(&totals[6], 1ull); }
+        else if (totals) atomicAdd(&totals[4], 1ull);
+      } else if (totals) atomicAdd(&totals[m == TS_OVERFLOW ? 2 : 3], 1ull);
+      if (to_fail) { const int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
+    }
+    return;
+  }
+  const int sub = lane & (LPC - 1), g = lane / LPC;
+  const bool vec_ok = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)sizeof(T)) & 15) == 0);
+  RegQuery<T> rq;
+  rq.load(X + row * ld, d, sub, vec_ok);
+  const uint32_t* tl = tlist + slot * (long long)tcap;
+  double* key_s = s_key[wp];
+  for (int b0 = 0; b0 < m; b0 += 32) {
+    const uint32_t jl = (b0 + lane < m) ? tl[b0 + lane] : 0xffffffffu;           // 32 survivors, coalesced
+    const int nit = min(LPC, (m - b0 + CPI - 1) / CPI);
+#pragma unroll 2
+    for (int j = 0; j < nit; ++j) {
+      const uint32_t jj = __shfl_sync(0xffffffffu, jl, CPI * j + g);
+      const bool real = jj != 0xffffffffu;
+      const double v = rq.eval(X + (long long)(real ? jj : 0u) * ld, sub);
+      if (real && sub == 0) key_s[b0 + CPI * j + g] = v;
+    }
+  }
+  __syncwarp();
+  // ---- (d2 pattern, row) pairs into registers; the initial placement is irrelevant to a sort ----
+  unsigned long long kt[EPL]; uint32_t it[EPL];
+#pragma unroll
+  for (int u = 0; u < EPL; ++u) {
+    const int e = u * 32 + lane;
+    kt[u] = e < m ? (unsigned long long)__double_as_longlong(key_s[e]) : 0x7ff0000000000000ull;
+    it[u] = e < m ? tl[e] : 0xffffffffu;
+  }
+  // ---- bitonic network, element index i = lane * EPL + u ----
+  RwSort<EPL, 2>::run(kt, it, lane);
+  if (lane == 0 && totals) atomicAdd(&totals[1], (unsigned long long)m);
+  // sorted pairs back to shared memory at their rank: the certificate reads rank k, the stores below walk the
+  // ranks lane-strided (coalesced) and the FP64 sqrt stays out of an unrolled register loop
+  uint32_t* id_s = s_id[wp];
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < EPL; ++u) {
+    const int r = lane * EPL + u;
+    key_s[r] = __longlong_as_double((long long)kt[u]);
+    id_s[r] = it[u];
+  }
+  __syncwarp();
+  // ---- certificate: the (k+1)-th smallest exact d2 strictly below every excluded reference's lower bound ----
+  const double kth = key_s[k];
+  const uint32_t kth_id = id_s[k];
+  const double b = bound[slot];
+  if (m < k1 || kth_id == 0xffffffffu || !(kth < b)) {
+    if (lane == 0) { const int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[5], 1ull); }
+    return;
+  }
+  // ---- self removal by index; if absent drop entry 0 (neighbors/_base.py:943-957) ----
+  int self_rank = 0x7fffffff;
+#pragma unroll
+  for (int u = 0; u < EPL; ++u) if (it[u] == (uint32_t)row && lane * EPL + u < k1) self_rank = lane * EPL + u;
+  self_rank = __reduce_min_sync(0xffffffffu, self_rank);
+  const int drop = self_rank == 0x7fffffff ? 0 : self_rank;
+  const long long o = (row - out_row0) * (long long)k;
+#pragma unroll 1
+  for (int r = lane; r < k1; r += 32) {
+    if (r == drop) continue;
+    const int p = r - (r > drop ? 1 : 0);
+    const double d2 = key_s[r];
+    if (sizeof(T) == 4) out_dist[o + p] = (T)(float)sqrt((double)(float)d2);   // f64(f32(sqrt(f64(f32(d2)))))  _argkmin.pyx.tp:285-295
+    else out_dist[o + p] = (T)sqrt(d2);
+    out_idx[o + p] = (int32_t)id_s[r];
+  }
+}
+
+#ifdef SBK_ENABLE_PROBES
+static int rw_env_int(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+#else
+static int rw_env_int(const char*, int dflt) { return dflt; }
+#endif
+
+int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with room for the slack survivors), 0 = not supported
+  const int need = k + 1 + std::max(8, (k + 1) / 8);
+  for (int c = 64; c <= 512; c <<= 1) if (c >= need) return c;
+  return 0;
+}
+
+int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
+                       const uint32_t* tlist, const int32_t* tcount, int tcap, const double* bound, int k,
+                       void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
+                       int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream) {
+  if (n_rows <= 0) return SBK_OK;
+  const unsigned grid = (unsigned)((n_rows + RW_WARPS - 1) / RW_WARPS);
+  // 3 CTAs (24 warps) per SM at 80 registers; the probe build can drop to 2 CTAs at up to 128 registers
+  static const int occ = rw_env_int("SBK_RW_OCC", 3);
+#define SBK_RW_LAUNCH(T, EPL)                                                                                           \
+  do {                                                                                                                  \
+    if (occ == 2) rerank_warp_kernel<T, EPL, 2><<<grid, RW_WARPS * 32, 0, stream>>>((const T*)X, d, ld, q_begin, n_rows, tlist, tcount, tcap, bound, k, \
+        (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);                  \
+    else rerank_warp_kernel<T, EPL, 3><<<grid, RW_WARPS * 32, 0, stream>>>((const T*)X, d, ld, q_begin, n_rows, tlist, tcount, tcap, bound, k, \
+        (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);                  \
+  } while (0)
+#define SBK_RW_DISPATCH(T)                                                                                              \
+  do {                                                                                                                  \
+    if (tcap <= 64) SBK_RW_LAUNCH(T, 2); else if (tcap <= 128) SBK_RW_LAUNCH(T, 4);                                     \
+    else if (tcap <= 256) SBK_RW_LAUNCH(T, 8); else SBK_RW_LAUNCH(T, 16);                                               \
+  } while (0)
+  if (tcap > 512 || tcap < 1) { set_error("rerank: survivor capacity %d not supported by the warp kernel", tcap); return SBK_ERR_INVALID; }
+  if (dtype == SBK_F32) SBK_RW_DISPATCH(float); else SBK_RW_DISPATCH(double);
+#undef SBK_RW_DISPATCH
+#undef SBK_RW_LAUNCH
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}
+bool rerank_warp_supported(int dtype, int d, int k) {
+  return rerank_warp_cap(k) != 0 && d <= (dtype == SBK_F32 ? RegQuery<float>::MAX_D : RegQuery<double>::MAX_D);
+}
+
 size_t rerank_smem(int d, int pmax, int ncand_cap) {
   return (size_t)((d + 1) & ~1) * 8 + (size_t)pmax * 12 + (size_t)ncand_cap * 8 + 16;
 }
@@ -533,7 +756,7 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   const double* scale, const int32_t* orig, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const int32_t* slot_list, const int* n_list, int list_cap) {
   if (cand_pair && !orig) { set_error("rerank: tensor-path candidates need the position -> row map"); return SBK_ERR_INVALID; }
   if (n_slots <= 0) return SBK_OK;
   // tensor path: all candidates staged (ncand_cap), survivors of the two-phase cut sorted in a
@@ -544,13 +767,13 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
   size_t smem = rerank_smem(d, pmax, ncand_cap);
   if (smem > 227 * 1024) { set_error("rerank: candidate capacity %lld too large", cand_stride); return SBK_ERR_INVALID; }
   if (n_seg < 1 || n_seg > 4 || cand_stride % n_seg) { set_error("rerank: bad segmentation"); return SBK_ERR_INVALID; }
-  dim3 grid((unsigned)n_slots);
+  dim3 grid((unsigned)(slot_list ? std::min<long long>(n_slots, list_cap) : n_slots));
 #define SBK_RR_LAUNCH(T, REGQ)                                                                                          \
   do {                                                                                                                  \
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T, T, REGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     rerank_kernel<T, T, REGQ><<<grid, RR_THREADS, smem, stream>>>(                                                      \
         (const T*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale, \
-        orig, k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals);                                \
+        orig, k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals, slot_list, n_list, list_cap);                               \
   } while (0)
   if (dtype == SBK_F32) {
     if (d <= RegQuery<float>::MAX_D) SBK_RR_LAUNCH(float, true); else SBK_RR_LAUNCH(float, false);
