@@ -27,8 +27,8 @@ sys.path.insert(0, ROOT)
 
 # torchrun exports OMP_NUM_THREADS=1; the CPU legs (reference arm, cpu_baseline) must use every host
 # core, as SemiBin does through --threads (SemiBin/utils.py:71-83).  Set before numpy/sklearn load.
-if ('reference' in sys.argv) or os.environ.get('WORLD_SIZE', '1') == '1':
-    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count())
+if ('reference' in sys.argv) or os.environ.get('RANK', '0') == '0':
+    os.environ['OMP_NUM_THREADS'] = str(os.cpu_count())     # rank 0 runs the scikit-learn legs (baseline, parity spot check)
 
 import numpy as np  # noqa: E402
 
@@ -152,10 +152,12 @@ def run_reference(args):
     X = synth_embeddings(n)
     cores = os.cpu_count()
     total_steps = args.steps + args.warmup
-    # bounded sample: ~8e9 pairs per step at the default N (about 10-30 s on 8-32 cores)
+    # bounded sample, but never fewer than 4 * 256 * cores query rows: scikit-learn then parallelises over X chunks
+    # (parallel_on_X, _argkmin.pyx.tp) exactly as it does for the full graph; below that it switches to parallel_on_Y
     block = max(256, min(n, int(8.2e9 / n)))
     if total_steps > 8:
         block = max(256, block * 8 // total_steps)
+    block = min(n, max(block, 4 * 256 * cores))
     lo = (n // 2 // block) * block
     for _ in range(args.warmup):
         reference_knn_block(X, k, (lo, lo + block))
@@ -164,7 +166,8 @@ def run_reference(args):
         reference_knn_block(X, k, (lo, lo + block))
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     value = block / dt
-    sample = f'{block} query rows x all {n} references per step (sklearn NearestNeighbors brute, k+1={k + 1}), contigs/s = rows/s'
+    sample = (f'{block} query rows x all {n} references per step (sklearn NearestNeighbors brute, k+1={k + 1}), contigs/s = rows/s: '
+              f'EXTRAPOLATED to the full graph from this row block (>= 4*256*cores rows, so the chunking/threading strategy is the full graph\'s)')
     line = {
         'impl': 'reference', 'metric': 'kNN-graph contigs/sec', 'value': value, 'unit': 'contigs/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
@@ -172,7 +175,8 @@ def run_reference(args):
         'data': 'synthetic',
         'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
                    'n': n, 'd': D_EMB, 'k': k},
-        'cpu_baseline': {'value': value, 'unit': 'contigs/s', 'cores': cores, 'kind': 'reference', 'sample': sample},
+        'extrapolated': True,
+        'cpu_baseline': {'value': value, 'unit': 'contigs/s', 'cores': cores, 'kind': 'reference', 'sample': sample, 'extrapolated': True},
         'e2e': {'value': value, 'unit': 'contigs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -184,7 +188,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from semibin_b200 import _lib
-    from semibin_b200.neighbors import knn, knn_host
+    from semibin_b200.neighbors import knn, knn_host, kneighbors_graph
     from semibin_b200 import dist as sdist
 
     rank = env_int('RANK', 0)
@@ -253,19 +257,32 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
 
-    # end-to-end through the host-buffer call
+    # end-to-end through the reference-facing call: sklearn-signature kneighbors_graph on a plain numpy matrix ->
+    # scipy csr_matrix (cluster.py:94-99).  ONE process drives all N GPUs of the run (rank 0; the other ranks wait at
+    # the barrier), exactly what an unmodified single-process SemiBin gets from patch.install() + SBK_DEVICES=N.
+    X_np = X_host.numpy()
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_ms, g = None, None
+    barrier()
+    if rank == 0:
+        g = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)))     # warm-up (pins the result arrays once)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            g = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)))
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    barrier()
+    # second figure: the SPMD host-buffer call (one process per GPU, each rank its own row block)
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
         step_e2e()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+    spmd_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    te = torch.tensor([spmd_ms], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = float(te.item())
+    spmd_ms = float(te.item())
 
     # dominant kernel: tcgen05 filter pass (per launch: one launch per step per rank)
     peaks = measured_peaks()
@@ -294,11 +311,17 @@ def run_ours(args):
                        'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
             'clocks': sampler.summary(),
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
-                    # whole-job bytes: every embedding row is uploaded once (each rank its own row block, the rest
-                    # arrives over NVLink) and every result row is downloaded once (by the rank that computed it)
-                    'h2d_bytes_per_step': int(X_host.numel() * 4),
-                    'd2h_bytes_per_step': int(n * k * 8),
-                    'api': 'semibin_b200.neighbors.knn_host: pinned host embedding in (row block per rank, all-gathered over NVLink when N>1), (dist f32, idx i32) row block out in pinned host memory; row blocks downloaded while the next block is computed'},
+                    # whole-job bytes: the numpy matrix is uploaded to every device that takes part, every result row
+                    # is downloaded once as (float64 distance, int64 index), the dtypes scipy / scikit-learn hand back
+                    'h2d_bytes_per_step': int(X_host.numel() * 4) * world,
+                    'd2h_bytes_per_step': int(n * k * 16),
+                    'api': "semibin_b200.neighbors.kneighbors_graph(X_numpy, 200, mode='distance', p=2) -> scipy csr_matrix "
+                           '(the call at SemiBin/cluster.py:94-99), one process driving all N GPUs (devices=N / SBK_DEVICES): pageable '
+                           'numpy matrix in, device-widened (float64, int64) row chunks downloaded into the pinned arrays of the '
+                           'csr_matrix while the next chunk is computed',
+                    'spmd_host_buffers': {'value': n / (spmd_ms * 1e-3), 'ms_per_step': spmd_ms,
+                                          'api': 'semibin_b200.neighbors.knn_host under torchrun (one process per GPU, (dist f32, idx i32) row '
+                                                 'blocks into pinned host memory)', 'd2h_bytes_per_step': int(n * k * 8)}},
             'gpu_launches': int(sum(s['n_launches'] for s in stats)),
             'roofline': roofline,
             'stages_ms': stage_ms,
@@ -306,20 +329,33 @@ def run_ours(args):
                                                        'n_reranked', 'n_retry_rows', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate',
                                                        'sample_size', 'cand_capacity', 'order_stat', 'kpad')} if stats else None,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
+            # live scikit-learn on a row block: the reported CPU baseline (N = 1) and, at EVERY N, a parity spot check
+            # of the result the reference-facing call just returned (the csr_matrix gathered from all N devices)
             Xn = X_host.numpy()
             block = max(256, min(n, int(8.2e9 / n)))
+            if world > 1:
+                block = max(256, block // 4)
             lo_b = (n // 2 // block) * block
             t0 = time.perf_counter()
             rd, ri = reference_knn_block(Xn, k, (lo_b, lo_b + block))
             dt = time.perf_counter() - t0
-            # the baseline sample doubles as a parity spot check of the last step's result
             from oracle import compare
-            res = compare.compare_knn(rd, ri, d[lo_b:lo_b + block].cpu().numpy().astype(np.float64),
-                                      i[lo_b:lo_b + block].cpu().numpy().astype(np.int64), rtol=1e-5)
-            line['cpu_baseline'] = {'value': block / dt, 'unit': 'contigs/s', 'cores': os.cpu_count(), 'kind': 'reference',
-                                    'sample': f'{block} query rows x all {n} references, live scikit-learn brute kneighbors (the call SemiBin makes), one run',
-                                    'parity_rows_bad': res['n_rows_bad'], 'parity_rows_tied': res['n_rows_tied']}
+            gd = g.data.reshape(n, k)[lo_b:lo_b + block]
+            gi = g.indices.reshape(n, k)[lo_b:lo_b + block]
+            res = compare.compare_knn(rd, ri, gd, gi, rtol=1e-5)
+            base = {'value': block / dt, 'unit': 'contigs/s', 'cores': os.cpu_count(), 'kind': 'reference',
+                    'sample': f'{block} query rows x all {n} references, live scikit-learn brute kneighbors (the call SemiBin makes), one run',
+                    'parity_rows_bad': res['n_rows_bad'], 'parity_rows_tied': res['n_rows_tied'],
+                    'parity_of': f'kneighbors_graph csr_matrix built on {world} device(s)'}
+            if world == 1:
+                # the device-resident result of the timed steps against the same block
+                res2 = compare.compare_knn(rd, ri, d[lo_b:lo_b + block].cpu().numpy().astype(np.float64),
+                                           i[lo_b:lo_b + block].cpu().numpy().astype(np.int64), rtol=1e-5)
+                base['parity_rows_bad_device_result'] = res2['n_rows_bad']
+                line['cpu_baseline'] = base
+            else:
+                line['parity'] = base
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

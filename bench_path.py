@@ -51,18 +51,18 @@ def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
     (b_d, b_i, st_b), res['knn_feat_ms'] = timed(lambda: knn(F, k, return_stats=True))
     ths = cluster.threshold_sequence()
     cluster.edges_stage1(a_d, a_i, b_d, b_i, ths)
-    (w, rowmax, counts), res['stage1_ms'] = timed(lambda: cluster.edges_stage1(a_d, a_i, b_d, b_i, ths))
+    (keep, rowmax, counts), res['stage1_ms'] = timed(lambda: cluster.edges_stage1(a_d, a_i, b_d, b_i, ths))
     thr = cluster.pick_threshold(counts.cpu().numpy(), n, max_node)
-    cluster.edges_stage2(w, a_i, 0, thr, Dp, S, combined)
-    (X, Y, V), res['stage2_ms'] = timed(lambda: cluster.edges_stage2(w, a_i, 0, thr, Dp, S, combined))
+    cluster.edges_stage2(keep, a_d, a_i, 0, thr, Dp, S, combined)
+    (X, Y, V), res['stage2_ms'] = timed(lambda: cluster.edges_stage2(keep, a_d, a_i, 0, thr, Dp, S, combined))
     n_edges = int(X.shape[0])
     kept_dir = n_edges * 2                       # directed edges surviving ~ 2x upper triangle
     res.update(n=n, S=S, combined=combined, k=k, d_feat=int(F.shape[1]), threshold=thr, n_edges=n_edges,
                stats_emb={k2: st_a[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')},
                stats_feat={k2: st_b[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')})
-    b1 = n * k * (4 + 4 + 4 + 8) + n * k * 8
+    b1 = n * k * (4 + 4 + 4 + 8) + n * ((k + 31) // 32) * 4
     res['stage1_GBps'] = b1 / res['stage1_ms'] / 1e6
-    b2 = n * k * 12 + kept_dir * (8 * S if not combined else 0) + n_edges * 16 * 2
+    b2 = n * k * 8 + n * ((k + 31) // 32) * 4 + kept_dir * (12 * S if not combined else 0) + n_edges * 16 * 2
     res['stage2_GBps'] = b2 / res['stage2_ms'] / 1e6
     res['edge_list_total_ms'] = res['knn_emb_ms'] + res['knn_feat_ms'] + res['stage1_ms'] + res['stage2_ms']
     res['tflops_feat_filter'] = 2.0 * n * n * F.shape[1] / (st_b['ms_filter'] * 1e-3) / 1e12 if st_b['ms_filter'] else None
@@ -73,7 +73,8 @@ def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
                                               b_d.cpu().numpy(), b_i.cpu().numpy().astype(np.int64), depth,
                                               max_node=max_node, is_combined=combined, n_sample=S)
         res['cpu_sparse_restatement_s'] = time.perf_counter() - t0
-        res['parity'] = compare.compare_edges((RX, RY, RV), (X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()))
+        res['parity'] = compare.compare_edges((RX, RY, RV), (X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()), explain=8,
+                                              bound_fn=None if combined else (lambda x, y: oe.kl_weight_bound(depth, S, x, y)))
     return res
 
 

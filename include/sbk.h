@@ -9,8 +9,8 @@
  *                             SemiBin/cluster.py:94-99 (float32 embedding), :100-105 (float64
  *                             features), SemiBin/long_read_cluster.py:108-113
  *                             -> sklearn/neighbors/_base.py:756-1041, ArgKmin32/64
- *   sbk_edges_stage1        SemiBin/cluster.py:109-122  (kNN(emb) ∩ kNN(features), 1-min(d,1),
- *                             row max, per-threshold counts for the max_node search)
+ *   sbk_edges_stage1        SemiBin/cluster.py:109-122  (kNN(emb) ∩ kNN(features) as a bit mask,
+ *                             row max of 1-min(d,1), per-threshold counts for the max_node search)
  *   sbk_edges_stage2        SemiBin/cluster.py:127-151 + cal_kl :13-60 evaluated only at
  *                             surviving edges (threshold prune, KL factor, <=1e-6 cut,
  *                             upper triangle, row-major compaction)
@@ -132,33 +132,51 @@ int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t l
                    void* workspace, size_t ws_bytes, int algo,
                    sbk_knn_stats* stats, void* cuda_stream, void* copy_stream);
 
+/* The whole of sklearn.neighbors.kneighbors_graph(X, k, mode=..., p=2) for rows [q_begin, q_end) (cluster.py:94-105,
+ * long_read_cluster.py:108-113): the CSR arrays scikit-learn hands back (neighbors/_base.py:1031-1041) are written
+ * straight into HOST memory, widened on the device,
+ *   host_data    : double[(q_end-q_begin)*k]   distances in ascending order per row (float32-rounded values for
+ *                  SBK_F32 input); NULL for mode='connectivity' (the caller fills ones)
+ *   host_indices : int64[(q_end-q_begin)*k]
+ * (indptr is arange(0, n*k+1, k)).  Pinned host buffers make the per-chunk downloads overlap the next chunk's
+ * compute; device outputs, widening staging and the kNN workspace all live in `workspace`.  Both streams are
+ * synchronised on return. */
+size_t sbk_knn_graph_workspace_bytes(int dtype, int64_t n_ref, int32_t d, int64_t n_query, int32_t k, int algo);
+int sbk_knn_graph(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                  int64_t q_begin, int64_t q_end, int32_t k,
+                  double* host_data, int64_t* host_indices, int64_t chunk_rows,
+                  void* workspace, size_t ws_bytes, int algo,
+                  sbk_knn_stats* stats, void* cuda_stream, void* copy_stream);
+
 /* Number of thresholds of the max_node search (cluster.py:118-125). */
 #define SBK_MAX_THRESHOLDS 32
 
 /* Stage 1 of the short-read edge list for rows [row_begin, row_begin+n_rows):
- *   w[r*k+c] = 1 - min(emb_dist, 1) if emb_idx[r*k+c] is also in kmer_idx row r
- *              with kmer_dist != 0 and emb_dist != 0, else 0     (cluster.py:109-116)
- *   rowmax[r] = max_c w[r*k+c]                                     (cluster.py:119)
+ *   keep_bits[r*W + c/32] bit c%32 = 1  iff  emb_idx[r*k+c] is also in kmer_idx row r with kmer_dist != 0 and
+ *              emb_dist != 0  (the intersection of cluster.py:109-113; W = ceil(k/32) words per row)
+ *   rowmax[r] = max over the kept entries of w = 1 - min(emb_dist, 1), 0 for an empty row   (cluster.py:115-119)
  *   counts[m] += #{r : rowmax[r] > thresholds[m]}  (int64, caller zeroes)   (:122)
- * kmer_dist may be NULL (then every feature-graph entry counts as non-zero). */
+ * kmer_dist may be NULL (then every feature-graph entry counts as non-zero).  The N x k float64 weight matrix of
+ * the reference is never materialised: stage 2 recomputes w from emb_dist. */
 int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
                      const double* kmer_dist, const int32_t* kmer_idx,
                      int64_t n_rows, int32_t k,
                      const double* thresholds, int32_t n_thresholds,
-                     double* w, double* rowmax, long long* counts, void* cuda_stream);
+                     uint32_t* keep_bits, double* rowmax, long long* counts, void* cuda_stream);
 
-size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k);
+size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k, int64_t n_total, int32_t n_sample);
 
-/* Stage 2: drop w <= threshold, multiply by the KL factor (float32 op order of
- * cluster.py:129-141 / cal_kl numpy branch) unless is_combined, drop <= 1e-6,
- * keep column > row, emit row-major sorted.  depth is float[n_total, 2*n_sample]
- * interleaved [mean_s, var_s] for ALL contigs (columns are global indices).
+/* Stage 2: w = 1 - min(emb_dist, 1) at the kept entries, drop w <= threshold, multiply by the KL factor (float32
+ * op order of cluster.py:129-141 / cal_kl numpy branch; the float32 log of every contig's variance is evaluated
+ * once per contig and sample, correctly rounded) unless is_combined, drop <= 1e-6, keep column > row, emit
+ * row-major sorted.  depth is float[n_total, 2*n_sample] interleaved [mean_s, var_s] for ALL n_total contigs
+ * (columns are global indices).
  *   out_x/out_y : int32[capacity], out_v : double[capacity]
  *   n_edges     : device int64, number of edges produced (if > capacity only
  *                 the first `capacity` are written). */
-int sbk_edges_stage2(const double* w, const int32_t* emb_idx,
+int sbk_edges_stage2(const uint32_t* keep_bits, const float* emb_dist, const int32_t* emb_idx,
                      int64_t row_begin, int64_t n_rows, int32_t k, double threshold,
-                     const float* depth, int32_t n_sample, int is_combined,
+                     const float* depth, int64_t n_total, int32_t n_sample, int is_combined,
                      int32_t* out_x, int32_t* out_y, double* out_v, int64_t capacity,
                      long long* n_edges, void* workspace, size_t ws_bytes, void* cuda_stream);
 

@@ -68,15 +68,16 @@ def assert_knn_parity(ref_d, ref_i, got_d, got_i, rtol=1e-5, max_tied_frac=1.0, 
     return res
 
 
-def compare_edges(ref, got, rtol=1e-5, atol=2.5e-7, cut=1e-6):
+def compare_edges(ref, got, rtol=1e-5, atol=0.0, cut=1e-6, bound_fn=None, explain=0):
     """ref/got: (X int, Y int, V float64) edge lists sorted row-major.
 
-    Edges must be the same set except (a) edges whose weight sits within the
-    float32 rounding of the `<= 1e-6` survival cut (cluster.py:143) and (b)
-    edges removed/kept because of an exact-zero distance (tie class, see
-    DESIGN.md).  Weights: |dv| <= rtol*|v| + atol, atol = a few float32 ulps of
-    the KL factor (its float32 log is evaluator-dependent in the reference
-    itself: numexpr vs numpy vs libm)."""
+    Weights must agree within  rtol*|v| + bound(edge)  where `bound_fn(X, Y)` is the DERIVED per-edge bound of the
+    one evaluator-dependent operation on the path (oracle.edges.kl_weight_bound: the float32 log of cal_kl); with
+    bound_fn=None (combined mode: no KL factor) the weights must agree within rtol alone.  `atol` is kept only for
+    callers that compare against goldens of unknown provenance and defaults to 0.
+    Edges must be the same set except edges whose weight sits within that same tolerance of the `<= 1e-6` survival
+    cut (cluster.py:143) and edges removed/kept because of an exact-zero distance (tie class).
+    explain=n lists up to n offending edges (x, y, v_ref, v_got, allowed)."""
     rx, ry, rv = [np.asarray(a) for a in ref]
     gx, gy, gv = [np.asarray(a) for a in got]
     rk = rx.astype(np.int64) << 32 | ry.astype(np.int64)
@@ -86,16 +87,32 @@ def compare_edges(ref, got, rtol=1e-5, atol=2.5e-7, cut=1e-6):
     common, ri, gi = np.intersect1d(rk, gk, assume_unique=True, return_indices=True)
     only_r = np.setdiff1d(np.arange(len(rk)), ri)
     only_g = np.setdiff1d(np.arange(len(gk)), gi)
+
+    def bnd(x, y):
+        if bound_fn is None or len(x) == 0:
+            return np.zeros(len(x), np.float64)
+        return np.asarray(bound_fn(x, y), np.float64)
+
     dv = np.abs(rv[ri] - gv[gi])
-    bad_w = dv > rtol * np.abs(rv[ri]) + atol
-    near_cut_r = np.abs(rv[only_r] - cut) <= rtol * cut + atol
-    near_cut_g = np.abs(gv[only_g] - cut) <= rtol * cut + atol
-    return dict(n_ref=len(rk), n_got=len(gk), n_common=len(common), sorted_ok=sorted_ok,
-                n_only_ref=int(len(only_r)), n_only_got=int(len(only_g)),
-                n_only_ref_unexplained=int((~near_cut_r).sum()),
-                n_only_got_unexplained=int((~near_cut_g).sum()),
-                n_bad_weight=int(bad_w.sum()),
-                max_rel_w=float((dv / np.maximum(np.abs(rv[ri]), 1e-300)).max()) if len(ri) else 0.0)
+    allowed = rtol * np.abs(rv[ri]) + atol + bnd(rx[ri], ry[ri])
+    bad_w = dv > allowed
+    near_cut_r = np.abs(rv[only_r] - cut) <= rtol * cut + atol + bnd(rx[only_r], ry[only_r])
+    near_cut_g = np.abs(gv[only_g] - cut) <= rtol * cut + atol + bnd(gx[only_g], gy[only_g])
+    out = dict(n_ref=len(rk), n_got=len(gk), n_common=len(common), sorted_ok=sorted_ok,
+               n_only_ref=int(len(only_r)), n_only_got=int(len(only_g)),
+               n_only_ref_unexplained=int((~near_cut_r).sum()),
+               n_only_got_unexplained=int((~near_cut_g).sum()),
+               n_bad_weight=int(bad_w.sum()),
+               n_weight_differs=int((dv > 0).sum()),
+               n_beyond_rtol=int((dv > rtol * np.abs(rv[ri])).sum()),
+               max_rel_w=float((dv / np.maximum(np.abs(rv[ri]), 1e-300)).max()) if len(ri) else 0.0,
+               max_excess=float((dv / np.maximum(allowed, 1e-300)).max()) if len(ri) else 0.0)
+    if explain:
+        # the worst edges relative to what the derived bound allows (offenders first)
+        order = np.argsort(-(dv / np.maximum(allowed, 1e-300)))[:explain]
+        out['worst'] = [dict(x=int(rx[ri][t]), y=int(ry[ri][t]), v_ref=float(rv[ri][t]), v_got=float(gv[gi][t]),
+                             diff=float(dv[t]), allowed=float(allowed[t])) for t in order]
+    return out
 
 
 def assert_edges_parity(ref, got, **kw):

@@ -52,11 +52,15 @@ SIGNATURES = {
     'sbk_knn_stream': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_int,
                                  C.POINTER(KnnStats), C.c_void_p, C.c_void_p]),
+    'sbk_knn_graph_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int]),
+    'sbk_knn_graph': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_int,
+                                C.POINTER(KnnStats), C.c_void_p, C.c_void_p]),
     'sbk_edges_stage1': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    'sbk_edges_stage2_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
-    'sbk_edges_stage2': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double,
-                                   C.c_void_p, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+    'sbk_edges_stage2_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32, C.c_int64, C.c_int32]),
+    'sbk_edges_stage2': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_double,
+                                   C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'sbk_radius_sweep': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32,
                                    C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_double,
@@ -124,6 +128,7 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """Current torch stream of `device` (default: the current device) as a cudaStream_t."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

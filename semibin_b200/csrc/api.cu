@@ -38,14 +38,14 @@ struct KnnWs {
   uint32_t* cand_idx; uint2* cand_pair; int32_t* cand_count; double* bound;   // exact path: columns; tensor path: (column, score)
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
-  uint32_t* tlist; int32_t* tcount; int32_t* retry;     // tensor path: survivor lists of tc_select, rows handed back by the warp rerank
+  int32_t* retry;                                       // tensor path: rows handed back by the warp rerank
   void* tc;                                             // tensor-path staging area
   size_t tc_bytes;
 };
 
 struct KnnShape {
   int algo; long long chunk; long long cand_stride; int n_split; long long fb_rows; int fb_split;
-  int tcap; long long retry_cap;                        // warp rerank: survivor capacity per row (0 = block rerank), retry list length
+  int tcap; long long retry_cap;                        // warp rerank: sort capacity per row (0 = block rerank only), retry list length
   TcPlan plan;
 };
 
@@ -76,7 +76,7 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     if (n_ref / 2048 < s.fb_split) s.fb_split = (int)std::max<long long>(1, n_ref / 2048);
     while (s.fb_split > 1 && (size_t)s.fb_split * k1 * 12 > 150 * 1024) s.fb_split /= 2;
     s.tcap = rerank_warp_supported(dtype, d, k) ? rerank_warp_cap(k) : 0;
-    s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 8) : 0;
+    s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 4) : 0;
   }
   return s;
 }
@@ -92,8 +92,6 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, i
   w.cand_total = a.take<unsigned long long>(16);  // [0] candidates emitted, [1] reranked in FP64, [2..5] failure classes; [8..] same, retry launches
   w.fb_idx = a.take<uint32_t>((size_t)s.fb_rows * s.fb_split * k1);
   w.fb_count = a.take<int32_t>((size_t)s.fb_rows + 1);
-  w.tlist = a.take<uint32_t>((size_t)s.chunk * s.tcap);
-  w.tcount = a.take<int32_t>((size_t)s.chunk + 1);
   w.retry = a.take<int32_t>((size_t)s.retry_cap + 1);
   w.tc = nullptr; w.tc_bytes = 0;
   if (s.algo == SBK_KNN_TENSOR) {
@@ -179,9 +177,50 @@ extern "C" size_t sbk_knn_workspace_bytes(int dtype, int64_t n_ref, int32_t d, i
   return a.off + 1024;
 }
 
-// Host sink of sbk_knn_stream: finished query chunks are copied to host memory on `copy_stream` while the
-// next chunk is computed.
-struct HostSink { void* dist; int32_t* idx; long long chunk_rows; cudaStream_t copy_stream; };
+// Host sink of sbk_knn_stream / sbk_knn_graph: finished query chunks are copied to host memory on `copy_stream`
+// while the next chunk is computed.  wide = 1 delivers scikit-learn's CSR arrays (float64 data, int64 indices,
+// neighbors/_base.py:1031-1041): a widening kernel on the copy stream fills a device staging buffer ahead of each
+// download, so the host never converts anything.
+struct HostSink {
+  void* dist; void* idx;                 // host destinations (dist may be NULL: mode='connectivity')
+  long long chunk_rows; cudaStream_t copy_stream;
+  int wide; double* st_dist; long long* st_idx; long long st_rows;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+widen_kernel(const T* __restrict__ d, const int32_t* __restrict__ i, long long n, double* __restrict__ od,
+             long long* __restrict__ oi) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    if (od) od[t] = (double)d[t];
+    oi[t] = (long long)i[t];
+  }
+}
+
+// rows [r0, r0 + n_rows) of the device result (od / oi point at row r0) -> host rows [r0, ...); enqueued on the copy stream
+static int sink_rows(const HostSink* sk, int dtype, int k, const void* od, const int32_t* oi, long long r0, long long n_rows) {
+  const size_t esz = dtype == SBK_F32 ? 4 : 8;
+  if (!sk->wide) {
+    if (sk->dist) SBK_CUDA_CHECK(cudaMemcpyAsync((char*)sk->dist + (size_t)r0 * k * esz, od, (size_t)n_rows * k * esz, cudaMemcpyDeviceToHost, sk->copy_stream));
+    SBK_CUDA_CHECK(cudaMemcpyAsync((int32_t*)sk->idx + (size_t)r0 * k, oi, (size_t)n_rows * k * sizeof(int32_t), cudaMemcpyDeviceToHost, sk->copy_stream));
+    return SBK_OK;
+  }
+  for (long long p0 = 0; p0 < n_rows; p0 += sk->st_rows) {
+    const long long pn = std::min(sk->st_rows, n_rows - p0);
+    const long long cells = pn * k;
+    const unsigned blocks = (unsigned)std::min<long long>((cells + 255) / 256, 148 * 8);
+    const char* pd = (const char*)od + (size_t)p0 * k * esz;
+    const int32_t* pi = oi + (size_t)p0 * k;
+    const bool need_d = sk->dist != nullptr && dtype == SBK_F32;      // float64 distances are downloaded as they are
+    if (dtype == SBK_F32) widen_kernel<float><<<blocks, 256, 0, sk->copy_stream>>>((const float*)pd, pi, cells, need_d ? sk->st_dist : nullptr, sk->st_idx);
+    else widen_kernel<double><<<blocks, 256, 0, sk->copy_stream>>>((const double*)pd, pi, cells, nullptr, sk->st_idx);
+    SBK_LAUNCH_CHECK();
+    if (sk->dist) SBK_CUDA_CHECK(cudaMemcpyAsync((double*)sk->dist + (size_t)(r0 + p0) * k, need_d ? (const void*)sk->st_dist : (const void*)pd,
+                                                 (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, sk->copy_stream));
+    SBK_CUDA_CHECK(cudaMemcpyAsync((long long*)sk->idx + (size_t)(r0 + p0) * k, sk->st_idx, (size_t)cells * sizeof(long long), cudaMemcpyDeviceToHost, sk->copy_stream));
+  }
+  return SBK_OK;
+}
 
 static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
                     int64_t q_begin, int64_t q_end, int32_t k,
@@ -259,16 +298,16 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_rerank);
       if (s.tcap > 0 && !probe_block_rerank()) {
-        // final selection (thr / bound tightened from the complete lists) -> warp-per-row rerank of the survivors ->
-        // block-per-row rerank of the few rows with more survivors than a warp sorts (device-side list, no host sync)
+        // warp-per-row rerank straight from the candidate lists, then the block-per-row kernel for the few rows it
+        // hands back (device-side list, no host sync)
         SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
-        rc = tc_select_chunk(&tcs, s.plan, row0, cn, k, w.cand_pair, w.cand_count, w.bound, w.tlist, w.tcount, s.tcap, w.cand_total, stream);
-        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.tlist, w.tcount, s.tcap, w.bound, k, od, oi, row0,
-                                         w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap, w.cand_total, stream);
+        rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.cand_pair, w.cand_count, (int)s.cand_stride, w.bound, tcs.nrm, tcs.norms4,
+                                tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap,
+                                w.cand_total, stream);
         if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                                     w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total + 8, stream,
                                     w.retry, w.n_fail + 2, (int)s.retry_cap);
-        st.n_launches += 4;
+        st.n_launches += 3;
       } else {
         rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                            w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
@@ -283,8 +322,8 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       events.push_back(ev);
       SBK_CUDA_CHECK(cudaEventRecord(ev, stream));
       SBK_CUDA_CHECK(cudaStreamWaitEvent(sink->copy_stream, ev, 0));
-      SBK_CUDA_CHECK(cudaMemcpyAsync((char*)sink->dist + (size_t)c0 * k * esz, od, (size_t)cn * k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
-      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx + (size_t)c0 * k, oi, (size_t)cn * k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
+      rc = sink_rows(sink, dtype, k, od, oi, c0, cn);
+      if (rc) { drop_events(); return rc; }
     }
     st.n_chunks++;
   }
@@ -326,14 +365,14 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (sink) {
     // the recomputed rows replace what the chunk downloads carried for them (copies on one stream stay ordered)
-    if (h_fail > 4096) {
-      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->dist, out_dist, (size_t)n_q * k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
-      SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx, out_idx, (size_t)n_q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
+    if (h_fail > (sink->wide ? 256 : 4096)) {
+      rc = sink_rows(sink, dtype, k, out_dist, out_idx, 0, n_q);
+      if (rc) { drop_events(); return rc; }
     } else {
       for (int f = 0; f < h_fail; ++f) {
         const size_t r = (size_t)(h_rows[f] - q_begin);
-        SBK_CUDA_CHECK(cudaMemcpyAsync((char*)sink->dist + r * k * esz, (char*)out_dist + r * k * esz, (size_t)k * esz, cudaMemcpyDeviceToHost, sink->copy_stream));
-        SBK_CUDA_CHECK(cudaMemcpyAsync(sink->idx + r * k, out_idx + r * k, (size_t)k * sizeof(int32_t), cudaMemcpyDeviceToHost, sink->copy_stream));
+        rc = sink_rows(sink, dtype, k, (char*)out_dist + r * k * esz, out_idx + r * k, (long long)r, 1);
+        if (rc) { drop_events(); return rc; }
       }
     }
     SBK_CUDA_CHECK(cudaStreamSynchronize(sink->copy_stream));
@@ -367,8 +406,51 @@ extern "C" int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d
                               sbk_knn_stats* stats, void* cuda_stream, void* copy_stream) {
   if (!host_dist || !host_idx) { set_error("knn_stream: host output buffers required"); return SBK_ERR_INVALID; }
   if (copy_stream == cuda_stream) { set_error("knn_stream: the copy stream must differ from the compute stream"); return SBK_ERR_INVALID; }
-  HostSink sink; sink.dist = host_dist; sink.idx = host_idx; sink.chunk_rows = chunk_rows; sink.copy_stream = (cudaStream_t)copy_stream;
+  HostSink sink; memset(&sink, 0, sizeof(sink));
+  sink.dist = host_dist; sink.idx = host_idx; sink.chunk_rows = chunk_rows; sink.copy_stream = (cudaStream_t)copy_stream;
   return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
+                  (cudaStream_t)cuda_stream, &sink);
+}
+
+// ---- sbk_knn_graph: the arrays of sklearn.neighbors.kneighbors_graph straight into host memory ----
+static constexpr long long GRAPH_STAGE_ROWS = 1 << 17;
+struct GraphWs { void* dev_dist; int32_t* dev_idx; double* st_dist; long long* st_idx; long long st_rows; void* knn_ws; size_t knn_bytes; };
+static void graph_carve(Arena& a, int dtype, int64_t n_ref, int32_t d, int64_t n_q, int32_t k, int algo, GraphWs& g) {
+  const size_t esz = dtype == SBK_F32 ? 4 : 8;
+  g.dev_dist = a.take<char>((size_t)n_q * k * esz);
+  g.dev_idx = a.take<int32_t>((size_t)n_q * k);
+  g.st_rows = std::min<long long>(std::max<long long>(n_q, 1), GRAPH_STAGE_ROWS);
+  g.st_dist = a.take<double>(dtype == SBK_F32 ? (size_t)g.st_rows * k : 0);
+  g.st_idx = a.take<long long>((size_t)g.st_rows * k);
+  g.knn_bytes = sbk_knn_workspace_bytes(dtype, n_ref, d, n_q, k, algo);
+  g.knn_ws = a.take<char>(g.knn_bytes);
+}
+
+extern "C" size_t sbk_knn_graph_workspace_bytes(int dtype, int64_t n_ref, int32_t d, int64_t n_query, int32_t k, int algo) {
+  if (knn_check(dtype, n_ref, d, 0, std::min<int64_t>(n_query, n_ref), k) != SBK_OK) return 0;
+  Arena a(nullptr, 0);
+  GraphWs g;
+  graph_carve(a, dtype, n_ref, d, n_query, k, algo, g);
+  return a.off + 1024;
+}
+
+extern "C" int sbk_knn_graph(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                             int64_t q_begin, int64_t q_end, int32_t k,
+                             double* host_data, int64_t* host_indices, int64_t chunk_rows,
+                             void* workspace, size_t ws_bytes, int algo,
+                             sbk_knn_stats* stats, void* cuda_stream, void* copy_stream) {
+  int rc = knn_check(dtype, n_ref, d, q_begin, q_end, k);
+  if (rc) return rc;
+  if (!host_indices) { set_error("knn_graph: host indices buffer required"); return SBK_ERR_INVALID; }
+  if (copy_stream == cuda_stream) { set_error("knn_graph: the copy stream must differ from the compute stream"); return SBK_ERR_INVALID; }
+  Arena a(workspace, ws_bytes);
+  GraphWs g;
+  graph_carve(a, dtype, n_ref, d, q_end - q_begin, k, algo, g);
+  if (!a.ok() || workspace == nullptr) { set_error("knn_graph: workspace %zu B < required %zu B", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
+  HostSink sink; memset(&sink, 0, sizeof(sink));
+  sink.dist = host_data; sink.idx = host_indices; sink.chunk_rows = chunk_rows; sink.copy_stream = (cudaStream_t)copy_stream;
+  sink.wide = 1; sink.st_dist = g.st_dist; sink.st_idx = g.st_idx; sink.st_rows = g.st_rows;
+  return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, g.dev_dist, g.dev_idx, g.knn_ws, g.knn_bytes, algo, stats,
                   (cudaStream_t)cuda_stream, &sink);
 }
 

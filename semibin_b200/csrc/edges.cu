@@ -3,14 +3,18 @@
 // All kernels are HBM-bound streaming passes over the N x k neighbour rows.
 #include "common.cuh"
 #include "scan.cuh"
+#include <algorithm>
 
 namespace sbk {
 
 static constexpr int E_THREADS = 128;
 static constexpr int E_MAXK = 1024;
 
-// Stage 1: one warp per row.  w = 1 - min(d_emb, 1) where the column is in both graphs and neither
-// distance is an explicit zero (eliminate_zeros, cluster.py:109,112); row max (cluster.py:119).
+// Stage 1: one warp per row.  An embedding-graph entry survives the intersection iff its column is also in the
+// row of the feature graph and neither distance is an explicit zero (eliminate_zeros, cluster.py:109,112); the
+// survivors are recorded as ONE BIT per entry (keep[r][c/32] bit c%32: 25 bytes per row at k = 200) and only
+// the row maximum of w = 1 - min(d_emb, 1) (cluster.py:115-119) leaves the kernel -- stage 2 recomputes w from
+// the float32 distance it reads anyway, so the N x k float64 matrix of weights is never written or read back.
 // The feature-graph columns of the row go into a per-warp open-addressing hash set in shared memory
 // (load factor <= 0.5), so the intersection is O(k) per row and the kernel streams at HBM speed
 // instead of doing k^2 compares.
@@ -18,7 +22,7 @@ static constexpr int E1_WARPS = 4;
 __global__ void __launch_bounds__(E1_WARPS * 32)
 edges_stage1_kernel(const float* __restrict__ emb_dist, const int32_t* __restrict__ emb_idx,
                     const double* __restrict__ kmer_dist, const int32_t* __restrict__ kmer_idx,
-                    long long n_rows, int k, int tab_size, double* __restrict__ w, double* __restrict__ rowmax) {
+                    long long n_rows, int k, int tab_size, uint32_t* __restrict__ keep, double* __restrict__ rowmax) {
   extern __shared__ int32_t e1_tab[];                           // [E1_WARPS][tab_size], tab_size = power of two >= 2k
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long r = (long long)blockIdx.x * E1_WARPS + wp;
@@ -38,22 +42,27 @@ edges_stage1_kernel(const float* __restrict__ emb_dist, const int32_t* __restric
     }
   }
   __syncwarp();
+  const int words = (k + 31) >> 5;
   double mx = 0.0;                                              // implicit zeros count
-  for (int c = lane; c < k; c += 32) {
-    const int32_t j = emb_idx[r * k + c];
-    const double d = (double)emb_dist[r * k + c];
-    bool found = false;
-    uint32_t h = ((uint32_t)j * 2654435761u) & tmask;
-    for (;;) {
-      const int32_t t = tab[h];
-      if (t == j) { found = true; break; }
-      if (t == -1) break;
-      h = (h + 1) & tmask;
+  for (int c0 = 0; c0 < k; c0 += 32) {                          // warp-uniform trip count (ballot inside)
+    const int c = c0 + lane;
+    bool kept = false;
+    if (c < k) {
+      const int32_t j = emb_idx[r * k + c];
+      const double d = (double)emb_dist[r * k + c];
+      bool found = false;
+      uint32_t h = ((uint32_t)j * 2654435761u) & tmask;
+      for (;;) {
+        const int32_t t = tab[h];
+        if (t == j) { found = true; break; }
+        if (t == -1) break;
+        h = (h + 1) & tmask;
+      }
+      kept = found && d != 0.0;
+      if (kept) mx = fmax(mx, 1.0 - fmin(d, 1.0));
     }
-    double ww = 0.0;
-    if (found && d != 0.0) ww = 1.0 - fmin(d, 1.0);
-    w[r * k + c] = ww;
-    mx = fmax(mx, ww);
+    const uint32_t bits = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) keep[r * words + (c0 >> 5)] = bits;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -92,17 +101,26 @@ threshold_count_kernel(const double* __restrict__ rowmax, long long n,
   if (threadIdx.x < n_thr && blk[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)blk[threadIdx.x]);
 }
 
+// Per contig and sample: (max(m, 1e-6), max(v, 1), float32 log of that v) -- the clamps of cluster.py:24-29 and
+// the one transcendental of cal_kl, evaluated once per contig and sample (N*S logs) instead of once per edge and
+// sample.  The float32 log is taken as the correctly rounded value of the float64 log (the
+// reference's own evaluators -- numpy's SIMD log, numexpr's -- are not correctly rounded and disagree with each
+// other; oracle.edges.kl_factor_bound derives the resulting tolerance).
+__global__ void __launch_bounds__(256)
+edges_mvl_kernel(const float* __restrict__ depth, long long n_total, int n_sample, float* __restrict__ mvl) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_total * n_sample) return;
+  const float m = fmaxf(depth[2 * t], 1e-6f);
+  const float v = fmaxf(depth[2 * t + 1], 1.0f);
+  mvl[3 * t] = m; mvl[3 * t + 1] = v; mvl[3 * t + 2] = (float)log((double)v);
+}
+
 // float32 KL term of cal_kl (cluster.py:13-60, numpy evaluator :49-60), row i / col j:
 //   (log v_j - log v_i)/2 + ((m_j - m_i)^2 + v_i) / (2 v_j) - 0.5, clipped to [1e-6, 1-1e-6]
-// every operation individually rounded to float32 (no FMA contraction).  The
-// float32 log is taken as the correctly rounded value of the float64 log.
-// (mi, vi, lvi) arrive clamped / precomputed for the row: max(m, 1e-6), max(v, 1), float(log(v)).
-__device__ __forceinline__ float kl_term(float mi, float vi, float lvi, float mj, float vj) {
-  mj = fmaxf(mj, 1e-6f);
-  vj = fmaxf(vj, 1.0f);
-  const float lvj = (float)log((double)vj);
+// every operation individually rounded to float32 (no FMA contraction); halving is exact.
+__device__ __forceinline__ float kl_term(float mi, float vi, float lvi, float mj, float vj, float lvj) {
   float v_div = __fsub_rn(lvj, lvi);
-  v_div = __fdiv_rn(v_div, 2.0f);
+  v_div = __fmul_rn(v_div, 0.5f);
   float m_dif = __fsub_rn(mj, mi);
   m_dif = __fmul_rn(m_dif, m_dif);
   m_dif = __fadd_rn(m_dif, vi);
@@ -113,12 +131,13 @@ __device__ __forceinline__ float kl_term(float mi, float vi, float lvi, float mj
   return fminf(fmaxf(v_div, lo), hi);
 }
 
-// Stage 2a: one CTA per row: threshold prune, KL factor, <=1e-6 cut, upper
-// triangle, sort by column; result staged row-strided + per-row count.
+// Stage 2a: one CTA per row: the intersection bits of stage 1, w = 1 - min(d, 1) (float64, cluster.py:115-116),
+// threshold prune, KL factor, <=1e-6 cut, upper triangle, sort by column; result staged row-strided + per-row count.
 __global__ void __launch_bounds__(E_THREADS)
-edges_stage2_kernel(const double* __restrict__ w, const int32_t* __restrict__ emb_idx,
+edges_stage2_kernel(const uint32_t* __restrict__ keep_bits, const float* __restrict__ emb_dist,
+                    const int32_t* __restrict__ emb_idx,
                     long long row_begin, int k, double threshold,
-                    const float* __restrict__ depth, int n_sample, int is_combined,
+                    const float* __restrict__ mvl, int n_sample, int is_combined,
                     int32_t* __restrict__ stage_y, double* __restrict__ stage_v,
                     int32_t* __restrict__ row_cnt) {
   __shared__ double skey[E_MAXK];
@@ -129,26 +148,26 @@ edges_stage2_kernel(const double* __restrict__ w, const int32_t* __restrict__ em
   const long long r = blockIdx.x;
   const long long gi = row_begin + r;
   const int tid = threadIdx.x;
+  const int words = (k + 31) >> 5;
   if (tid == 0) s_n = 0;
-  if (!is_combined) {
-    for (int s2 = tid; s2 < n_sample; s2 += E_THREADS) {
-      const float m = fmaxf(depth[gi * 2 * n_sample + 2 * s2], 1e-6f);
-      const float v = fmaxf(depth[gi * 2 * n_sample + 2 * s2 + 1], 1.0f);
-      row_mvl[3 * s2] = m; row_mvl[3 * s2 + 1] = v; row_mvl[3 * s2 + 2] = (float)log((double)v);
-    }
-  }
+  if (!is_combined)
+    for (int t = tid; t < 3 * n_sample; t += E_THREADS) row_mvl[t] = mvl[gi * 3 * n_sample + t];
   __syncthreads();
   for (int c = tid; c < k; c += E_THREADS) {
-    double ww = w[r * k + c];
     const int32_t j = emb_idx[r * k + c];
-    // only the upper triangle is emitted (cluster.py:146-148): test it first, the KL factor of a dropped
-    // entry is never looked at
-    bool keep = (ww != 0.0) && !(ww <= threshold) && ((long long)j > gi);   // cluster.py:127-128
+    // only the upper triangle is emitted (cluster.py:146-148): test it first, the weight and the KL factor of a
+    // dropped entry are never looked at
+    bool keep = ((keep_bits[r * words + (c >> 5)] >> (c & 31)) & 1u) && ((long long)j > gi);
+    double ww = 0.0;
+    if (keep) {
+      ww = 1.0 - fmin((double)emb_dist[r * k + c], 1.0);       // :115-116
+      keep = (ww != 0.0) && !(ww <= threshold);                // :112-113 (eliminate_zeros), :127-128
+    }
     if (keep && !is_combined) {
-      const float* dj = depth + (long long)j * 2 * n_sample;
+      const float* dj = mvl + (long long)j * 3 * n_sample;
       float acc = 0.f;
       for (int s = 0; s < n_sample; ++s) {
-        const float kl = kl_term(row_mvl[3 * s], row_mvl[3 * s + 1], row_mvl[3 * s + 2], dj[2 * s], dj[2 * s + 1]);
+        const float kl = kl_term(row_mvl[3 * s], row_mvl[3 * s + 1], row_mvl[3 * s + 2], dj[3 * s], dj[3 * s + 1], dj[3 * s + 2]);
         acc = (s == 0) ? -kl : __fsub_rn(acc, kl);            // kl *= -1 ; kl_matrix -= kl
       }
       acc = __fadd_rn(acc, (float)n_sample);                   // += n_sample
@@ -214,7 +233,7 @@ extern "C" int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
                                 const double* kmer_dist, const int32_t* kmer_idx,
                                 int64_t n_rows, int32_t k,
                                 const double* thresholds, int32_t n_thresholds,
-                                double* w, double* rowmax, long long* counts, void* cuda_stream) {
+                                uint32_t* keep_bits, double* rowmax, long long* counts, void* cuda_stream) {
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   if (k < 1 || k > E_MAXK) { set_error("edges: k=%d outside [1,%d]", k, E_MAXK); return SBK_ERR_INVALID; }
   if (n_thresholds < 0 || n_thresholds > SBK_MAX_THRESHOLDS) { set_error("edges: n_thresholds=%d", n_thresholds); return SBK_ERR_INVALID; }
@@ -222,7 +241,7 @@ extern "C" int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
   const int tab_size = (int)pow2ceil((uint32_t)(2 * k));
   const size_t smem1 = (size_t)E1_WARPS * tab_size * sizeof(int32_t);
   edges_stage1_kernel<<<(unsigned)((n_rows + E1_WARPS - 1) / E1_WARPS), E1_WARPS * 32, smem1, stream>>>(
-      emb_dist, emb_idx, kmer_dist, kmer_idx, n_rows, k, tab_size, w, rowmax);
+      emb_dist, emb_idx, kmer_dist, kmer_idx, n_rows, k, tab_size, keep_bits, rowmax);
   SBK_LAUNCH_CHECK();
   if (n_thresholds > 0) {
     int blocks = (int)((n_rows + 256 * 16 - 1) / (256 * 16));
@@ -234,35 +253,45 @@ extern "C" int sbk_edges_stage1(const float* emb_dist, const int32_t* emb_idx,
   return SBK_OK;
 }
 
-extern "C" size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k) {
+extern "C" size_t sbk_edges_stage2_workspace_bytes(int64_t n_rows, int32_t k, int64_t n_total, int32_t n_sample) {
   Arena a(nullptr, 0);
   a.take<int32_t>((size_t)n_rows * k);
   a.take<double>((size_t)n_rows * k);
   a.take<int32_t>((size_t)n_rows + 1);
   a.take<long long>((size_t)n_rows + 1);
   a.take<long long>(scan_workspace_elems(n_rows));
+  a.take<float>((size_t)std::max<int64_t>(n_total, 0) * (size_t)std::max(n_sample, 0) * 3);
   return a.off + 256;
 }
 
-extern "C" int sbk_edges_stage2(const double* w, const int32_t* emb_idx,
+extern "C" int sbk_edges_stage2(const uint32_t* keep_bits, const float* emb_dist, const int32_t* emb_idx,
                                 int64_t row_begin, int64_t n_rows, int32_t k, double threshold,
-                                const float* depth, int32_t n_sample, int is_combined,
+                                const float* depth, int64_t n_total, int32_t n_sample, int is_combined,
                                 int32_t* out_x, int32_t* out_y, double* out_v, int64_t capacity,
                                 long long* n_edges, void* workspace, size_t ws_bytes, void* cuda_stream) {
   cudaStream_t stream = (cudaStream_t)cuda_stream;
   if (k < 1 || k > E_MAXK) { set_error("edges: k=%d outside [1,%d]", k, E_MAXK); return SBK_ERR_INVALID; }
-  if (!is_combined && (n_sample < 1 || depth == nullptr)) { set_error("edges: KL weighting needs depth and n_sample >= 1"); return SBK_ERR_INVALID; }
+  if (!is_combined && (n_sample < 1 || depth == nullptr || n_total < row_begin + n_rows)) {
+    set_error("edges: KL weighting needs depth[n_total, 2*n_sample] with n_sample >= 1 and n_total >= row_begin + n_rows");
+    return SBK_ERR_INVALID;
+  }
+  if (n_sample > 1024) { set_error("edges stage2: n_sample=%d > 1024", n_sample); return SBK_ERR_INVALID; }
   Arena a(workspace, ws_bytes);
   int32_t* stage_y = a.take<int32_t>((size_t)n_rows * k);
   double* stage_v = a.take<double>((size_t)n_rows * k);
   int32_t* row_cnt = a.take<int32_t>((size_t)n_rows + 1);
   long long* row_off = a.take<long long>((size_t)n_rows + 1);
   long long* bsum = a.take<long long>(scan_workspace_elems(n_rows));
+  float* mvl = a.take<float>(is_combined ? 0 : (size_t)n_total * n_sample * 3);
   if (!a.ok()) { set_error("edges stage2: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   if (n_rows <= 0) { SBK_CUDA_CHECK(cudaMemsetAsync(n_edges, 0, sizeof(long long), stream)); return SBK_OK; }
-  if (n_sample > 1024) { set_error("edges stage2: n_sample=%d > 1024", n_sample); return SBK_ERR_INVALID; }
-  edges_stage2_kernel<<<(unsigned)n_rows, E_THREADS, (size_t)(is_combined ? 0 : n_sample) * 3 * sizeof(float), stream>>>(w, emb_idx, row_begin, k, threshold, depth, n_sample,
-                                                                 is_combined, stage_y, stage_v, row_cnt);
+  if (!is_combined) {
+    const long long cells = (long long)n_total * n_sample;
+    edges_mvl_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, stream>>>(depth, n_total, n_sample, mvl);
+    SBK_LAUNCH_CHECK();
+  }
+  edges_stage2_kernel<<<(unsigned)n_rows, E_THREADS, (size_t)(is_combined ? 0 : n_sample) * 3 * sizeof(float), stream>>>(
+      keep_bits, emb_dist, emb_idx, row_begin, k, threshold, mvl, n_sample, is_combined, stage_y, stage_v, row_cnt);
   SBK_LAUNCH_CHECK();
   int rc = exclusive_scan(row_cnt, n_rows, row_off, bsum, stream);
   if (rc) return rc;

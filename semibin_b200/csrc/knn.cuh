@@ -19,12 +19,14 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
                   cudaStream_t stream, const int32_t* slot_list = nullptr, const int* n_list = nullptr, int list_cap = 0);
-// warp-per-row rerank of the survivor lists written by tc_select_chunk (tensor path); rows it cannot take
-// (TS_WIDE) are appended to retry_slots / n_retry for launch_rerank's retry mode, uncertified rows to fail_rows
+// warp-per-row rerank straight from the filter's candidate lists (tensor path); rows it cannot take (too many
+// candidates for its registers / survivors for its sort) are appended to retry_slots / n_retry for launch_rerank's
+// retry mode, uncertified rows to fail_rows
 int rerank_warp_cap(int k);
 bool rerank_warp_supported(int dtype, int d, int k);
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                       const uint32_t* tlist, const int32_t* tcount, int tcap, const double* bound, int k,
+                       const uint2* cand, const int32_t* cand_count, int cand_cap, const double* bound,
+                       const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                        int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream);
 
@@ -96,14 +98,6 @@ int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
 // tightened between launches from the candidates seen so far.
 int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, int k,
                     uint2* cand, int32_t* cand_count, double* bound, int* n_launches, int* n_refines, cudaStream_t stream);
-// Final selection over the complete candidate lists of a chunk: tightens thr / bound from the (k+1)-th smallest
-// lower bound and writes the survivors as rows: tlist[slot * tcap + 0..tcount[slot]).  Negative tcount:
-static constexpr int TS_OVERFLOW = -1;   // a candidate segment overflowed            -> exact fallback
-static constexpr int TS_WIDE = -2;       // more than tcap survivors                   -> block-per-row rerank of the full list
-static constexpr int TS_FEW = -3;        // fewer than k+1 candidates                  -> exact fallback
-int tc_select_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, int k,
-                    const uint2* cand, const int32_t* cand_count, double* bound,
-                    uint32_t* tlist, int32_t* tcount, int tcap, unsigned long long* totals, cudaStream_t stream);
 int tc_dump_scores(TcState* st, const TcPlan& p, long long n_q, float* out, long long out_ld, cudaStream_t stream);
 int tc_debug_norms(TcState* st, const TcPlan& p, long long n, float* norms4_out, double* nrm_out, int32_t* info,
                    cudaStream_t stream);

@@ -541,16 +541,22 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
 }
 
 // ---------------------------------------------------------------------------
-// warp-per-row rerank of the survivor lists of tc_select_kernel (tensor path, the common case)
+// warp-per-row rerank (tensor path, the common case)
 // ---------------------------------------------------------------------------
-// One warp owns one query row from the first gather to the last store: no block barriers, 24+ rows in flight
-// per SM, the gathers of two candidate groups outstanding per lane.  The row's survivors T (k+1 plus the few
-// whose lower bound sits inside the slack, already mapped to rows) are evaluated in FP64 by groups of LPC lanes
-// (RegQuery: the lane's slice of the query lives in registers), the squared distances are parked in 2 KB of
-// shared memory per warp, then sorted by (d2, row) in REGISTERS by a bitonic network over the warp (32 * EPL
-// elements, EPL per lane, blocked: strides below EPL are register-to-register, the others one shuffle per word).
-// d2 >= 0, so its bit pattern orders like the value and (pattern, row) compares as integers.
-// Certificate, self removal and sklearn's rounding recipe as in rerank_kernel.
+// One warp owns one query row from its candidate list to the last store: no block barriers, 24 rows in flight per
+// SM, the gathers of two candidate groups outstanding per lane.  Same two phases as rerank_kernel:
+//   select  the lower bounds of the row's candidates (<= 24 per lane, in registers) are quantised to 16 bits over
+//           their range and the (k+1)-th smallest is found bit by bit from warp-wide counts; A = everything up to
+//           it (a superset of the k+1 smallest lower bounds); positions -> rows
+//   phase 1 FP64 direct-difference d2 of A by groups of LPC lanes (RegQuery: the lane's slice of the query lives
+//           in registers); dmax = max d2 over A >= the (k+1)-th smallest exact d2 of the row
+//   phase 2 the candidates outside A whose lower bound still allows d2 <= dmax (a few per row) are evaluated too
+//   sort    (d2, row) in REGISTERS by a bitonic network over the warp (32 * EPL elements, EPL per lane, blocked:
+//           strides below EPL are register-to-register, the others one shuffle per word); d2 >= 0, so its bit
+//           pattern orders like the value and (pattern, row) compares as integers
+//   certificate, self removal and sklearn's rounding recipe as in rerank_kernel.
+// Rows with more candidates than the registers hold or more survivors than the sort holds are handed to
+// rerank_kernel through a device-side list (no host round trip).
 static constexpr int RW_WARPS = 8;
 __device__ __forceinline__ bool rw_less(unsigned long long ka, uint32_t ia, unsigned long long kb, uint32_t ib) {
   return (ka < kb) | ((ka == kb) & (ia < ib));      // bitwise on purpose: no short-circuit branches
@@ -605,54 +611,152 @@ template <> struct RwSort<4, 256> { static __device__ __forceinline__ void run(u
 template <> struct RwSort<8, 512> { static __device__ __forceinline__ void run(unsigned long long (&)[8], uint32_t (&)[8], int) {} };
 template <> struct RwSort<16, 1024> { static __device__ __forceinline__ void run(unsigned long long (&)[16], uint32_t (&)[16], int) {} };
 
+static constexpr int RW_KEYS = 24;                    // candidate lower bounds per lane held in registers
+// FP64 squared distances of the rows id_s[lo..hi) -> key_s[lo..hi); returns the lane's running maximum
+template <typename T>
+__device__ __forceinline__ double rw_distances(const T* __restrict__ X, long long ld, const RegQuery<T>& rq,
+                                               const uint32_t* id_s, double* key_s, int lo, int hi, int sub, int g, double mx) {
+  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC;
+#pragma unroll 2
+  for (int e0 = lo; e0 < hi; e0 += CPI) {               // warp-uniform trip count (shuffles inside eval)
+    const int e = e0 + g;
+    const bool real = e < hi;
+    const uint32_t jj = real ? id_s[e] : 0u;
+    const double v = rq.eval(X + (long long)jj * ld, sub);
+    if (real) { mx = fmax(mx, v); if (sub == 0) key_s[e] = v; }
+  }
+  return mx;
+}
+__device__ __forceinline__ double rw_warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 template <typename T, int EPL, int MINB>
 __global__ void __launch_bounds__(RW_WARPS * 32, MINB)
 rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_begin, long long n_rows,
-                   const uint32_t* __restrict__ tlist, const int32_t* __restrict__ tcount, int tcap,
-                   const double* __restrict__ bound, int k,
+                   const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
+                   const double* __restrict__ bound, const double* __restrict__ nrm, const float4* __restrict__ norms4,
+                   const double* __restrict__ scale, const int32_t* __restrict__ orig, int k,
                    T* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
                    int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
                    int32_t* __restrict__ retry_slots, int* __restrict__ n_retry, int retry_cap,
                    unsigned long long* __restrict__ totals) {
   constexpr int NEL = 32 * EPL;
-  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC;
+  constexpr int LPC = DistCfg<T>::LPC;
   __shared__ double s_key[RW_WARPS][NEL];
   __shared__ uint32_t s_id[RW_WARPS][NEL];
   const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
   const long long slot = (long long)blockIdx.x * RW_WARPS + wp;
   if (slot >= n_rows) return;
   const long long row = q_begin + slot;
-  const int m = tcount[slot];
   const int k1 = k + 1;
-  if (m < 0 || m > NEL) {
-    if (lane == 0) {
-      bool to_fail = true;
-      if (m == TS_WIDE || m > NEL) {
-        const int p = atomicAdd(n_retry, 1);
-        if (p < retry_cap) { retry_slots[p] = (int32_t)slot; to_fail = false; if (totals) atomicAdd(&totals[6], 1ull); }
-        else if (totals) atomicAdd(&totals[4], 1ull);
-      } else if (totals) atomicAdd(&totals[m == TS_OVERFLOW ? 2 : 3], 1ull);
-      if (to_fail) { const int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; }
-    }
-    return;
+  const int seg_cap = cand_cap >> 2;
+  // the four segments of the row as one list: element e lives at base[e + adj(segment of e)]
+  int n, p1, p2, p3; bool bad = false;
+  {
+    int c0 = cand_count[slot * 4], c1 = cand_count[slot * 4 + 1], c2 = cand_count[slot * 4 + 2], c3 = cand_count[slot * 4 + 3];
+    bad = c0 > seg_cap || c1 > seg_cap || c2 > seg_cap || c3 > seg_cap;
+    c0 = min(c0, seg_cap); c1 = min(c1, seg_cap); c2 = min(c2, seg_cap); c3 = min(c3, seg_cap);
+    p1 = c0; p2 = c0 + c1; p3 = p2 + c2; n = p3 + c3;
   }
+  const int adj1 = seg_cap - p1, adj2 = 2 * seg_cap - p2, adj3 = 3 * seg_cap - p3;
+  auto elem = [&](int e) { return e + (e >= p3 ? adj3 : e >= p2 ? adj2 : e >= p1 ? adj1 : 0); };
+  // exits: overflow / too few candidates -> exact fallback; too many for this kernel -> block-per-row rerank
+  auto hand_back = [&](int why) {                        // why: 2 overflow, 3 too few, 4 too many survivors, -1 retry
+    if (lane == 0) {
+      bool to_fail = why >= 0;
+      if (why < 0) {
+        const int p = atomicAdd(n_retry, 1);
+        if (p < retry_cap) { retry_slots[p] = (int32_t)slot; if (totals) atomicAdd(&totals[6], 1ull); }
+        else { to_fail = true; why = 4; }
+      }
+      if (to_fail) { const int p = atomicAdd(n_fail, 1); fail_rows[p] = (int32_t)row; if (totals) atomicAdd(&totals[why], 1ull); }
+    }
+  };
+  if (bad || n < k1) { hand_back(bad ? 2 : 3); return; }
+  if (n > 32 * RW_KEYS) { hand_back(-1); return; }
+  const uint2* base = cand + slot * (long long)cand_cap;
+  uint32_t* id_s = s_id[wp];
+  double* key_s = s_key[wp];
+  // ---- select: 16-bit quantised lower bounds, (k+1)-th smallest bit by bit ----
+  float lo_f, sc_f; uint32_t res = 0;
+  int mA = 0;
+  {
+    float lv[RW_KEYS];
+    uint32_t omin = 0xffffffffu, omax = 0u;
+#pragma unroll
+    for (int u = 0; u < RW_KEYS; ++u) {
+      const int e = lane + 32 * u;
+      lv[u] = 0.f;
+      if (e < n) {
+        lv[u] = __uint_as_float(base[elem(e)].y);
+        const uint32_t o = f2ord(lv[u]);
+        omin = min(omin, o); omax = max(omax, o);
+      }
+    }
+    omin = __reduce_min_sync(0xffffffffu, omin); omax = __reduce_max_sync(0xffffffffu, omax);
+    lo_f = ord2f(omin);
+    const float range = ord2f(omax) - lo_f;
+    sc_f = range > 0.f ? 65535.0f / range : 0.f;
+    uint32_t q[RW_KEYS];
+#pragma unroll
+    for (int u = 0; u < RW_KEYS; ++u)
+      q[u] = (lane + 32 * u < n) ? min(65535u, __float2uint_rz((lv[u] - lo_f) * sc_f)) : 0x10000u;
+    for (int bit = 15; bit >= 0; --bit) {               // res = the (k+1)-th smallest quantised value
+      const uint32_t t = res | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < RW_KEYS; ++u) cnt += q[u] < t ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt < k1) res = t;
+    }
+    // A = {q <= res}: at least k+1 members; positions -> rows, compacted into shared memory
+#pragma unroll
+    for (int u = 0; u < RW_KEYS; ++u) {
+      if (32 * u < n) {                                  // warp-uniform
+        const bool inA = q[u] <= res;
+        const uint32_t bal = __ballot_sync(0xffffffffu, inA);
+        const int at = mA + __popc(bal & ((1u << lane) - 1u));
+        if (inA && at < NEL) id_s[at] = (uint32_t)orig[base[elem(lane + 32 * u)].x];
+        mA += __popc(bal);
+      }
+    }
+  }
+  if (mA > NEL) { hand_back(-1); return; }
+  __syncwarp();
   const int sub = lane & (LPC - 1), g = lane / LPC;
   const bool vec_ok = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)sizeof(T)) & 15) == 0);
   RegQuery<T> rq;
   rq.load(X + row * ld, d, sub, vec_ok);
-  const uint32_t* tl = tlist + slot * (long long)tcap;
-  double* key_s = s_key[wp];
-  for (int b0 = 0; b0 < m; b0 += 32) {
-    const uint32_t jl = (b0 + lane < m) ? tl[b0 + lane] : 0xffffffffu;           // 32 survivors, coalesced
-    const int nit = min(LPC, (m - b0 + CPI - 1) / CPI);
-#pragma unroll 2
-    for (int j = 0; j < nit; ++j) {
-      const uint32_t jj = __shfl_sync(0xffffffffu, jl, CPI * j + g);
-      const bool real = jj != 0xffffffffu;
-      const double v = rq.eval(X + (long long)(real ? jj : 0u) * ld, sub);
-      if (real && sub == 0) key_s[b0 + CPI * j + g] = v;
+  // ---- phase 1 ----
+  const double dmax = rw_warp_max(rw_distances<T>(X, ld, rq, id_s, key_s, 0, mA, sub, g, 0.0));
+  // ---- phase 2: candidates outside A whose lower bound does not exclude d2 <= dmax ----
+  int m = mA;
+  {
+    const double S = scale[0];
+    // L_ij <= S^2 d2_ij - nrm_i + sigma_i; the inflation covers the rounding of dmax and of this expression
+    const double cut = S * S * dmax * (1.0 + 1e-12) - nrm[row] * (1.0 - 1e-12) + (double)norms4[row].w + 1e-300;
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      bool take = false; uint32_t pos = 0;
+      if (e < n) {
+        const uint2 pr = base[elem(e)];
+        const float l = __uint_as_float(pr.y);
+        const uint32_t qq = min(65535u, __float2uint_rz((l - lo_f) * sc_f));
+        take = qq > res && (double)l <= cut; pos = pr.x;
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, take);
+      const int at = m + __popc(bal & ((1u << lane) - 1u));
+      if (take && at < NEL) id_s[at] = (uint32_t)orig[pos];
+      m += __popc(bal);
     }
   }
+  if (m > NEL) { hand_back(-1); return; }
+  __syncwarp();
+  if (m > mA) rw_distances<T>(X, ld, rq, id_s, key_s, mA, m, sub, g, 0.0);
+  if (lane == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
   __syncwarp();
   // ---- (d2 pattern, row) pairs into registers; the initial placement is irrelevant to a sort ----
   unsigned long long kt[EPL]; uint32_t it[EPL];
@@ -660,14 +764,12 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   for (int u = 0; u < EPL; ++u) {
     const int e = u * 32 + lane;
     kt[u] = e < m ? (unsigned long long)__double_as_longlong(key_s[e]) : 0x7ff0000000000000ull;
-    it[u] = e < m ? tl[e] : 0xffffffffu;
+    it[u] = e < m ? id_s[e] : 0xffffffffu;
   }
   // ---- bitonic network, element index i = lane * EPL + u ----
   RwSort<EPL, 2>::run(kt, it, lane);
-  if (lane == 0 && totals) atomicAdd(&totals[1], (unsigned long long)m);
   // sorted pairs back to shared memory at their rank: the certificate reads rank k, the stores below walk the
   // ranks lane-strided (coalesced) and the FP64 sqrt stays out of an unrolled register loop
-  uint32_t* id_s = s_id[wp];
   __syncwarp();
 #pragma unroll
   for (int u = 0; u < EPL; ++u) {
@@ -708,36 +810,39 @@ static int rw_env_int(const char* name, int dflt) { const char* v = getenv(name)
 static int rw_env_int(const char*, int dflt) { return dflt; }
 #endif
 
-int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with room for the slack survivors), 0 = not supported
+int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with room for the phase-2 survivors), 0 = not supported
   const int need = k + 1 + std::max(8, (k + 1) / 8);
   for (int c = 64; c <= 512; c <<= 1) if (c >= need) return c;
   return 0;
 }
 
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                       const uint32_t* tlist, const int32_t* tcount, int tcap, const double* bound, int k,
+                       const uint2* cand, const int32_t* cand_count, int cand_cap, const double* bound,
+                       const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                        int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream) {
   if (n_rows <= 0) return SBK_OK;
+  const int cap = rerank_warp_cap(k);
+  if (cap == 0) { set_error("rerank: k=%d not supported by the warp kernel", k); return SBK_ERR_INVALID; }
   const unsigned grid = (unsigned)((n_rows + RW_WARPS - 1) / RW_WARPS);
   // 3 CTAs (24 warps) per SM at 80 registers; the probe build can drop to 2 CTAs at up to 128 registers
   static const int occ = rw_env_int("SBK_RW_OCC", 3);
+#define SBK_RW_ARGS(T) (const T*)X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, bound, nrm, norms4, scale, orig, k, \
+      (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals
 #define SBK_RW_LAUNCH(T, EPL)                                                                                           \
   do {                                                                                                                  \
-    if (occ == 2) rerank_warp_kernel<T, EPL, 2><<<grid, RW_WARPS * 32, 0, stream>>>((const T*)X, d, ld, q_begin, n_rows, tlist, tcount, tcap, bound, k, \
-        (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);                  \
-    else rerank_warp_kernel<T, EPL, 3><<<grid, RW_WARPS * 32, 0, stream>>>((const T*)X, d, ld, q_begin, n_rows, tlist, tcount, tcap, bound, k, \
-        (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);                  \
+    if (occ == 2) rerank_warp_kernel<T, EPL, 2><<<grid, RW_WARPS * 32, 0, stream>>>(SBK_RW_ARGS(T));                   \
+    else rerank_warp_kernel<T, EPL, 3><<<grid, RW_WARPS * 32, 0, stream>>>(SBK_RW_ARGS(T));                            \
   } while (0)
 #define SBK_RW_DISPATCH(T)                                                                                              \
   do {                                                                                                                  \
-    if (tcap <= 64) SBK_RW_LAUNCH(T, 2); else if (tcap <= 128) SBK_RW_LAUNCH(T, 4);                                     \
-    else if (tcap <= 256) SBK_RW_LAUNCH(T, 8); else SBK_RW_LAUNCH(T, 16);                                               \
+    if (cap <= 64) SBK_RW_LAUNCH(T, 2); else if (cap <= 128) SBK_RW_LAUNCH(T, 4);                                       \
+    else if (cap <= 256) SBK_RW_LAUNCH(T, 8); else SBK_RW_LAUNCH(T, 16);                                                \
   } while (0)
-  if (tcap > 512 || tcap < 1) { set_error("rerank: survivor capacity %d not supported by the warp kernel", tcap); return SBK_ERR_INVALID; }
   if (dtype == SBK_F32) SBK_RW_DISPATCH(float); else SBK_RW_DISPATCH(double);
 #undef SBK_RW_DISPATCH
 #undef SBK_RW_LAUNCH
+#undef SBK_RW_ARGS
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }

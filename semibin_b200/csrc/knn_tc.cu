@@ -474,96 +474,6 @@ tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ can
   }
 }
 
-// Final selection after the last filter launch (one warp per query row).  The candidate list is now complete:
-// it holds EVERY reference with L <= thr.  tau = the (k+1)-th smallest lower bound of the row (exact up to its
-// low TS_LOWBIT pattern bits, rounded up) is an upper bound of the k+1 smallest lower bounds, so the threshold
-// drops to tc_threshold(tau) exactly as in tc_refine_kernel, and with it the certificate bound: every reference
-// with L > thr_new -- candidate or not -- has d2 > bound_new.  The survivors T = {L <= thr_new} (k+1 plus the few
-// whose lower bound sits inside the slack) are mapped to rows and written as a dense list for the warp-per-row
-// rerank; nothing else of the candidate list is read again.
-//   tcount[slot] = |T| (<= tcap), or TS_OVERFLOW / TS_FEW (-> exact fallback), or TS_WIDE (|T| > tcap: the row is
-//   reranked by the block-per-row kernel from its full candidate list; thr/bound are left untouched for it).
-static constexpr int TS_REG = 24;               // ordered keys per lane held in registers (rows with <= 768 candidates)
-static constexpr int TS_LOWBIT = 8;
-template <bool IN_REGS>
-__device__ __forceinline__ uint32_t ts_key(const uint2* __restrict__ base, const int (&c)[4], int seg_cap, int e, int n) {
-  if (e >= n) return 0xffffffffu;
-  int sgm = 0;
-  while (e >= c[sgm]) { e -= c[sgm]; ++sgm; }                     // n <= sum of the four counts
-  return tc_f2ord(__uint_as_float(base[(long long)sgm * seg_cap + e].y));
-}
-__global__ void __launch_bounds__(256)
-tc_select_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
-                 long long row_lo, long long n_rows, int k1, int tcap,
-                 const float4* __restrict__ norms4, const double* __restrict__ nrm, const double* __restrict__ scale,
-                 int kpad, int d, const int32_t* __restrict__ orig, float* __restrict__ thr, double* __restrict__ bound,
-                 uint32_t* __restrict__ tlist, int32_t* __restrict__ tcount, unsigned long long* __restrict__ totals) {
-  const long long slot = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (slot >= n_rows) return;
-  const int seg_cap = cand_cap >> 2;
-  int c[4], n = 0; bool bad = false;
-#pragma unroll
-  for (int sgm = 0; sgm < 4; ++sgm) { c[sgm] = cand_count[slot * 4 + sgm]; bad |= c[sgm] > seg_cap; c[sgm] = min(c[sgm], seg_cap); n += c[sgm]; }
-  if (bad || n < k1) { if (lane == 0) tcount[slot] = bad ? TS_OVERFLOW : TS_FEW; return; }
-  if (lane == 0 && totals) atomicAdd(&totals[0], (unsigned long long)n);
-  const uint2* base = cand + slot * (long long)cand_cap;
-  uint32_t res = 0;                              // largest v with #(keys < v) < k1, built bit by bit
-  if (n <= 32 * TS_REG) {
-    uint32_t key[TS_REG];
-#pragma unroll
-    for (int u = 0; u < TS_REG; ++u) key[u] = ts_key<true>(base, c, seg_cap, lane + 32 * u, n);
-    for (int bit = 31; bit >= TS_LOWBIT; --bit) {
-      const uint32_t t = res | (1u << bit);
-      int cnt = 0;
-#pragma unroll
-      for (int u = 0; u < TS_REG; ++u) cnt += key[u] < t ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < k1) res = t;
-    }
-  } else {                                       // long lists: the keys are re-read (L1/L2) at every step
-    for (int bit = 31; bit >= TS_LOWBIT; --bit) {
-      const uint32_t t = res | (1u << bit);
-      int cnt = 0;
-      for (int e = lane; e < n; e += 32) cnt += ts_key<false>(base, c, seg_cap, e, n) < t ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < k1) res = t;
-    }
-  }
-  const uint32_t tau_ord = res | ((1u << TS_LOWBIT) - 1u);        // >= the k1-th smallest key
-  const long long grow = row_lo + slot;
-  float thr_new = 0.f; double bound_new = 0.0;
-  if (lane == 0) tc_threshold(tc_ord2f(tau_ord), norms4[grow], nrm[grow], kpad, d, scale[0], &thr_new, &bound_new);
-  thr_new = __shfl_sync(0xffffffffu, thr_new, 0);
-  const float thr_old = thr[slot];
-  const bool tighter = thr_new < thr_old;
-  const uint32_t sel_ord = tc_f2ord(tighter ? thr_new : thr_old);
-  // survivors, in list order: ballot compaction, positions -> rows
-  uint32_t* out = tlist + slot * (long long)tcap;
-  int m = 0;
-  for (int e0 = 0; e0 < n; e0 += 32) {
-    int e = e0 + lane;
-    bool keep = false; uint32_t pos = 0;
-    if (e < n) {
-      int sgm = 0;
-      while (e >= c[sgm]) { e -= c[sgm]; ++sgm; }
-      const uint2 pr = base[(long long)sgm * seg_cap + e];
-      keep = tc_f2ord(__uint_as_float(pr.y)) <= sel_ord; pos = pr.x;
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-    const int at = m + __popc(bal & ((1u << lane) - 1u));
-    if (keep && at < tcap) out[at] = (uint32_t)orig[pos];
-    m += __popc(bal);
-  }
-  if (lane == 0) {
-    if (m > tcap) { tcount[slot] = TS_WIDE; }
-    else {
-      tcount[slot] = m;
-      if (tighter) { thr[slot] = thr_new; bound[slot] = bound_new; }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------
 // the tcgen05 kernel
 // ---------------------------------------------------------------------------
@@ -1173,17 +1083,6 @@ int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
       }
     }
   }
-  return SBK_OK;
-}
-
-int tc_select_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, int k,
-                    const uint2* cand, const int32_t* cand_count, double* bound,
-                    uint32_t* tlist, int32_t* tcount, int tcap, unsigned long long* totals, cudaStream_t stream) {
-  if (n_rows <= 0) return SBK_OK;
-  tc_select_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, row0, n_rows, k + 1, tcap,
-                                                                    st->norms4, st->nrm, st->scale, p.kpad, st->d, st->orig,
-                                                                    st->thr, bound, tlist, tcount, totals);
-  SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
 

@@ -122,14 +122,14 @@ def build_edge_list_sharded(embedding, features, depth, *, max_edges, max_node, 
     lo, hi = row_block(n, rank, world)
     a_d, a_i = knn(emb, k, q_begin=lo, q_end=hi, algo=algo)
     b_d, b_i = knn(feat, k, q_begin=lo, q_end=hi, algo=algo)
-    w, rowmax, counts = cluster.edges_stage1(a_d, a_i, b_d, b_i, cluster.threshold_sequence())
+    keep, rowmax, counts = cluster.edges_stage1(a_d, a_i, b_d, b_i, cluster.threshold_sequence())
     counts = allreduce_counts(counts.contiguous(), group)
     threshold = cluster.pick_threshold(counts.cpu().numpy(), n, max_node)
     dep = None
     if not is_combined:
         dep = depth.float().contiguous().cuda() if isinstance(depth, torch.Tensor) else \
             torch.as_tensor(np.ascontiguousarray(depth, dtype=np.float32)).cuda()
-    X, Y, V = cluster.edges_stage2(w, a_i, lo, threshold, dep, n_sample, is_combined)
+    X, Y, V = cluster.edges_stage2(keep, a_d, a_i, lo, threshold, dep, n_sample, is_combined)
     X, Y, V = gather_edges(X, Y, V, group)
     if to_host is False:
         return X, Y, V

@@ -33,17 +33,33 @@ def _graph_arrays(graph):
     if isinstance(graph, (tuple, list)):
         dist, idx = graph
         if isinstance(dist, np.ndarray):
-            dist = torch.from_numpy(np.ascontiguousarray(dist, dtype=np.float32))
+            d32 = np.ascontiguousarray(dist, dtype=np.float32)
+            if dist.dtype != np.float32 and not np.array_equal(d32.astype(dist.dtype), dist):
+                raise NotImplementedError('dbscan_sweep: distances must be float32-representable')
+            dist = torch.from_numpy(d32)
         if isinstance(idx, np.ndarray):
             idx = torch.from_numpy(np.ascontiguousarray(idx).astype(np.int32))
+        if dist.dtype == torch.float64 and not torch.equal(dist.float().double(), dist):
+            raise NotImplementedError('dbscan_sweep: distances must be float32-representable')
         return dist.float().contiguous().cuda(), idx.int().contiguous().cuda()
+    from . import neighbors
+    kept = neighbors.device_graph_of(graph)
+    if kept is not None:                                   # the graph our kneighbors_graph drop-in just built: still on the device
+        return kept[0].float(), kept[1]
     indptr = np.asarray(graph.indptr)
     n = graph.shape[0]
     k = int(indptr[1] - indptr[0]) if n else 0
     if not np.array_equal(indptr, np.arange(0, n * k + 1, k)):
         raise NotImplementedError('dbscan(metric="precomputed") is implemented for kneighbors_graph '
                                   'output (the same number of neighbours in every row)')
-    dist = torch.from_numpy(np.asarray(graph.data, dtype=np.float32).reshape(n, k)).cuda()
+    data = np.asarray(graph.data)
+    d32 = data.astype(np.float32)
+    if data.dtype != np.float32 and not np.array_equal(d32.astype(data.dtype), data):
+        # the sweep compares float32-valued distances (what kneighbors_graph yields for the float32 features of
+        # long_read_cluster.py:75-81); a float64-valued graph would be rounded -> refuse instead of mislabelling
+        raise NotImplementedError('dbscan(metric="precomputed"): graph distances must be float32-representable '
+                                  '(build the graph from float32 features, as SemiBin does)')
+    dist = torch.from_numpy(d32.reshape(n, k)).cuda()
     idx = torch.from_numpy(np.asarray(graph.indices).astype(np.int32).reshape(n, k)).cuda()
     return dist, idx
 
@@ -141,24 +157,36 @@ def long_read_labels(embedding, depth, lengths, *, n_sample, is_combined, eps_li
 class _SweepCache:
     """Serves the reference's 12 sequential dbscan() calls (long_read_cluster.py:
     115-120) from ONE GPU sweep: the first call on a graph computes every eps of
-    EPS_GRID, later calls on the same graph object are lookups."""
+    EPS_GRID, later calls on the same graph object are lookups.
+    The cache holds STRONG references to the graph and the weights it was computed for and compares them by
+    identity, so a later graph that happens to land on a freed address can never be served stale labels; it is
+    dropped as soon as a different graph (the next sample) comes in, or by `reset()` (the kneighbors_graph drop-in
+    calls it whenever it builds a new graph)."""
 
     def __init__(self):
-        self.key = None
+        self.reset()
+
+    def reset(self):
+        self.graph = None
+        self.weight = None
+        self.min_samples = None
         self.res = {}
+
+    def _same(self, X, min_samples, sample_weight):
+        return self.graph is X and self.weight is sample_weight and self.min_samples == min_samples
 
     def __call__(self, X, eps=0.5, *, min_samples=5, metric='precomputed', sample_weight=None, n_jobs=None,
                  **kw):
         if metric != 'precomputed':
             raise ValueError('semibin_b200.dbscan implements metric="precomputed" only')
-        key = (id(X), min_samples, id(sample_weight))
-        if key != self.key or eps not in self.res:
+        same = self._same(X, min_samples, sample_weight)
+        if not same or eps not in self.res:
             grid = EPS_GRID if eps in EPS_GRID else [eps]
             labels, cores = dbscan_sweep(X, grid, min_samples=min_samples, sample_weight=sample_weight,
                                          return_core=True)
-            if key != self.key:
-                self.res = {}
-            self.key = key
+            if not same:
+                self.reset()
+                self.graph, self.weight, self.min_samples = X, sample_weight, min_samples
             for e, lab, c in zip(grid, labels, cores):
                 self.res[e] = (c, lab)
         return self.res[eps]

@@ -182,29 +182,172 @@ def _copy_stream(device):
     return s
 
 
-def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2, metric_params=None,
-                     include_self=False, n_jobs=None, algo='auto'):
-    """Same signature as sklearn.neighbors.kneighbors_graph for the arguments
-    the reference uses (cluster.py:94-105): mode='distance', p=2, n_jobs
-    ignored (it is ignored by sklearn's brute path as well).  Returns csr_matrix."""
+_last_graph = {'ref': None, 'dev': None}      # the device copy of the most recent graph (for the dbscan drop-in)
+_graph_listeners = []                         # callables run whenever a new graph is built (the dbscan cache resets)
+
+
+def device_graph_of(graph):
+    """(dist, idx) CUDA tensors of `graph` if it is the csr_matrix the last kneighbors_graph call returned and its
+    device copy was kept (keep_device=True), else None."""
+    ref = _last_graph['ref']
+    if ref is not None and ref() is graph:
+        return _last_graph['dev']
+    return None
+
+
+def _csr_from_arrays(data, indices, N, k):
+    """csr_matrix over existing arrays without scipy's constructor pass (it would down-cast the int64 indices scikit-
+    learn hands back, neighbors/_base.py:1031-1041, and copy 1.6 GB at 1M x 200)."""
     from scipy.sparse import csr_matrix
+    g = csr_matrix((N, N), dtype=np.float64)
+    g.data, g.indices = data, indices
+    g.indptr = np.arange(0, N * k + 1, k, dtype=np.int64)
+    return g
+
+
+def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2, metric_params=None,
+                     include_self=False, n_jobs=None, algo='auto', devices=None, n_blocks=4, keep_device=False,
+                     return_stats=False):
+    """Same signature as sklearn.neighbors.kneighbors_graph for the arguments
+    the reference uses (cluster.py:94-105, long_read_cluster.py:108-113): mode='distance', p=2, n_jobs
+    ignored (it is ignored by sklearn's brute path as well).  Returns csr_matrix: float64 data (float32-rounded values
+    for float32 input), int64 indices in ascending-distance order, indptr = arange * k.
+
+    One library call per device (`sbk_knn_graph`): the device widens every finished row chunk to (float64, int64)
+    and downloads it into the pinned arrays the csr_matrix is built over while the next chunk is computed; the
+    host converts nothing.  `devices` (default: the SBK_DEVICES environment variable, else the current device)
+    spreads the query rows over several GPUs of the box from this ONE process: one host thread and stream pair per
+    device, the matrix replicated, each device writing its own row block of the same host arrays -- no collective.
+    keep_device=True additionally keeps the (dist, idx) device tensors of a single-device build for
+    long_read.dbscan_sweep (see device_graph_of)."""
+    import torch
     if mode not in ('distance', 'connectivity'):
         raise ValueError("Unsupported mode, must be one of 'connectivity', or 'distance' but got '%s' instead" % mode)
     if metric not in ('minkowski', 'euclidean', 'l2') or (metric == 'minkowski' and p != 2) or metric_params:
         raise ValueError('semibin_b200.kneighbors_graph implements the Euclidean (p=2) metric only')
     if include_self not in (False, 'auto'):
         raise ValueError('include_self=True is not on the SemiBin path')
-    Xd = _as_device_matrix(X)
-    N = Xd.shape[0]
-    dist, idx = knn(Xd, n_neighbors, algo=algo)
+    _lib.require_cuda()
+    for fn in _graph_listeners:
+        fn()
     k = int(n_neighbors)
-    indices = idx.cpu().numpy().astype(np.int64).ravel()
-    if mode == 'distance':
-        data = dist.cpu().numpy().astype(np.float64).ravel()
+    if isinstance(X, np.ndarray):
+        if X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
+        Xt = torch.from_numpy(np.ascontiguousarray(X))
+    elif isinstance(X, torch.Tensor):
+        Xt = X if X.dtype in (torch.float32, torch.float64) else X.double()
+        Xt = Xt.contiguous()
     else:
-        data = np.ones(N * k, dtype=np.float64)
-    indptr = np.arange(0, N * k + 1, k, dtype=np.int64)
-    g = csr_matrix((data, indices, indptr), shape=(N, N))
-    if g.indices.dtype != np.int64:          # scipy narrows small index arrays; sklearn hands back int64
-        g.indices, g.indptr = indices, indptr
-    return g
+        raise TypeError('X must be a numpy array or a torch tensor')
+    if Xt.dim() != 2:
+        raise ValueError('X must be 2-D')
+    N = Xt.shape[0]
+    if not (0 < k < N):
+        raise ValueError(f'Expected n_neighbors < n_samples_fit, but n_neighbors = {k}, n_samples_fit = {N}, '
+                         f'n_samples = {N}')
+    devs = resolve_devices(devices, Xt)
+    # pinned result arrays: the csr_matrix is built over them (torch caches freed pinned blocks, so only the first
+    # graph of a size pays for page-locking)
+    indices = torch.empty((N * k,), dtype=torch.int64, pin_memory=True)
+    data = torch.empty((N * k,), dtype=torch.float64, pin_memory=True) if mode == 'distance' else None
+    stats = graph_rows_multi(Xt, k, devs, data, indices, algo=algo, n_blocks=n_blocks,
+                             keep_device=keep_device and len(devs) == 1)
+    data_np = data.numpy() if data is not None else np.ones(N * k, dtype=np.float64)
+    g = _csr_from_arrays(data_np, indices.numpy(), N, k)
+    import weakref
+    dev_pair = stats.pop('device_graph', None) if isinstance(stats, dict) else None
+    _last_graph['ref'], _last_graph['dev'] = (weakref.ref(g), dev_pair) if dev_pair is not None else (None, None)
+    return (g, stats) if return_stats else g
+
+
+def resolve_devices(devices, X=None):
+    """Device list of a single-process multi-GPU call: explicit list / count, else SBK_DEVICES (a count or a comma
+    separated list of ordinals), else the device X lives on, else the current device."""
+    import os
+    import torch
+    if devices is None:
+        env = os.environ.get('SBK_DEVICES', '').strip()
+        if env:
+            devices = [int(t) for t in env.split(',')] if ',' in env else int(env)
+    if devices is None:
+        if X is not None and isinstance(X, torch.Tensor) and X.is_cuda:
+            return [X.device.index]
+        return [torch.cuda.current_device()]
+    if isinstance(devices, int):
+        devices = list(range(devices))
+    devs = [torch.device(d).index if not isinstance(d, int) else d for d in devices]
+    n = torch.cuda.device_count()
+    if not devs or any(d is None or d < 0 or d >= n for d in devs) or len(set(devs)) != len(devs):
+        raise ValueError(f'devices={devices!r}: need distinct CUDA ordinals below {n}')
+    return devs
+
+
+def _graph_rows_one(Xt, k, dev, lo, hi, data, indices, algo, n_blocks, keep_device, out):
+    """Rows [lo, hi) of the graph on device `dev`, written into rows [lo, hi) of the shared host arrays."""
+    import torch
+    try:
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            device = torch.device('cuda', dev)
+            Xd = Xt.to(device, non_blocking=True) if not (Xt.is_cuda and Xt.device == device) else Xt
+            N, D = Xd.shape
+            n_q = hi - lo
+            dtype = _lib.SBK_F32 if Xd.dtype == torch.float32 else _lib.SBK_F64
+            a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
+            ws_bytes = lib.sbk_knn_graph_workspace_bytes(dtype, N, D, n_q, k, a)
+            if ws_bytes == 0:
+                raise ValueError(_lib.last_error())
+            ws = _workspace(ws_bytes, device)
+            copy = _copy_stream(device)
+            wave_rows = (torch.cuda.get_device_properties(device).multi_processor_count // 2) * 256
+            chunk = plan_chunk_rows(n_q, n_blocks, wave_rows)
+            st = _lib.KnnStats()
+            hd = None if data is None else C.c_void_p(data.data_ptr() + lo * k * 8)
+            hi_ptr = C.c_void_p(indices.data_ptr() + lo * k * 8)
+            rc = lib.sbk_knn_graph(_lib.ptr(Xd), dtype, N, D, Xd.stride(0), lo, hi, k, hd, hi_ptr, chunk,
+                                   _lib.ptr(ws), ws.numel(), a, C.byref(st), _lib.stream_ptr(device), copy.cuda_stream)
+            _lib.check(rc)
+            res = st.as_dict()
+            if keep_device:
+                # the device outputs sit at the head of the workspace (graph_carve in api.cu): copy them out
+                esz = 4 if dtype == _lib.SBK_F32 else 8
+                nd = n_q * k
+                dist = ws[:nd * esz].view(Xd.dtype).reshape(n_q, k).clone()
+                off = (nd * esz + 255) // 256 * 256
+                idx = ws[off:off + nd * 4].view(torch.int32).reshape(n_q, k).clone()
+                res['device_graph'] = (dist, idx)
+            out[dev] = res
+    except BaseException as e:       # re-raised by the caller (a thread must not swallow it)
+        out[dev] = e
+
+
+def graph_rows_multi(Xt, k, devs, data, indices, *, algo='auto', n_blocks=4, keep_device=False):
+    """Contiguous row blocks of the graph, one per device of `devs`, all written into the same host arrays.
+    One device: a plain call.  Several: one host thread per device (ctypes releases the GIL for the library call)."""
+    from .dist import row_block
+    N = Xt.shape[0]
+    out = {}
+    if len(devs) == 1:
+        _graph_rows_one(Xt, k, devs[0], 0, N, data, indices, algo, n_blocks, keep_device, out)
+    else:
+        import threading
+        if not Xt.is_cuda and not Xt.is_pinned():
+            Xt = Xt.pin_memory()              # G concurrent uploads of one host matrix: pin it once
+        threads = []
+        for r, dev in enumerate(devs):
+            lo, hi = row_block(N, r, len(devs))
+            t = threading.Thread(target=_graph_rows_one, args=(Xt, k, dev, lo, hi, data, indices, algo, n_blocks, False, out))
+            t.start()
+            threads.append(t)
+        for t in threads:
+            t.join()
+    for dev in devs:
+        if isinstance(out.get(dev), BaseException):
+            raise out[dev]
+    if len(devs) == 1:
+        return out[devs[0]]
+    agg = {'per_device': {d: out[d] for d in devs}}
+    for key in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'n_launches'):
+        agg[key] = sum(out[d][key] for d in devs)
+    return agg

@@ -21,9 +21,14 @@ def install():
         return
     _saved.update(run_embed_infomap=rc.run_embed_infomap, kneighbors_graph=rl.kneighbors_graph, dbscan=rl.dbscan,
                   cluster_long_read=rl.cluster_long_read)
+    import functools
     rc.run_embed_infomap = cluster.run_embed_infomap
-    rl.kneighbors_graph = neighbors.kneighbors_graph
-    rl.dbscan = long_read._SweepCache()
+    # the graph stays on the device for the 12 dbscan() calls that follow it (long_read_cluster.py:108-120)
+    rl.kneighbors_graph = functools.partial(neighbors.kneighbors_graph, keep_device=True)
+    cache = long_read._SweepCache()
+    neighbors._graph_listeners.append(cache.reset)          # a new graph invalidates the sweep cache
+    _saved['listener'] = cache.reset
+    rl.dbscan = cache
     rl.cluster_long_read = long_read.cluster_long_read
 
 
@@ -36,4 +41,7 @@ def uninstall():
     rl.kneighbors_graph = _saved['kneighbors_graph']
     rl.dbscan = _saved['dbscan']
     rl.cluster_long_read = _saved['cluster_long_read']
+    from . import neighbors
+    if _saved.get('listener') in neighbors._graph_listeners:
+        neighbors._graph_listeners.remove(_saved['listener'])
     _saved.clear()

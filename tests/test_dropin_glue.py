@@ -150,7 +150,7 @@ def test_run_embed_infomap_handoff_matches_reference(monkeypatch):
     emb, labels, cap = run_ours(model, data, **kw)
     np.testing.assert_array_equal(emb, ref_emb)
     np.testing.assert_array_equal(cap['edges'], np.stack([X, Y], axis=1))
-    np.testing.assert_allclose(cap['edge_weights'], V, rtol=1e-5, atol=2.5e-7)
+    np.testing.assert_array_equal(cap['edge_weights'], V)        # the oracle stands in for the GPU stages here: bit-equal
     np.testing.assert_array_equal(cap['vertex_weights'], ref_cap['vertex_weights'])
     assert cap['trials'] == ref_cap['trials'] == 10 and cap['n_vertices'] == ref_cap['n_vertices']
     assert labels.shape == (len(data),) and set(labels[0::2]) == {0} and set(labels[1::2]) == {1}
@@ -165,5 +165,5 @@ def test_run_embed_infomap_handoff_matches_reference(monkeypatch):
     X, Y, V, _, ref_cap = rc.capture_edge_handoff(rc._IdentityModel(emb_s), frame, **kw)
     _, _, cap = run_ours(rc._IdentityModel(emb_s), frame, device='cpu', **kw)
     np.testing.assert_array_equal(cap['edges'], np.stack([X, Y], axis=1))
-    np.testing.assert_allclose(cap['edge_weights'], V, rtol=1e-5, atol=2.5e-7)
+    np.testing.assert_array_equal(cap['edge_weights'], V)        # the oracle stands in for the GPU stages here: bit-equal
     np.testing.assert_array_equal(cap['vertex_weights'], ref_cap['vertex_weights'])

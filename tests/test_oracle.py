@@ -191,3 +191,49 @@ def test_integrate_edge_cases():
     # no bin with a marker: loop ends (:133-134)
     lab, n = oi.integrate_restated(np.zeros((1, 4), np.int64), [500] * 4, [np.array([], np.int32)] * 4, 100)
     assert n == 0
+
+
+def test_numpy_log_f32_ulp():
+    """The evaluator-dependent operation of the path: np.log on float32 (cal_kl, cluster.py:49-60) is not correctly
+    rounded.  Measure its error on this CPU; oracle.edges.LOG_ULPS (numpy's documented 3.83 ulp + 0.5 for the
+    kernel's correctly rounded log) must cover it."""
+    rng = np.random.default_rng(0)
+    x = np.exp(rng.uniform(0, np.log(1e9), size=2_000_000)).astype(np.float32)
+    a = np.log(x)
+    b = np.log(x.astype(np.float64))
+    ulp = np.spacing(np.abs(b).astype(np.float32)).astype(np.float64)
+    err = np.abs(a.astype(np.float64) - b) / np.maximum(ulp, 1e-300)
+    assert err.max() + 0.5 <= edges.LOG_ULPS, err.max()
+
+
+@pytest.mark.parametrize('S', [1, 3, 10])
+def test_kl_bound_covers_log_evaluators(S):
+    """Derived weight tolerance (oracle.edges.kl_factor_bound): the factor evaluated with numpy's float32 log and
+    with the correctly rounded log (the CUDA kernel's) differ by less than the bound on every pair -- including
+    pairs near saturation, where the relative difference is far above 1e-5 -- and the bound is not vacuous."""
+    n = 60000
+    emb, genome = synth.embeddings(n, seed=20241, return_genome=True)
+    dep = synth.depth_table(n, S, 20241, genome)
+    rng = np.random.default_rng(1)
+    order = np.argsort(genome, kind='stable')
+    I = np.concatenate([np.repeat(order, 8), rng.integers(0, n, 400000)])
+    J = np.concatenate([np.roll(np.repeat(order, 8), 5), rng.integers(0, n, 400000)])
+
+    def factor(mode):
+        acc = None
+        for s in range(S):
+            kl = edges.kl_edges(dep[:, 2 * s], dep[:, 2 * s + 1], I, J, mode)
+            if acc is None:
+                kl *= -1
+                acc = kl
+            else:
+                acc -= kl
+        acc += S
+        acc /= S
+        return acc.astype(np.float64)
+    a, b = factor('numpy'), factor('rounded')
+    bound = edges.kl_factor_bound(dep, S, I, J)
+    diff = np.abs(a - b)
+    assert (diff > 0).any()                                   # the evaluators do differ
+    assert (diff <= bound).all(), float((diff / bound).max())
+    assert np.median(bound) < 1e-5 and bound.max() < 1e-4     # a few float32 ulps, not a blanket tolerance
