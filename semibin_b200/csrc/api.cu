@@ -301,7 +301,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
         // warp-per-row rerank straight from the candidate lists, then the block-per-row kernel for the few rows it
         // hands back (device-side list, no host sync)
         SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
-        rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.cand_pair, w.cand_count, (int)s.cand_stride, w.bound, tcs.nrm, tcs.norms4,
+        rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
                                 tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap,
                                 w.cand_total, stream);
         if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,

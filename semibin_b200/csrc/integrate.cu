@@ -12,11 +12,15 @@
 //       smallest contamination step, then largest F1, then smallest length, then LAST in the
 //       reference's iteration order (result index, position of the bin's first live contig)
 //     (:16-47: a later bin replaces the incumbent when F1 is equal and its length is <=);
-//   * the winner's live members are retired and only the bins they belonged to are re-reduced.
+//   * the winner's live members are retired and only the bins they belonged to are re-reduced;
+//   * the whole extraction loop (select -> retire -> re-reduce, :122-143) is ONE persistent cooperative kernel, one
+//     CTA per SM, three grid barriers per extracted bin and no host round trip (as three launches per extraction the
+//     loop was pure launch latency: 70 us per bin, twice the cost of the kNN graph and the DBSCAN sweep it follows).
 // F1 / contamination are evaluated in FP64 with the reference's operation order and no contraction, so
 // comparisons agree with the Python floats bit for bit; lengths and counts are integers.
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <vector>
 #include <string.h>
@@ -25,7 +29,7 @@ namespace sbk {
 
 static constexpr int IG_MAX_R = 32;
 static constexpr int IG_MAX_WORDS = 4;          // marker bit mask words per contig (<= 256 distinct markers)
-static constexpr int IG_SEL_BLOCKS = 64;
+static constexpr int IG_SEL_BLOCKS = 64;         // partial[] holds up to 4x this many CTAs' results
 
 struct IgBin { long long weight; int total, distinct, first, count; };
 
@@ -88,17 +92,17 @@ __global__ void ig_bounds_kernel(const int32_t* __restrict__ skeys, long long n,
   if (p == n - 1 || skeys[p + 1] != k) bend[base + k] = (int32_t)(p + 1);
 }
 
-// One CTA per bin (all bins, or the dirty list).  Clears the bin's dirty flag.
-__global__ void __launch_bounds__(128)
-ig_stats_kernel(IgConst c, const int32_t* __restrict__ order, const int32_t* __restrict__ bstart,
-                const int32_t* __restrict__ bend, const unsigned char* __restrict__ alive,
-                const long long* __restrict__ lengths, const unsigned long long* __restrict__ masks,
-                const int32_t* __restrict__ list, const IgStatus* __restrict__ status, long long n_bins_all,
-                IgBin* __restrict__ bins, unsigned int* __restrict__ dirty) {
-  __shared__ long long s_w[4];
-  __shared__ unsigned long long s_m[4][IG_MAX_WORDS];
-  __shared__ int s_t[4], s_f[4], s_c[4];
-  const long long n_items = list ? (long long)status->n_dirty : n_bins_all;
+// One CTA per bin (all bins, or the dirty list).  Clears the bin's dirty flag.  Grid-stride over the items, so the
+// same body serves the initial pass (one launch) and the re-reduction inside the persistent loop.
+__device__ __forceinline__ void ig_stats_body(const IgConst& c, const int32_t* __restrict__ order, const int32_t* __restrict__ bstart,
+                                              const int32_t* __restrict__ bend, const unsigned char* __restrict__ alive,
+                                              const long long* __restrict__ lengths, const unsigned long long* __restrict__ masks,
+                                              const int32_t* __restrict__ list, long long n_items,
+                                              IgBin* __restrict__ bins, unsigned int* __restrict__ dirty) {
+  __shared__ long long s_w[8];
+  __shared__ unsigned long long s_m[8][IG_MAX_WORDS];
+  __shared__ int s_t[8], s_f[8], s_c[8];
+  const int nwarp = blockDim.x >> 5;
   for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
     const long long g = list ? (long long)list[it] : it;
     const int r = ig_result_of(c, g);
@@ -129,7 +133,7 @@ ig_stats_kernel(IgConst c, const int32_t* __restrict__ order, const int32_t* __r
     if (threadIdx.x == 0) {
       IgBin b; b.weight = 0; b.total = 0; b.first = 0x7fffffff; b.count = 0;
       unsigned long long mm[IG_MAX_WORDS] = {0ull, 0ull, 0ull, 0ull};
-      for (int q = 0; q < 4; ++q) {
+      for (int q = 0; q < nwarp; ++q) {
         b.weight += s_w[q]; b.total += s_t[q]; b.first = min(b.first, s_f[q]); b.count += s_c[q];
         for (int u = 0; u < IG_MAX_WORDS; ++u) mm[u] |= s_m[q][u];
       }
@@ -140,6 +144,14 @@ ig_stats_kernel(IgConst c, const int32_t* __restrict__ order, const int32_t* __r
     }
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(256)
+ig_stats_kernel(IgConst c, const int32_t* __restrict__ order, const int32_t* __restrict__ bstart,
+                const int32_t* __restrict__ bend, const unsigned char* __restrict__ alive,
+                const long long* __restrict__ lengths, const unsigned long long* __restrict__ masks,
+                long long n_bins_all, IgBin* __restrict__ bins, unsigned int* __restrict__ dirty) {
+  ig_stats_body(c, order, bstart, bend, alive, lengths, masks, nullptr, n_bins_all, bins, dirty);
 }
 
 // Bins that can ever be chosen (long_read_cluster.py:26-34): both quantities only shrink as contigs retire.
@@ -172,80 +184,97 @@ __device__ __forceinline__ IgKey ig_shfl_key(const IgKey& k, int o) {
   return x;
 }
 
-// Chooses the next bin.  The last CTA to finish combines the partial results and evaluates the loop
-// conditions of long_read_cluster.py:123-134.
+// The extraction loop of long_read_cluster.py:122-143 as one persistent cooperative kernel (one CTA per SM).
+// Per extracted bin:
+//   1. every CTA: arg-max over its share of the eligible bins -> partial[blockIdx]           | grid barrier
+//   2. every CTA combines ALL partials itself (the decision and the loop state are replicated, no second barrier),
+//      evaluates the loop conditions of :123-134, retires the winner's live members and lists the bins they
+//      belong to (:136-141)                                                                   | grid barrier
+//   3. the listed bins are re-reduced                                                         | grid barrier
 __global__ void __launch_bounds__(256)
-ig_select_kernel(IgConst c, const IgBin* __restrict__ bins, const int32_t* __restrict__ elig,
-                 const int* __restrict__ n_elig, IgKey* __restrict__ partial, IgStatus* __restrict__ status) {
+ig_loop_kernel(IgConst c, const long long* __restrict__ labels, const int32_t* __restrict__ order,
+               const int32_t* __restrict__ bstart, const int32_t* __restrict__ bend,
+               unsigned char* __restrict__ alive, const long long* __restrict__ lengths,
+               const unsigned long long* __restrict__ masks, IgBin* __restrict__ bins, unsigned int* __restrict__ dirty,
+               int32_t* __restrict__ dirty_list, const int32_t* __restrict__ elig, const int* __restrict__ n_elig,
+               IgKey* __restrict__ partial, IgStatus* __restrict__ status, long long* __restrict__ out_labels,
+               long long max_iter) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
   __shared__ IgKey s_k[8];
-  __shared__ bool s_last;
-  if (status->done) return;
-  IgKey best; best.bin = -1; best.cls = 9; best.f1 = 0; best.w = 0; best.r = 0; best.first = 0;
+  __shared__ int s_best;
+  // loop state, replicated in every thread of every CTA (identical by construction)
+  long long remaining_weight = status->remaining_weight, remaining_count = status->remaining_count;
+  int n_extracted = 0;
   const int n = *n_elig;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int g = elig[e];
-    const IgKey k = ig_key_of(c, bins[g], g);
-    if (ig_better(k, best)) best = k;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { const IgKey x = ig_shfl_key(best, o); if (ig_better(x, best)) best = x; }
-  if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int q = 1; q < 8; ++q) if (ig_better(s_k[q], best)) best = s_k[q];
-    partial[blockIdx.x] = best;
-    __threadfence();
-    s_last = atomicAdd(&status->sel_ticket, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!s_last || threadIdx.x != 0) return;
-  __threadfence();
-  status->sel_ticket = 0;
-  status->n_dirty = 0;                                   // the previous extraction's dirty list has been consumed
-  IgKey b = partial[0];
-  for (int q = 1; q < (int)gridDim.x; ++q) if (ig_better(partial[q], b)) b = partial[q];
-  if (status->remaining_weight < c.minfasta) { status->best = -1; status->done = 1; return; }      // :123
-  if (status->remaining_count == 1) {                                                               // :124-126
-    status->best = -2; status->cur_label = status->n_extracted; status->n_extracted += 1; return;
-  }
-  if (b.bin < 0) { status->best = -1; status->done = 1; return; }                                   // :133-134
-  status->best = b.bin; status->cur_label = status->n_extracted; status->n_extracted += 1;
-  status->remaining_weight -= bins[b.bin].weight;
-  status->remaining_count -= bins[b.bin].count;
-}
-
-// Retires the live members of the chosen bin and lists the bins they belong to (:136-141).
-__global__ void __launch_bounds__(256)
-ig_remove_kernel(IgConst c, const long long* __restrict__ labels, const int32_t* __restrict__ order,
-                 const int32_t* __restrict__ bstart, const int32_t* __restrict__ bend,
-                 unsigned char* __restrict__ alive, long long* __restrict__ out_labels,
-                 unsigned int* __restrict__ dirty, int32_t* __restrict__ dirty_list, IgStatus* __restrict__ status) {
-  if (status->done) return;
-  const int best = status->best;
-  if (best == -1) return;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (best == -2) {                                      // the single remaining contig becomes a bin of its own
-    for (long long i = t0; i < c.N; i += stride)
-      if (alive[i]) { alive[i] = 0; out_labels[i] = status->cur_label; }
-    if (t0 == 0) status->done = 1;
-    return;
-  }
-  const int r = ig_result_of(c, best);
-  const int32_t* mem = order + (long long)r * c.N;
-  const int lo = bstart[best], hi = bend[best];
-  for (long long p = lo + t0; p < hi; p += stride) {
-    const int i = mem[p];
-    if (!alive[i]) continue;
-    alive[i] = 0;
-    out_labels[i] = status->cur_label;
-    for (int q = 0; q < c.R; ++q) {
-      const long long l = labels[(long long)q * c.N + i];
-      if (l < 0) continue;
-      const long long g = c.base[q] + l;
-      if (dirty[g] == 0u && atomicExch(&dirty[g], 1u) == 0u) dirty_list[atomicAdd(&status->n_dirty, 1)] = (int32_t)g;
+  bool done = false;
+  for (long long iter = 0; iter < max_iter && !done; ++iter) {
+    // ---- 1. partial arg-max ----
+    IgKey best; best.bin = -1; best.cls = 9; best.f1 = 0; best.w = 0; best.r = 0; best.first = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int g = elig[e];
+      const IgKey kk = ig_key_of(c, bins[g], g);
+      if (ig_better(kk, best)) best = kk;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const IgKey x = ig_shfl_key(best, o); if (ig_better(x, best)) best = x; }
+    if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < (int)(blockDim.x >> 5); ++q) if (ig_better(s_k[q], best)) best = s_k[q];
+      partial[blockIdx.x] = best;
+      if (blockIdx.x == 0) status->n_dirty = 0;              // the previous extraction's dirty list has been consumed
+    }
+    grid.sync();
+    // ---- 2. decision (replicated), retire the winner ----
+    if (threadIdx.x == 0) {
+      IgKey b = partial[0];
+      for (int q = 1; q < (int)gridDim.x; ++q) if (ig_better(partial[q], b)) b = partial[q];
+      int choice;
+      if (remaining_weight < c.minfasta) choice = -1;                                    // :123
+      else if (remaining_count == 1) choice = -2;                                        // :124-126
+      else if (b.bin < 0) choice = -1;                                                   // :133-134
+      else choice = b.bin;
+      s_best = choice;
+    }
+    __syncthreads();
+    const int choice = s_best;
+    if (choice == -1) { done = true; break; }
+    const int cur_label = n_extracted;
+    n_extracted += 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (choice == -2) {                                      // the single remaining contig becomes a bin of its own
+      for (long long i = t0; i < c.N; i += stride)
+        if (alive[i]) { alive[i] = 0; out_labels[i] = cur_label; }
+      done = true;
+      break;
+    }
+    remaining_weight -= bins[choice].weight;                 // bins[] is not written before the next barrier
+    remaining_count -= bins[choice].count;
+    {
+      const int r = ig_result_of(c, choice);
+      const int32_t* mem = order + (long long)r * c.N;
+      const int lo = bstart[choice], hi = bend[choice];
+      for (long long p = lo + t0; p < hi; p += stride) {
+        const int i = mem[p];
+        if (!alive[i]) continue;
+        alive[i] = 0;
+        out_labels[i] = cur_label;
+        for (int q = 0; q < c.R; ++q) {
+          const long long l = labels[(long long)q * c.N + i];
+          if (l < 0) continue;
+          const long long g = c.base[q] + l;
+          if (dirty[g] == 0u && atomicExch(&dirty[g], 1u) == 0u) dirty_list[atomicAdd(&status->n_dirty, 1)] = (int32_t)g;
+        }
+      }
+    }
+    grid.sync();
+    // ---- 3. re-reduce the touched bins ----
+    ig_stats_body(c, order, bstart, bend, alive, lengths, masks, dirty_list, (long long)status->n_dirty, bins, dirty);
+    grid.sync();
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { status->n_extracted = n_extracted; status->done = done ? 1 : 0; }
 }
 
 
@@ -272,7 +301,7 @@ static void ig_carve(Arena& a, long long n, int R, IgWs& w) {
   w.dirty = a.take<unsigned int>(max_bins); w.dirty_list = a.take<int32_t>(max_bins);
   w.elig = a.take<int32_t>(max_bins); w.n_elig = a.take<int>(4);
   w.alive = a.take<unsigned char>((size_t)n);
-  w.partial = a.take<IgKey>(IG_SEL_BLOCKS);
+  w.partial = a.take<IgKey>(IG_SEL_BLOCKS * 4);
   w.status = a.take<IgStatus>(2);
   w.cub_bytes = ig_cub_bytes(n);
   w.cub_tmp = a.take<char>(w.cub_bytes);
@@ -347,26 +376,28 @@ extern "C" int sbk_integrate(const long long* labels, int32_t n_results, int64_t
   SBK_CUDA_CHECK(cudaMemcpyAsync(w.status, &st, sizeof(st), cudaMemcpyHostToDevice, stream));
   if (n_bins > 0) {
     const unsigned sg = (unsigned)std::min<long long>(n_bins, 148 * 64);
-    ig_stats_kernel<<<sg, 128, 0, stream>>>(c, w.order, w.bstart, w.bend, w.alive, lengths, marker_masks, nullptr, w.status,
-                                            n_bins, w.bins, w.dirty);
+    ig_stats_kernel<<<sg, 256, 0, stream>>>(c, w.order, w.bstart, w.bend, w.alive, lengths, marker_masks, n_bins, w.bins, w.dirty);
     SBK_LAUNCH_CHECK();
     ig_eligible_kernel<<<(unsigned)((n_bins + 255) / 256), 256, 0, stream>>>(w.bins, n_bins, minfasta, w.elig, w.n_elig);
     SBK_LAUNCH_CHECK();
   }
-  // ---- extraction loop: a batch of iterations per host round trip (kernels are no-ops once `done` is set) ----
-  const int BATCH = 16;
-  for (long long guard = 0; guard <= n / BATCH + 2; ++guard) {
-    for (int b = 0; b < BATCH; ++b) {
-      ig_select_kernel<<<IG_SEL_BLOCKS, 256, 0, stream>>>(c, w.bins, w.elig, w.n_elig, w.partial, w.status);
-      ig_remove_kernel<<<128, 256, 0, stream>>>(c, labels, w.order, w.bstart, w.bend, w.alive, out_labels, w.dirty, w.dirty_list, w.status);
-      ig_stats_kernel<<<256, 128, 0, stream>>>(c, w.order, w.bstart, w.bend, w.alive, lengths, marker_masks, w.dirty_list, w.status,
-                                               n_bins, w.bins, w.dirty);
-    }
-    SBK_LAUNCH_CHECK();
-    SBK_CUDA_CHECK(cudaMemcpyAsync(&st, w.status, sizeof(st), cudaMemcpyDeviceToHost, stream));
-    SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
-    if (st.done) break;
+  // ---- extraction loop: one persistent cooperative kernel, one CTA per SM ----
+  {
+    int dev = 0, sms = 0, occ = 0;
+    SBK_CUDA_CHECK(cudaGetDevice(&dev));
+    SBK_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SBK_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ig_loop_kernel, 256, 0));
+    if (occ < 1) { set_error("integrate: the loop kernel does not fit on an SM"); return SBK_ERR_INTERNAL; }
+    const int grid = std::min(sms, IG_SEL_BLOCKS * 4);
+    long long max_iter = n + 2;
+    const long long* labels_p = labels; const long long* lengths_p = lengths; const unsigned long long* masks_p = marker_masks;
+    void* args[] = {(void*)&c, (void*)&labels_p, (void*)&w.order, (void*)&w.bstart, (void*)&w.bend, (void*)&w.alive,
+                    (void*)&lengths_p, (void*)&masks_p, (void*)&w.bins, (void*)&w.dirty, (void*)&w.dirty_list, (void*)&w.elig,
+                    (void*)&w.n_elig, (void*)&w.partial, (void*)&w.status, (void*)&out_labels, (void*)&max_iter};
+    SBK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)ig_loop_kernel, dim3(grid), dim3(256), args, 0, stream));
   }
+  SBK_CUDA_CHECK(cudaMemcpyAsync(&st, w.status, sizeof(st), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (!st.done) { set_error("integrate: extraction loop did not terminate"); return SBK_ERR_INTERNAL; }
   if (n_extracted) *n_extracted = st.n_extracted;
   return SBK_OK;

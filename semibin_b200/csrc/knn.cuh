@@ -25,7 +25,7 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
 int rerank_warp_cap(int k);
 bool rerank_warp_supported(int dtype, int d, int k);
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                       const uint2* cand, const int32_t* cand_count, int cand_cap, const double* bound,
+                       const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                        int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream);

@@ -611,19 +611,103 @@ template <> struct RwSort<4, 256> { static __device__ __forceinline__ void run(u
 template <> struct RwSort<8, 512> { static __device__ __forceinline__ void run(unsigned long long (&)[8], uint32_t (&)[8], int) {} };
 template <> struct RwSort<16, 1024> { static __device__ __forceinline__ void run(unsigned long long (&)[16], uint32_t (&)[16], int) {} };
 
-static constexpr int RW_KEYS = 24;                    // candidate lower bounds per lane held in registers
-// FP64 squared distances of the rows id_s[lo..hi) -> key_s[lo..hi); returns the lane's running maximum
-template <typename T>
-__device__ __forceinline__ double rw_distances(const T* __restrict__ X, long long ld, const RegQuery<T>& rq,
-                                               const uint32_t* id_s, double* key_s, int lo, int hi, int sub, int g, double mx) {
-  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC;
-#pragma unroll 2
-  for (int e0 = lo; e0 < hi; e0 += CPI) {               // warp-uniform trip count (shuffles inside eval)
-    const int e = e0 + g;
-    const bool real = e < hi;
-    const uint32_t jj = real ? id_s[e] : 0u;
-    const double v = rq.eval(X + (long long)jj * ld, sub);
-    if (real) { mx = fmax(mx, v); if (sub == 0) key_s[e] = v; }
+// Lean FP64 row distance for the warp kernel: a group of LPC lanes evaluates one candidate row, lane `sub` owns the
+// 16-byte chunks sub, sub + LPC, ... of every row; its slice of the query lives in registers as double.  Compile-time
+// VEC (16-byte loads: rows 16-byte aligned) and precomputed per-chunk activity bits keep the inner loop free of
+// branches and address arithmetic: one predicated LDG.128 per chunk from a per-lane base pointer.  Two rows per
+// call so that both rows' loads are in flight before either is consumed.  Fixed xor-shuffle tree: deterministic,
+// and bit-identical to RegQuery::eval / sqdist_g8 (same per-lane partial sums, same combination order).
+template <typename T, bool VEC>
+struct WarpDist {
+  using C = DistCfg<T>;
+  static constexpr int NV = C::NCH * C::V;
+  double q[NV];
+  double qt;
+  int d, nfull, sub;
+  unsigned act;                                        // bit j: chunk sub + LPC * j exists
+  bool tail;                                           // this lane owns a tail column (d not a multiple of V)
+
+  __device__ __forceinline__ void load(const T* __restrict__ x, int d_, int sub_) {
+    d = d_; nfull = d_ / C::V; sub = sub_; act = 0u;
+#pragma unroll
+    for (int j = 0; j < C::NCH; ++j) {
+      const int ch = sub_ + C::LPC * j;
+      if (ch < nfull) act |= 1u << j;
+#pragma unroll
+      for (int e = 0; e < C::V; ++e) q[j * C::V + e] = ch < nfull ? (double)x[ch * C::V + e] : 0.0;
+    }
+    const int ct = nfull * C::V + sub_;
+    tail = sub_ < C::V && ct < d_;
+    qt = tail ? (double)x[ct] : 0.0;
+  }
+
+  __device__ __forceinline__ void fetch(const T* __restrict__ y, T (&v)[NV], T& vt) const {
+#pragma unroll
+    for (int j = 0; j < C::NCH; ++j) {
+#pragma unroll
+      for (int e = 0; e < C::V; ++e) v[j * C::V + e] = (T)0;
+      if ((act >> j) & 1u) {
+        if (VEC) {
+          if (sizeof(T) == 4) {
+            const float4 f = __ldg(reinterpret_cast<const float4*>(y) + sub + C::LPC * j);
+            v[j * C::V] = (T)f.x; v[j * C::V + 1] = (T)f.y; v[j * C::V + 2] = (T)f.z; v[j * C::V + 3] = (T)f.w;
+          } else {
+            const double2 f = __ldg(reinterpret_cast<const double2*>(y) + sub + C::LPC * j);
+            v[j * C::V] = (T)f.x; v[j * C::V + 1] = (T)f.y;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < C::V; ++e) v[j * C::V + e] = __ldg(y + (sub + C::LPC * j) * C::V + e);
+        }
+      }
+    }
+    vt = (T)0;
+    if (tail) vt = __ldg(y + nfull * C::V + sub);
+  }
+
+  __device__ __forceinline__ double reduce(const T (&v)[NV], T vt) const {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (sizeof(T) == 4) {
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {               // inactive chunks hold zeros on both sides
+        const double t0 = q[4 * j] - (double)v[4 * j], t1 = q[4 * j + 1] - (double)v[4 * j + 1];
+        const double t2 = q[4 * j + 2] - (double)v[4 * j + 2], t3 = q[4 * j + 3] - (double)v[4 * j + 3];
+        a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); a2 = fma(t2, t2, a2); a3 = fma(t3, t3, a3);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < C::NCH; ++j) {
+        const double t0 = q[2 * j] - (double)v[2 * j], t1 = q[2 * j + 1] - (double)v[2 * j + 1];
+        if (j & 1) { a2 = fma(t0, t0, a2); a3 = fma(t1, t1, a3); }
+        else { a0 = fma(t0, t0, a0); a1 = fma(t1, t1, a1); }
+      }
+    }
+    { const double t = qt - (double)vt; a0 = fma(t, t, a0); }      // zero on both sides where there is no tail
+    double s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = C::LPC / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  }
+};
+
+// FP64 squared distances of the rows id_s[lo..hi) -> key_s[lo..hi); returns the lane's running maximum.
+// Two candidate groups per turn: 2 * NCH loads in flight per lane.
+template <typename T, bool VEC>
+__device__ __forceinline__ double rw_distances(const T* __restrict__ X, long long ld, const WarpDist<T, VEC>& wd,
+                                               const uint32_t* id_s, double* key_s, int lo, int hi, int g, double mx) {
+  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC, NV = WarpDist<T, VEC>::NV;
+#pragma unroll 1
+  for (int e0 = lo; e0 < hi; e0 += 2 * CPI) {          // warp-uniform trip count (shuffles in reduce)
+    const int ea = e0 + g, eb = e0 + CPI + g;
+    const bool ra = ea < hi, rb = eb < hi;
+    const uint32_t ja = id_s[ra ? ea : lo], jb = id_s[rb ? eb : lo];      // an idle group re-reads a valid row
+    T va[NV], vb[NV]; T ta, tb;
+    wd.fetch(X + (long long)ja * ld, va, ta);
+    wd.fetch(X + (long long)jb * ld, vb, tb);
+    const double da = wd.reduce(va, ta);
+    const double db = wd.reduce(vb, tb);
+    if (ra) { mx = fmax(mx, da); if (wd.sub == 0) key_s[ea] = da; }
+    if (rb) { mx = fmax(mx, db); if (wd.sub == 0) key_s[eb] = db; }
   }
   return mx;
 }
@@ -633,22 +717,26 @@ __device__ __forceinline__ double rw_warp_max(double v) {
   return v;
 }
 
-template <typename T, int EPL, int MINB>
+static constexpr int RW_QCAP = 3072;                   // candidates per row the select phase holds (16-bit keys in shared memory)
+template <typename T, int EPL, int MINB, bool VEC>
 __global__ void __launch_bounds__(RW_WARPS * 32, MINB)
 rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_begin, long long n_rows,
                    const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
-                   const double* __restrict__ bound, const double* __restrict__ nrm, const float4* __restrict__ norms4,
-                   const double* __restrict__ scale, const int32_t* __restrict__ orig, int k,
+                   const float* __restrict__ thr, const double* __restrict__ bound, const double* __restrict__ nrm,
+                   const float4* __restrict__ norms4, const double* __restrict__ scale, const int32_t* __restrict__ orig, int k,
                    T* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
                    int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
                    int32_t* __restrict__ retry_slots, int* __restrict__ n_retry, int retry_cap,
                    unsigned long long* __restrict__ totals) {
   constexpr int NEL = 32 * EPL;
   constexpr int LPC = DistCfg<T>::LPC;
-  __shared__ double s_key[RW_WARPS][NEL];
-  __shared__ uint32_t s_id[RW_WARPS][NEL];
-  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-  const long long slot = (long long)blockIdx.x * RW_WARPS + wp;
+  extern __shared__ __align__(16) unsigned char rw_smem[];
+  double* key_s = reinterpret_cast<double*>(rw_smem) + (size_t)(threadIdx.x >> 5) * NEL;                   // [RW_WARPS][NEL]
+  uint32_t* id_s = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + (size_t)(threadIdx.x >> 5) * NEL;
+  uint16_t* q_s = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + RW_WARPS * NEL)
+                  + (size_t)(threadIdx.x >> 5) * RW_QCAP;                                                  // [RW_WARPS][RW_QCAP]
+  const int lane = threadIdx.x & 31;
+  const long long slot = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   if (slot >= n_rows) return;
   const long long row = q_begin + slot;
   const int k1 = k + 1;
@@ -664,7 +752,7 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   const int adj1 = seg_cap - p1, adj2 = 2 * seg_cap - p2, adj3 = 3 * seg_cap - p3;
   auto elem = [&](int e) { return e + (e >= p3 ? adj3 : e >= p2 ? adj2 : e >= p1 ? adj1 : 0); };
   // exits: overflow / too few candidates -> exact fallback; too many for this kernel -> block-per-row rerank
-  auto hand_back = [&](int why) {                        // why: 2 overflow, 3 too few, 4 too many survivors, -1 retry
+  auto hand_back = [&](int why) {                        // why: 2 overflow, 3 too few, -1 retry
     if (lane == 0) {
       bool to_fail = why >= 0;
       if (why < 0) {
@@ -676,62 +764,49 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
     }
   };
   if (bad || n < k1) { hand_back(bad ? 2 : 3); return; }
-  if (n > 32 * RW_KEYS) { hand_back(-1); return; }
+  if (n > RW_QCAP) { hand_back(-1); return; }
   const uint2* base = cand + slot * (long long)cand_cap;
-  uint32_t* id_s = s_id[wp];
-  double* key_s = s_key[wp];
-  // ---- select: 16-bit quantised lower bounds, (k+1)-th smallest bit by bit ----
-  float lo_f, sc_f; uint32_t res = 0;
-  int mA = 0;
+  // ---- select: lower bounds quantised to 16 bits between the row's own score and its final threshold ----
+  // Every candidate of the later launches has L <= thr (the thresholds only ever dropped), the k+1 smallest with
+  // the planned confidence; candidates above it (admitted by an earlier, looser threshold) clamp to the top level.
+  // The self score  -||z_i||^2  is the smallest possible lower bound up to the slack.
+  float lo_f, sc_f;
   {
-    float lv[RW_KEYS];
-    uint32_t omin = 0xffffffffu, omax = 0u;
-#pragma unroll
-    for (int u = 0; u < RW_KEYS; ++u) {
-      const int e = lane + 32 * u;
-      lv[u] = 0.f;
-      if (e < n) {
-        lv[u] = __uint_as_float(base[elem(e)].y);
-        const uint32_t o = f2ord(lv[u]);
-        omin = min(omin, o); omax = max(omax, o);
-      }
-    }
-    omin = __reduce_min_sync(0xffffffffu, omin); omax = __reduce_max_sync(0xffffffffu, omax);
-    lo_f = ord2f(omin);
-    const float range = ord2f(omax) - lo_f;
+    const float hi_f = thr[slot];
+    lo_f = (float)(-nrm[row]) - 0.125f * fabsf(hi_f + (float)nrm[row]) - 1.0f;
+    const float range = hi_f - lo_f;
     sc_f = range > 0.f ? 65535.0f / range : 0.f;
-    uint32_t q[RW_KEYS];
-#pragma unroll
-    for (int u = 0; u < RW_KEYS; ++u)
-      q[u] = (lane + 32 * u < n) ? min(65535u, __float2uint_rz((lv[u] - lo_f) * sc_f)) : 0x10000u;
-    for (int bit = 15; bit >= 0; --bit) {               // res = the (k+1)-th smallest quantised value
-      const uint32_t t = res | (1u << bit);
-      int cnt = 0;
-#pragma unroll
-      for (int u = 0; u < RW_KEYS; ++u) cnt += q[u] < t ? 1 : 0;
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < k1) res = t;
-    }
-    // A = {q <= res}: at least k+1 members; positions -> rows, compacted into shared memory
-#pragma unroll
-    for (int u = 0; u < RW_KEYS; ++u) {
-      if (32 * u < n) {                                  // warp-uniform
-        const bool inA = q[u] <= res;
-        const uint32_t bal = __ballot_sync(0xffffffffu, inA);
-        const int at = mA + __popc(bal & ((1u << lane) - 1u));
-        if (inA && at < NEL) id_s[at] = (uint32_t)orig[base[elem(lane + 32 * u)].x];
-        mA += __popc(bal);
-      }
-    }
+  }
+  for (int e = lane; e < n; e += 32) {
+    const float l = __uint_as_float(base[elem(e)].y);
+    q_s[e] = (uint16_t)min(65535u, __float2uint_rz(fmaxf(l - lo_f, 0.f) * sc_f));
+  }
+  __syncwarp();
+  uint32_t res = 0;                                      // the (k+1)-th smallest quantised value, bit by bit
+  for (int bit = 15; bit >= 0; --bit) {
+    const uint32_t t = res | (1u << bit);
+    int cnt = 0;
+    for (int e = lane; e < n; e += 32) cnt += (uint32_t)q_s[e] < t ? 1 : 0;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (cnt < k1) res = t;
+  }
+  // A = {q <= res}: at least k+1 members; positions -> rows, compacted into shared memory
+  int mA = 0;
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    const bool inA = e < n && (uint32_t)q_s[e] <= res;
+    const uint32_t bal = __ballot_sync(0xffffffffu, inA);
+    const int at = mA + __popc(bal & ((1u << lane) - 1u));
+    if (inA && at < NEL) id_s[at] = (uint32_t)orig[base[elem(e)].x];
+    mA += __popc(bal);
   }
   if (mA > NEL) { hand_back(-1); return; }
   __syncwarp();
   const int sub = lane & (LPC - 1), g = lane / LPC;
-  const bool vec_ok = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)sizeof(T)) & 15) == 0);
-  RegQuery<T> rq;
-  rq.load(X + row * ld, d, sub, vec_ok);
+  WarpDist<T, VEC> wd;
+  wd.load(X + row * ld, d, sub);
   // ---- phase 1 ----
-  const double dmax = rw_warp_max(rw_distances<T>(X, ld, rq, id_s, key_s, 0, mA, sub, g, 0.0));
+  const double dmax = rw_warp_max(rw_distances<T, VEC>(X, ld, wd, id_s, key_s, 0, mA, g, 0.0));
   // ---- phase 2: candidates outside A whose lower bound does not exclude d2 <= dmax ----
   int m = mA;
   {
@@ -741,11 +816,9 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
     for (int e0 = 0; e0 < n; e0 += 32) {
       const int e = e0 + lane;
       bool take = false; uint32_t pos = 0;
-      if (e < n) {
+      if (e < n && (uint32_t)q_s[e] > res) {
         const uint2 pr = base[elem(e)];
-        const float l = __uint_as_float(pr.y);
-        const uint32_t qq = min(65535u, __float2uint_rz((l - lo_f) * sc_f));
-        take = qq > res && (double)l <= cut; pos = pr.x;
+        take = (double)__uint_as_float(pr.y) <= cut; pos = pr.x;
       }
       const uint32_t bal = __ballot_sync(0xffffffffu, take);
       const int at = m + __popc(bal & ((1u << lane) - 1u));
@@ -755,7 +828,7 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   }
   if (m > NEL) { hand_back(-1); return; }
   __syncwarp();
-  if (m > mA) rw_distances<T>(X, ld, rq, id_s, key_s, mA, m, sub, g, 0.0);
+  if (m > mA) rw_distances<T, VEC>(X, ld, wd, id_s, key_s, mA, m, g, 0.0);
   if (lane == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
   __syncwarp();
   // ---- (d2 pattern, row) pairs into registers; the initial placement is irrelevant to a sort ----
@@ -816,8 +889,21 @@ int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with
   return 0;
 }
 
+template <typename T, int EPL, int MINB, bool VEC>
+static int rw_launch(unsigned grid, cudaStream_t stream, const T* X, int d, long long ld, long long q_begin, long long n_rows,
+                     const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
+                     const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
+                     T* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
+                     int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals) {
+  const size_t smem = (size_t)RW_WARPS * (32 * EPL * 12 + RW_QCAP * 2);
+  SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_warp_kernel<T, EPL, MINB, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rerank_warp_kernel<T, EPL, MINB, VEC><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr,
+      bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);
+  return SBK_OK;
+}
+
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                       const uint2* cand, const int32_t* cand_count, int cand_cap, const double* bound,
+                       const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                        int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream) {
@@ -825,14 +911,17 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
   const int cap = rerank_warp_cap(k);
   if (cap == 0) { set_error("rerank: k=%d not supported by the warp kernel", k); return SBK_ERR_INVALID; }
   const unsigned grid = (unsigned)((n_rows + RW_WARPS - 1) / RW_WARPS);
-  // 3 CTAs (24 warps) per SM at 80 registers; the probe build can drop to 2 CTAs at up to 128 registers
-  static const int occ = rw_env_int("SBK_RW_OCC", 3);
-#define SBK_RW_ARGS(T) (const T*)X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, bound, nrm, norms4, scale, orig, k, \
+  const size_t esz = dtype == SBK_F32 ? 4 : 8;
+  const bool vec = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)esz) & 15) == 0);
+  // 2 CTAs (16 warps) per SM at up to 128 registers by default; the probe build can ask for 3 CTAs at 80 registers
+  static const int occ = rw_env_int("SBK_RW_OCC", 2);
+  int rc = SBK_OK;
+#define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
       (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals
 #define SBK_RW_LAUNCH(T, EPL)                                                                                           \
   do {                                                                                                                  \
-    if (occ == 2) rerank_warp_kernel<T, EPL, 2><<<grid, RW_WARPS * 32, 0, stream>>>(SBK_RW_ARGS(T));                   \
-    else rerank_warp_kernel<T, EPL, 3><<<grid, RW_WARPS * 32, 0, stream>>>(SBK_RW_ARGS(T));                            \
+    if (occ == 3) rc = vec ? rw_launch<T, EPL, 3, true>(SBK_RW_ARGS(T)) : rw_launch<T, EPL, 3, false>(SBK_RW_ARGS(T)); \
+    else rc = vec ? rw_launch<T, EPL, 2, true>(SBK_RW_ARGS(T)) : rw_launch<T, EPL, 2, false>(SBK_RW_ARGS(T));          \
   } while (0)
 #define SBK_RW_DISPATCH(T)                                                                                              \
   do {                                                                                                                  \
@@ -843,6 +932,7 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
 #undef SBK_RW_DISPATCH
 #undef SBK_RW_LAUNCH
 #undef SBK_RW_ARGS
+  if (rc) return rc;
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
