@@ -214,12 +214,27 @@ def run_ours(args):
 
     full_d = torch.empty((n, k), dtype=torch.float32, device='cuda') if (world > 1 and n % world == 0) else None
     full_i = torch.empty((n, k), dtype=torch.int32, device='cuda') if (world > 1 and n % world == 0) else None
+    # N > 1: the rerank kernels store every finished row into every rank's full result buffer (P2P over NVLink,
+    # symmetric memory), the gather rides on the compute kernel; --gather nccl (or a box without peer mapping)
+    # falls back to two all-gathers after the kernels
+    peer_bufs, gather_mode = None, 'none'
+    if world > 1:
+        gather_mode = 'nccl all_gather_into_tensor x2'
+        if args.gather == 'p2p':
+            try:
+                peer_bufs = sdist.PeerResult(n, k, torch.float32, X.device)
+                gather_mode = 'p2p stores from the rerank kernels into symmetric-memory result buffers + barrier'
+            except Exception as e:      # noqa: BLE001  (reported in the JSON line)
+                gather_mode = f'nccl all_gather_into_tensor x2 (symmetric memory unavailable: {type(e).__name__}: {e})'[:300]
 
     def step(collect=None):
-        d, i, st = knn(X, k, q_begin=lo, q_end=hi, algo=args.algo, return_stats=True, out=(dev_d, dev_i))
-        if world > 1:
-            d = sdist.all_gather_rows(d, n, out=full_d)
-            i = sdist.all_gather_rows(i, n, out=full_i)
+        if peer_bufs is not None:
+            d, i, st = sdist.knn_sharded_p2p(X, k, peer_bufs, algo=args.algo, return_stats=True)
+        else:
+            d, i, st = knn(X, k, q_begin=lo, q_end=hi, algo=args.algo, return_stats=True, out=(dev_d, dev_i))
+            if world > 1:
+                d = sdist.all_gather_rows(d, n, out=full_d)
+                i = sdist.all_gather_rows(i, n, out=full_i)
         if collect is not None:
             collect.append(st)
         return d, i
@@ -268,7 +283,8 @@ def run_ours(args):
         g = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)))     # warm-up (pins the result arrays once)
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            g = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)))
+            g = None        # the caller drops the previous graph: its pinned arrays go back to torch's host allocator
+            g, g_stats = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)), return_stats=True)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     barrier()
     # second figure: the SPMD host-buffer call (one process per GPU, each rank its own row block)
@@ -307,7 +323,7 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f16 tensor-core filter + f64 rerank (exact result)', 'data': 'synthetic',
             'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
-                       'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo, 'parallelism': f'row-block x{world}, references replicated',
+                       'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo, 'parallelism': f'row-block x{world}, references replicated', 'gather': gather_mode,
                        'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
             'clocks': sampler.summary(),
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
@@ -319,6 +335,8 @@ def run_ours(args):
                            '(the call at SemiBin/cluster.py:94-99), one process driving all N GPUs (devices=N / SBK_DEVICES): pageable '
                            'numpy matrix in, device-widened (float64, int64) row chunks downloaded into the pinned arrays of the '
                            'csr_matrix while the next chunk is computed',
+                    'host_split_ms': {'alloc_result': g_stats['host_ms']['alloc_result'], 'build': g_stats['host_ms']['build'],
+                                      'upload': g_stats.get('upload_ms')} if rank == 0 else None,
                     'spmd_host_buffers': {'value': n / (spmd_ms * 1e-3), 'ms_per_step': spmd_ms,
                                           'api': 'semibin_b200.neighbors.knn_host under torchrun (one process per GPU, (dist f32, idx i32) row '
                                                  'blocks into pinned host memory)', 'd2h_bytes_per_step': int(n * k * 8)}},
@@ -372,6 +390,7 @@ def main():
     ap.add_argument('--neighbors', dest='k', type=int, default=K_DEFAULT)
     ap.add_argument('--algo', default='auto')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl'])
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)

@@ -120,6 +120,20 @@ int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
 /* sbk_knn synchronises `cuda_stream` before it returns (it reads back the
  * certificate-failure count to size the fallback launch). */
 
+/* sbk_knn for the row-block sharded multi-GPU build (north_star item 4): besides out_dist / out_idx (this GPU's row
+ * block, rows [q_begin, q_end)), every finished row r is ALSO stored at row r of the n_peers FULL [n_ref, k] result
+ * buffers peer_dist[t] / peer_idx[t] -- device memory of the other GPUs of the box mapped into this process (CUDA
+ * IPC / symmetric memory / peer access).  The stores are plain P2P stores issued by the rerank kernels themselves, so
+ * the gather of the row blocks rides on the compute kernel over NVLink instead of following it as a collective; the
+ * caller only has to order a barrier after the call before it reads its own full buffer.  peer_dist / peer_idx are
+ * HOST arrays of device pointers; n_peers <= 8; 0 peers == sbk_knn. */
+int sbk_knn_peers(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                  int64_t q_begin, int64_t q_end, int32_t k,
+                  void* out_dist, int32_t* out_idx,
+                  int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
+                  void* workspace, size_t ws_bytes, int algo,
+                  sbk_knn_stats* stats, void* cuda_stream);
+
 /* sbk_knn with the result also delivered to HOST memory (the buffers kneighbors_graph hands to scipy,
  * cluster.py:94-105): the query rows are processed in chunks of `chunk_rows` (0 = the default chunking) and
  * every finished chunk is copied to host_dist / host_idx (pinned memory for an asynchronous copy) on

@@ -226,7 +226,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
                     int64_t q_begin, int64_t q_end, int32_t k,
                     void* out_dist, int32_t* out_idx,
                     void* workspace, size_t ws_bytes, int algo,
-                    sbk_knn_stats* stats, cudaStream_t stream, const HostSink* sink) {
+                    sbk_knn_stats* stats, cudaStream_t stream, const HostSink* sink, const PeerOut* peers = nullptr) {
   int rc = knn_check(dtype, n_ref, d, q_begin, q_end, k);
   if (rc) return rc;
   if (ld < d) { set_error("knn: ld=%lld < d=%d", (long long)ld, d); return SBK_ERR_INVALID; }
@@ -276,7 +276,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       if (rc) { drop_events(); return rc; }
       h = tm.begin(&st.ms_rerank);
       rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, w.cand_idx, nullptr, s.cand_stride, 1, w.cand_count,
-                         nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                         nullptr, nullptr, nullptr, nullptr, nullptr, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream, nullptr, nullptr, 0, peers);
       tm.end(h);
       st.n_launches += 2;
       if (rc) { drop_events(); return rc; }
@@ -303,14 +303,15 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
         SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
         rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
                                 tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap,
-                                w.cand_total, stream);
+                                w.cand_total, stream, peers);
         if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                                     w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total + 8, stream,
-                                    w.retry, w.n_fail + 2, (int)s.retry_cap);
+                                    w.retry, w.n_fail + 2, (int)s.retry_cap, peers);
         st.n_launches += 3;
       } else {
         rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
-                           w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream);
+                           w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream,
+                           nullptr, nullptr, 0, peers);
         st.n_launches += 3;
       }
       tm.end(h);
@@ -349,7 +350,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       // n_fail[1] counts rows the fallback itself could not resolve (none are expected)
       rc = launch_rerank(X, dtype, n_ref, d, ld, w.fail_rows + f0, 0, fn, w.fb_idx, nullptr, (long long)s.fb_split * k1, 1,
                          w.fb_count, nullptr, nullptr, nullptr, nullptr, nullptr, k, out_dist, out_idx, q_begin,
-                         w.fail_rows + n_q, w.n_fail + 1, nullptr, stream);
+                         w.fail_rows + n_q, w.n_fail + 1, nullptr, stream, nullptr, nullptr, 0, peers);
       if (rc) { drop_events(); return rc; }
     }
     tm.end(hfb);
@@ -396,6 +397,22 @@ extern "C" int sbk_knn(const void* X, int dtype, int64_t n_ref, int32_t d, int64
                        sbk_knn_stats* stats, void* cuda_stream) {
   return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
                   (cudaStream_t)cuda_stream, nullptr);
+}
+
+extern "C" int sbk_knn_peers(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
+                             int64_t q_begin, int64_t q_end, int32_t k,
+                             void* out_dist, int32_t* out_idx,
+                             int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
+                             void* workspace, size_t ws_bytes, int algo,
+                             sbk_knn_stats* stats, void* cuda_stream) {
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!peer_dist || !peer_idx))) { set_error("knn_peers: 0..8 peer buffers"); return SBK_ERR_INVALID; }
+  PeerOut po; po.n = n_peers;
+  for (int t = 0; t < n_peers; ++t) {
+    if (!peer_dist[t] || !peer_idx[t]) { set_error("knn_peers: null peer buffer %d", t); return SBK_ERR_INVALID; }
+    po.dist[t] = peer_dist[t]; po.idx[t] = peer_idx[t];
+  }
+  return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
+                  (cudaStream_t)cuda_stream, nullptr, &po);
 }
 
 extern "C" int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,

@@ -4,6 +4,12 @@
 
 namespace sbk {
 
+// Mirror destinations of the rerank output: the full [n_ref, k] result buffers of the other GPUs of the box (peer
+// memory mapped into this process).  The rerank kernels store every finished row to all of them with plain P2P
+// stores over NVLink, so the row-block gather of the multi-GPU build rides on the compute kernel instead of
+// following it as a collective.
+struct PeerOut { int n; void* dist[8]; int32_t* idx[8]; };
+
 // ---- exact (FP64 CUDA-core) filter + rerank: knn_exact.cu ----
 int exact_filter_cap(int k1);
 size_t exact_filter_smem(int d, int k1);
@@ -18,7 +24,8 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   const double* scale, const int32_t* orig, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
-                  cudaStream_t stream, const int32_t* slot_list = nullptr, const int* n_list = nullptr, int list_cap = 0);
+                  cudaStream_t stream, const int32_t* slot_list = nullptr, const int* n_list = nullptr, int list_cap = 0,
+                  const PeerOut* peers = nullptr);
 // warp-per-row rerank straight from the filter's candidate lists (tensor path); rows it cannot take (too many
 // candidates for its registers / survivors for its sort) are appended to retry_slots / n_retry for launch_rerank's
 // retry mode, uncertified rows to fail_rows
@@ -28,7 +35,8 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
-                       int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream);
+                       int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream,
+                       const PeerOut* peers = nullptr);
 
 // ---- tensor-core (tcgen05) filter: knn_tc.cu ----
 struct TcPlan {

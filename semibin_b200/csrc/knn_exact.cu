@@ -253,7 +253,7 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
               OutT* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
               int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
               unsigned long long* __restrict__ totals,
-              const int32_t* __restrict__ slot_list, const int* __restrict__ n_list, int list_cap) {
+              const int32_t* __restrict__ slot_list, const int* __restrict__ n_list, int list_cap, const PeerOut peers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* q = reinterpret_cast<double*>(smem_raw);           // [d]
   double* key = q + ((d + 1) & ~1);                          // [pmax]  survivors: exact d2
@@ -529,14 +529,20 @@ rerank_kernel(const T* __restrict__ X, long long n_ref, int d, long long ld,
     if (t == drop) continue;
     int p = t - (t > drop ? 1 : 0);
     double d2 = key[t];
+    OutT dv;
     if (sizeof(OutT) == 4) {
       // f64(f32(sqrt(f64(f32(d2)))))   sklearn _argkmin.pyx.tp:285-295
       float r = (float)d2;
-      out_dist[o + p] = (OutT)(float)sqrt((double)r);
+      dv = (OutT)(float)sqrt((double)r);
     } else {
-      out_dist[o + p] = (OutT)sqrt(d2);
+      dv = (OutT)sqrt(d2);
     }
+    out_dist[o + p] = dv;
     out_idx[o + p] = (int32_t)id[t];
+    for (int u = 0; u < peers.n; ++u) {          // the same row into the other GPUs' full result buffers (P2P stores)
+      reinterpret_cast<OutT*>(peers.dist[u])[row * (long long)k + p] = dv;
+      peers.idx[u][row * (long long)k + p] = (int32_t)id[t];
+    }
   }
 }
 
@@ -727,7 +733,7 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
                    T* __restrict__ out_dist, int32_t* __restrict__ out_idx, long long out_row0,
                    int32_t* __restrict__ fail_rows, int* __restrict__ n_fail,
                    int32_t* __restrict__ retry_slots, int* __restrict__ n_retry, int retry_cap,
-                   unsigned long long* __restrict__ totals) {
+                   unsigned long long* __restrict__ totals, const PeerOut peers) {
   constexpr int NEL = 32 * EPL;
   constexpr int LPC = DistCfg<T>::LPC;
   extern __shared__ __align__(16) unsigned char rw_smem[];
@@ -735,6 +741,8 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   uint32_t* id_s = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + (size_t)(threadIdx.x >> 5) * NEL;
   uint16_t* q_s = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + RW_WARPS * NEL)
                   + (size_t)(threadIdx.x >> 5) * RW_QCAP;                                                  // [RW_WARPS][RW_QCAP]
+  uint32_t* st_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL)
+                   + RW_WARPS * NEL) + (size_t)RW_WARPS * RW_QCAP) + (size_t)(threadIdx.x >> 5) * 64;        // [RW_WARPS][64] phase-2 ring
   const int lane = threadIdx.x & 31;
   const long long slot = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
   if (slot >= n_rows) return;
@@ -808,28 +816,55 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   // ---- phase 1 ----
   const double dmax = rw_warp_max(rw_distances<T, VEC>(X, ld, wd, id_s, key_s, 0, mA, g, 0.0));
   // ---- phase 2: candidates outside A whose lower bound does not exclude d2 <= dmax ----
+  // Streamed: passing candidates are staged (64-entry ring per warp), evaluated eight at a time and only those with
+  // d2 <= dmax are kept (A alone holds k+1 rows within dmax, so nothing farther can be among the k+1 nearest):
+  // dense neighbourhoods put hundreds of candidates inside the slack band, the sort still sees ~k+1 entries.
   int m = mA;
+  long long n_eval = mA;
   {
+    constexpr int CPI = 32 / LPC;
     const double S = scale[0];
     // L_ij <= S^2 d2_ij - nrm_i + sigma_i; the inflation covers the rounding of dmax and of this expression
     const double cut = S * S * dmax * (1.0 + 1e-12) - nrm[row] * (1.0 - 1e-12) + (double)norms4[row].w + 1e-300;
-    for (int e0 = 0; e0 < n; e0 += 32) {
-      const int e = e0 + lane;
-      bool take = false; uint32_t pos = 0;
-      if (e < n && (uint32_t)q_s[e] > res) {
-        const uint2 pr = base[elem(e)];
-        take = (double)__uint_as_float(pr.y) <= cut; pos = pr.x;
+    int head = 0, ns = 0;                               // ring state, warp-uniform
+    for (int e0 = 0; e0 < n || ns > 0; e0 += 32) {
+      if (e0 < n) {
+        const int e = e0 + lane;
+        bool take = false; uint32_t pos = 0;
+        if (e < n && (uint32_t)q_s[e] > res) {
+          const uint2 pr = base[elem(e)];
+          take = (double)__uint_as_float(pr.y) <= cut; pos = pr.x;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, take);
+        if (take) st_s[(head + ns + __popc(bal & ((1u << lane) - 1u))) & 63] = (uint32_t)orig[pos];
+        ns += __popc(bal);
+        __syncwarp();
       }
-      const uint32_t bal = __ballot_sync(0xffffffffu, take);
-      const int at = m + __popc(bal & ((1u << lane) - 1u));
-      if (take && at < NEL) id_s[at] = (uint32_t)orig[pos];
-      m += __popc(bal);
+      // evaluate full batches of 2 * CPI; at the end of the list also the last partial one
+      while (ns >= 2 * CPI || (e0 + 32 >= n && ns > 0)) {
+        const int nb = min(ns, 2 * CPI);
+        const bool ra = g < nb, rb = CPI + g < nb;
+        const uint32_t ja = st_s[(head + (ra ? g : 0)) & 63], jb = st_s[(head + (rb ? CPI + g : 0)) & 63];
+        T va[WarpDist<T, VEC>::NV], vb[WarpDist<T, VEC>::NV]; T ta, tb;
+        wd.fetch(X + (long long)ja * ld, va, ta);
+        wd.fetch(X + (long long)jb * ld, vb, tb);
+        const double da = wd.reduce(va, ta);
+        const double db = wd.reduce(vb, tb);
+        const bool ka = ra && sub == 0 && da <= dmax, kb = rb && sub == 0 && db <= dmax;
+        const uint32_t bala = __ballot_sync(0xffffffffu, ka), balb = __ballot_sync(0xffffffffu, kb);
+        const int ata = m + __popc(bala & ((1u << lane) - 1u));
+        const int atb = m + __popc(bala) + __popc(balb & ((1u << lane) - 1u));
+        if (ka && ata < NEL) { key_s[ata] = da; id_s[ata] = ja; }
+        if (kb && atb < NEL) { key_s[atb] = db; id_s[atb] = jb; }
+        m += __popc(bala) + __popc(balb);
+        n_eval += nb;
+        head = (head + nb) & 63; ns -= nb;
+        __syncwarp();
+      }
     }
   }
   if (m > NEL) { hand_back(-1); return; }
-  __syncwarp();
-  if (m > mA) rw_distances<T, VEC>(X, ld, wd, id_s, key_s, mA, m, g, 0.0);
-  if (lane == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)m); }
+  if (lane == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)n_eval); }
   __syncwarp();
   // ---- (d2 pattern, row) pairs into registers; the initial placement is irrelevant to a sort ----
   unsigned long long kt[EPL]; uint32_t it[EPL];
@@ -871,9 +906,16 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
     if (r == drop) continue;
     const int p = r - (r > drop ? 1 : 0);
     const double d2 = key_s[r];
-    if (sizeof(T) == 4) out_dist[o + p] = (T)(float)sqrt((double)(float)d2);   // f64(f32(sqrt(f64(f32(d2)))))  _argkmin.pyx.tp:285-295
-    else out_dist[o + p] = (T)sqrt(d2);
-    out_idx[o + p] = (int32_t)id_s[r];
+    T dv;
+    if (sizeof(T) == 4) dv = (T)(float)sqrt((double)(float)d2);   // f64(f32(sqrt(f64(f32(d2)))))  _argkmin.pyx.tp:285-295
+    else dv = (T)sqrt(d2);
+    const int32_t iv = (int32_t)id_s[r];
+    out_dist[o + p] = dv;
+    out_idx[o + p] = iv;
+    for (int u = 0; u < peers.n; ++u) {          // the same row into the other GPUs' full result buffers (P2P stores)
+      reinterpret_cast<T*>(peers.dist[u])[row * (long long)k + p] = dv;
+      peers.idx[u][row * (long long)k + p] = iv;
+    }
   }
 }
 
@@ -894,11 +936,11 @@ static int rw_launch(unsigned grid, cudaStream_t stream, const T* X, int d, long
                      const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                      const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                      T* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
-                     int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals) {
-  const size_t smem = (size_t)RW_WARPS * (32 * EPL * 12 + RW_QCAP * 2);
+                     int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, const PeerOut& peers) {
+  const size_t smem = (size_t)RW_WARPS * (32 * EPL * 12 + RW_QCAP * 2 + 64 * 4);
   SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_warp_kernel<T, EPL, MINB, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   rerank_warp_kernel<T, EPL, MINB, VEC><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr,
-      bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals);
+      bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, peers);
   return SBK_OK;
 }
 
@@ -906,8 +948,11 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
-                       int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream) {
+                       int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, cudaStream_t stream,
+                       const PeerOut* peers) {
   if (n_rows <= 0) return SBK_OK;
+  PeerOut po; po.n = 0;
+  if (peers) po = *peers;
   const int cap = rerank_warp_cap(k);
   if (cap == 0) { set_error("rerank: k=%d not supported by the warp kernel", k); return SBK_ERR_INVALID; }
   const unsigned grid = (unsigned)((n_rows + RW_WARPS - 1) / RW_WARPS);
@@ -917,7 +962,7 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
   static const int occ = rw_env_int("SBK_RW_OCC", 2);
   int rc = SBK_OK;
 #define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
-      (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals
+      (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, po
 #define SBK_RW_LAUNCH(T, EPL)                                                                                           \
   do {                                                                                                                  \
     if (occ == 3) rc = vec ? rw_launch<T, EPL, 3, true>(SBK_RW_ARGS(T)) : rw_launch<T, EPL, 3, false>(SBK_RW_ARGS(T)); \
@@ -951,7 +996,9 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
                   const double* scale, const int32_t* orig, int k,
                   void* out_dist, int32_t* out_idx, long long out_row0,
                   int32_t* fail_rows, int* n_fail, unsigned long long* totals,
-                  cudaStream_t stream, const int32_t* slot_list, const int* n_list, int list_cap) {
+                  cudaStream_t stream, const int32_t* slot_list, const int* n_list, int list_cap, const PeerOut* peers) {
+  PeerOut po; po.n = 0;
+  if (peers) po = *peers;
   if (cand_pair && !orig) { set_error("rerank: tensor-path candidates need the position -> row map"); return SBK_ERR_INVALID; }
   if (n_slots <= 0) return SBK_OK;
   // tensor path: all candidates staged (ncand_cap), survivors of the two-phase cut sorted in a
@@ -968,7 +1015,7 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
     SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_kernel<T, T, REGQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     rerank_kernel<T, T, REGQ><<<grid, RR_THREADS, smem, stream>>>(                                                      \
         (const T*)X, n_ref, d, ld, rows, q_begin, cand_idx, cand_pair, cand_stride, n_seg, cand_count, bound, nrm, norms4, scale, \
-        orig, k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals, slot_list, n_list, list_cap);                               \
+        orig, k, ncand_cap, pmax, (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, totals, slot_list, n_list, list_cap, po);                               \
   } while (0)
   if (dtype == SBK_F32) {
     if (d <= RegQuery<float>::MAX_D) SBK_RR_LAUNCH(float, true); else SBK_RR_LAUNCH(float, false);

@@ -72,6 +72,64 @@ def knn_sharded(X, n_neighbors, *, group=None, algo='auto', gather=True, local_k
     return all_gather_rows(d, n, group), all_gather_rows(i, n, group)
 
 
+class PeerResult:
+    """Full [n, k] (dist, idx) result buffers of every rank, each mapped into every process of the group (torch
+    symmetric memory: CUDA virtual-memory handles exchanged once at rendezvous).  `sbk_knn_peers` makes the rerank
+    kernels store every finished row into all of them with P2P stores over NVLink, so the row-block gather rides on
+    the compute kernel; the only thing left after the call is a barrier."""
+
+    def __init__(self, n, k, dtype, device, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = world_info(group)
+        self.n, self.k = n, k
+        self.dist = symm.empty((n, k), dtype=dtype, device=device)
+        self.idx = symm.empty((n, k), dtype=torch.int32, device=device)
+        hd = symm.rendezvous(self.dist, self.group)
+        hi = symm.rendezvous(self.idx, self.group)
+        self._handles = (hd, hi)
+        peers = [r for r in range(self.world) if r != self.rank]
+        self.n_peers = len(peers)
+        self.peer_dist = (C.c_void_p * max(1, len(peers)))(*[int(hd.buffer_ptrs[r]) for r in peers])
+        self.peer_idx = (C.c_void_p * max(1, len(peers)))(*[int(hi.buffer_ptrs[r]) for r in peers])
+
+
+def knn_sharded_p2p(X, n_neighbors, bufs, *, algo='auto', return_stats=False):
+    """Row-block sharded kNN graph with the gather fused into the rerank kernels: every rank computes its row block
+    [lo, hi) straight into rows [lo, hi) of its own full buffer AND of every peer's (bufs: PeerResult); after the
+    barrier every rank holds the full (dist, idx).  Returns (bufs.dist, bufs.idx)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .neighbors import _workspace
+    lib = _lib.load()
+    n, d = X.shape
+    k = int(n_neighbors)
+    lo, hi = row_block(n, bufs.rank, bufs.world)
+    dtype = _lib.SBK_F32 if X.dtype == torch.float32 else _lib.SBK_F64
+    a = _lib.ALGOS[algo] if isinstance(algo, str) else int(algo)
+    ws_bytes = lib.sbk_knn_workspace_bytes(dtype, n, d, hi - lo, k, a)
+    if ws_bytes == 0:
+        raise ValueError(_lib.last_error())
+    ws = _workspace(ws_bytes, X.device)
+    st = _lib.KnnStats()
+    out_d, out_i = bufs.dist[lo:hi], bufs.idx[lo:hi]
+    rc = lib.sbk_knn_peers(_lib.ptr(X), dtype, n, d, X.stride(0), lo, hi, k, _lib.ptr(out_d), _lib.ptr(out_i),
+                           bufs.n_peers, bufs.peer_dist, bufs.peer_idx, _lib.ptr(ws), ws.numel(), a, C.byref(st),
+                           _lib.stream_ptr(X.device))
+    _lib.check(rc)
+    # the call returns with this rank's stream drained (all its P2P stores issued and complete); once every rank
+    # has got here, every full buffer is complete
+    dist.barrier(group=bufs.group)
+    if return_stats:
+        return bufs.dist, bufs.idx, st.as_dict()
+    return bufs.dist, bufs.idx
+
+
 def allreduce_counts(counts, group=None):
     """Sum of the per-threshold row counts over ranks (cluster.py:122)."""
     dist = _dist()

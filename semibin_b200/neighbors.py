@@ -246,11 +246,14 @@ def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2
     if not (0 < k < N):
         raise ValueError(f'Expected n_neighbors < n_samples_fit, but n_neighbors = {k}, n_samples_fit = {N}, '
                          f'n_samples = {N}')
+    import time
+    t_start = time.perf_counter()
     devs = resolve_devices(devices, Xt)
     # pinned result arrays: the csr_matrix is built over them (torch caches freed pinned blocks, so only the first
     # graph of a size pays for page-locking)
     indices = torch.empty((N * k,), dtype=torch.int64, pin_memory=True)
     data = torch.empty((N * k,), dtype=torch.float64, pin_memory=True) if mode == 'distance' else None
+    t_alloc = time.perf_counter()
     stats = graph_rows_multi(Xt, k, devs, data, indices, algo=algo, n_blocks=n_blocks,
                              keep_device=keep_device and len(devs) == 1)
     data_np = data.numpy() if data is not None else np.ones(N * k, dtype=np.float64)
@@ -258,6 +261,8 @@ def kneighbors_graph(X, n_neighbors, *, mode='distance', metric='minkowski', p=2
     import weakref
     dev_pair = stats.pop('device_graph', None) if isinstance(stats, dict) else None
     _last_graph['ref'], _last_graph['dev'] = (weakref.ref(g), dev_pair) if dev_pair is not None else (None, None)
+    if isinstance(stats, dict):          # host wall-clock split of this call (ms)
+        stats['host_ms'] = dict(alloc_result=(t_alloc - t_start) * 1e3, build=(time.perf_counter() - t_alloc) * 1e3)
     return (g, stats) if return_stats else g
 
 
@@ -290,7 +295,12 @@ def _graph_rows_one(Xt, k, dev, lo, hi, data, indices, algo, n_blocks, keep_devi
         lib = _lib.load()
         with torch.cuda.device(dev):
             device = torch.device('cuda', dev)
+            import time
+            t0 = time.perf_counter()
             Xd = Xt.to(device, non_blocking=True) if not (Xt.is_cuda and Xt.device == device) else Xt
+            if not Xt.is_cuda:
+                torch.cuda.current_stream(device).synchronize()
+            t_up = (time.perf_counter() - t0) * 1e3
             N, D = Xd.shape
             n_q = hi - lo
             dtype = _lib.SBK_F32 if Xd.dtype == torch.float32 else _lib.SBK_F64
@@ -309,6 +319,7 @@ def _graph_rows_one(Xt, k, dev, lo, hi, data, indices, algo, n_blocks, keep_devi
                                    _lib.ptr(ws), ws.numel(), a, C.byref(st), _lib.stream_ptr(device), copy.cuda_stream)
             _lib.check(rc)
             res = st.as_dict()
+            res['upload_ms'] = t_up
             if keep_device:
                 # the device outputs sit at the head of the workspace (graph_carve in api.cu): copy them out
                 esz = 4 if dtype == _lib.SBK_F32 else 8
