@@ -366,11 +366,11 @@ def run_ours(args):
                     'sample': f'{block} query rows x all {n} references, live scikit-learn brute kneighbors (the call SemiBin makes), one run',
                     'parity_rows_bad': res['n_rows_bad'], 'parity_rows_tied': res['n_rows_tied'],
                     'parity_of': f'kneighbors_graph csr_matrix built on {world} device(s)'}
+            # the device-resident (gathered) result of the timed steps against the same block
+            res2 = compare.compare_knn(rd, ri, d[lo_b:lo_b + block].cpu().numpy().astype(np.float64),
+                                       i[lo_b:lo_b + block].cpu().numpy().astype(np.int64), rtol=1e-5)
+            base['parity_rows_bad_device_result'] = res2['n_rows_bad']
             if world == 1:
-                # the device-resident result of the timed steps against the same block
-                res2 = compare.compare_knn(rd, ri, d[lo_b:lo_b + block].cpu().numpy().astype(np.float64),
-                                           i[lo_b:lo_b + block].cpu().numpy().astype(np.int64), rtol=1e-5)
-                base['parity_rows_bad_device_result'] = res2['n_rows_bad']
                 line['cpu_baseline'] = base
             else:
                 line['parity'] = base

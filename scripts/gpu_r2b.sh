@@ -7,7 +7,7 @@ tail -30 gpurun_out/${tag}_pytest.log
 python bench.py --steps 5 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 tail -3 gpurun_out/${tag}_bench.err
 SBK_LIB_VARIANT=probe SBK_RERANK_BLOCK=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_blockrr.json 2> gpurun_out/${tag}_bench_blockrr.err
-SBK_LIB_VARIANT=probe SBK_RW_OCC=3 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_occ3.json 2> gpurun_out/${tag}_bench_occ3.err
+SBK_LIB_VARIANT=probe SBK_NO_ROW_ORDER=1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_noorder.json 2> gpurun_out/${tag}_bench_noorder.err
 CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $CMD > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'rerank_warp' -s 1 -c 1 -o gpurun_out/${tag}_rerank -f $CMD > gpurun_out/${tag}_ncu_rerank.log 2>&1

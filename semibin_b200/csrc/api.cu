@@ -30,8 +30,10 @@ static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the 
 #ifdef SBK_ENABLE_PROBES
 static int probe_mode() { static const int v = getenv("SBK_TC_PROBE") ? atoi(getenv("SBK_TC_PROBE")) : 0; return v; }
 static bool probe_block_rerank() { static const int v = getenv("SBK_RERANK_BLOCK") ? atoi(getenv("SBK_RERANK_BLOCK")) : 0; return v != 0; }
+static bool probe_no_row_order() { static const int v = getenv("SBK_NO_ROW_ORDER") ? atoi(getenv("SBK_NO_ROW_ORDER")) : 0; return v != 0; }
 #else
 static constexpr bool probe_block_rerank() { return false; }
+static constexpr bool probe_no_row_order() { return false; }
 #endif
 
 struct KnnWs {
@@ -39,6 +41,7 @@ struct KnnWs {
   int32_t* fail_rows; int* n_fail; unsigned long long* cand_total;
   uint32_t* fb_idx; int32_t* fb_count;                  // fallback (exact filter) candidate lists
   int32_t* retry;                                       // tensor path: rows handed back by the warp rerank
+  void* order_ws; size_t order_bytes;                   // tensor path: locality order of the chunk's rows for the warp rerank
   void* tc;                                             // tensor-path staging area
   size_t tc_bytes;
 };
@@ -93,6 +96,8 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, i
   w.fb_idx = a.take<uint32_t>((size_t)s.fb_rows * s.fb_split * k1);
   w.fb_count = a.take<int32_t>((size_t)s.fb_rows + 1);
   w.retry = a.take<int32_t>((size_t)s.retry_cap + 1);
+  w.order_bytes = s.tcap ? row_order_workspace_bytes(s.chunk) : 0;
+  w.order_ws = a.take<char>(w.order_bytes);
   w.tc = nullptr; w.tc_bytes = 0;
   if (s.algo == SBK_KNN_TENSOR) {
     w.tc_bytes = tc_workspace_bytes(s.plan, n_ref, s.chunk);
@@ -301,13 +306,15 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
         // warp-per-row rerank straight from the candidate lists, then the block-per-row kernel for the few rows it
         // hands back (device-side list, no host sync)
         SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
-        rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
+        int32_t* perm = nullptr;
+        if (!probe_no_row_order()) rc = launch_row_order(X, dtype, d, ld, row0, cn, tcs.centre, w.order_ws, w.order_bytes, &perm, stream);
+        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, perm, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
                                 tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap,
                                 w.cand_total, stream, peers);
         if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                                     w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total + 8, stream,
                                     w.retry, w.n_fail + 2, (int)s.retry_cap, peers);
-        st.n_launches += 3;
+        st.n_launches += 5;
       } else {
         rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                            w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total, stream,

@@ -31,7 +31,11 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
 // retry mode, uncertified rows to fail_rows
 int rerank_warp_cap(int k);
 bool rerank_warp_supported(int dtype, int d, int k);
-int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
+size_t row_order_workspace_bytes(long long n_rows);
+// locality order of the chunk's query rows for the warp rerank: perm_out[i] = slot visited i-th (lives in `ws`)
+int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
+                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream);
+int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows, const int32_t* perm,
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,

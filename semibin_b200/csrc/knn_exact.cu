@@ -13,6 +13,7 @@
 #include "knn.cuh"
 #include <algorithm>
 #include <stdlib.h>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace sbk {
 
@@ -623,7 +624,7 @@ template <> struct RwSort<16, 1024> { static __device__ __forceinline__ void run
 // branches and address arithmetic: one predicated LDG.128 per chunk from a per-lane base pointer.  Two rows per
 // call so that both rows' loads are in flight before either is consumed.  Fixed xor-shuffle tree: deterministic,
 // and bit-identical to RegQuery::eval / sqdist_g8 (same per-lane partial sums, same combination order).
-template <typename T, bool VEC>
+template <typename T, bool VEC, bool FULL>
 struct WarpDist {
   using C = DistCfg<T>;
   static constexpr int NV = C::NCH * C::V;
@@ -647,12 +648,17 @@ struct WarpDist {
     qt = tail ? (double)x[ct] : 0.0;
   }
 
+  // FULL: every chunk but the last exists for every lane (d > LPC * V * (NCH - 1)): those loads are unconditional
+  // and need no zero fill -- the shapes of the path (D = 100..128 float32, 136 / 146 float64) all qualify
   __device__ __forceinline__ void fetch(const T* __restrict__ y, T (&v)[NV], T& vt) const {
 #pragma unroll
     for (int j = 0; j < C::NCH; ++j) {
+      const bool always = FULL && j < C::NCH - 1;
+      if (!always) {
 #pragma unroll
-      for (int e = 0; e < C::V; ++e) v[j * C::V + e] = (T)0;
-      if ((act >> j) & 1u) {
+        for (int e = 0; e < C::V; ++e) v[j * C::V + e] = (T)0;
+      }
+      if (always || ((act >> j) & 1u)) {
         if (VEC) {
           if (sizeof(T) == 4) {
             const float4 f = __ldg(reinterpret_cast<const float4*>(y) + sub + C::LPC * j);
@@ -698,10 +704,10 @@ struct WarpDist {
 
 // FP64 squared distances of the rows id_s[lo..hi) -> key_s[lo..hi); returns the lane's running maximum.
 // Two candidate groups per turn: 2 * NCH loads in flight per lane.
-template <typename T, bool VEC>
-__device__ __forceinline__ double rw_distances(const T* __restrict__ X, long long ld, const WarpDist<T, VEC>& wd,
+template <typename T, bool VEC, bool FULL>
+__device__ __forceinline__ double rw_distances(const T* __restrict__ X, long long ld, const WarpDist<T, VEC, FULL>& wd,
                                                const uint32_t* id_s, double* key_s, int lo, int hi, int g, double mx) {
-  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC, NV = WarpDist<T, VEC>::NV;
+  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC, NV = WarpDist<T, VEC, FULL>::NV;
 #pragma unroll 1
   for (int e0 = lo; e0 < hi; e0 += 2 * CPI) {          // warp-uniform trip count (shuffles in reduce)
     const int ea = e0 + g, eb = e0 + CPI + g;
@@ -717,6 +723,33 @@ __device__ __forceinline__ double rw_distances(const T* __restrict__ X, long lon
   }
   return mx;
 }
+// Phase 2: the rows list[0..cnt) are evaluated the same way, but only those within dmax are appended to
+// (key_s, id_s) at m (ballot compaction over the group leaders); returns the new m (may exceed cap: caller checks).
+template <typename T, bool VEC, bool FULL>
+__device__ __forceinline__ int rw_distances_keep(const T* __restrict__ X, long long ld, const WarpDist<T, VEC, FULL>& wd,
+                                                 const uint32_t* list, int cnt, double dmax, double* key_s, uint32_t* id_s,
+                                                 int m, int cap, int g, int lane) {
+  constexpr int LPC = DistCfg<T>::LPC, CPI = 32 / LPC, NV = WarpDist<T, VEC, FULL>::NV;
+#pragma unroll 1
+  for (int e0 = 0; e0 < cnt; e0 += 2 * CPI) {
+    const int ea = e0 + g, eb = e0 + CPI + g;
+    const bool ra = ea < cnt, rb = eb < cnt;
+    const uint32_t ja = list[ra ? ea : 0], jb = list[rb ? eb : 0];
+    T va[NV], vb[NV]; T ta, tb;
+    wd.fetch(X + (long long)ja * ld, va, ta);
+    wd.fetch(X + (long long)jb * ld, vb, tb);
+    const double da = wd.reduce(va, ta);
+    const double db = wd.reduce(vb, tb);
+    const bool ka = ra && wd.sub == 0 && da <= dmax, kb = rb && wd.sub == 0 && db <= dmax;
+    const uint32_t bala = __ballot_sync(0xffffffffu, ka), balb = __ballot_sync(0xffffffffu, kb);
+    const int ata = m + __popc(bala & ((1u << lane) - 1u));
+    const int atb = m + __popc(bala) + __popc(balb & ((1u << lane) - 1u));
+    if (ka && ata < cap) { key_s[ata] = da; id_s[ata] = ja; }
+    if (kb && atb < cap) { key_s[atb] = db; id_s[atb] = jb; }
+    m += __popc(bala) + __popc(balb);
+  }
+  return m;
+}
 __device__ __forceinline__ double rw_warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -724,9 +757,12 @@ __device__ __forceinline__ double rw_warp_max(double v) {
 }
 
 static constexpr int RW_QCAP = 3072;                   // candidates per row the select phase holds (16-bit keys in shared memory)
-template <typename T, int EPL, int MINB, bool VEC>
+static constexpr int RW_P2CAP = 512;                   // phase-2 candidates per row (more: the block kernel takes the row)
+static constexpr size_t rw_smem_bytes(int nel) { return (size_t)RW_WARPS * ((size_t)nel * 12 + RW_QCAP * 2 + RW_P2CAP * 4); }
+template <typename T, int EPL, int MINB, bool VEC, bool FULL>
 __global__ void __launch_bounds__(RW_WARPS * 32, MINB)
 rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_begin, long long n_rows,
+                   const int32_t* __restrict__ perm,
                    const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
                    const float* __restrict__ thr, const double* __restrict__ bound, const double* __restrict__ nrm,
                    const float4* __restrict__ norms4, const double* __restrict__ scale, const int32_t* __restrict__ orig, int k,
@@ -737,15 +773,18 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   constexpr int NEL = 32 * EPL;
   constexpr int LPC = DistCfg<T>::LPC;
   extern __shared__ __align__(16) unsigned char rw_smem[];
-  double* key_s = reinterpret_cast<double*>(rw_smem) + (size_t)(threadIdx.x >> 5) * NEL;                   // [RW_WARPS][NEL]
-  uint32_t* id_s = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + (size_t)(threadIdx.x >> 5) * NEL;
-  uint16_t* q_s = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL) + RW_WARPS * NEL)
-                  + (size_t)(threadIdx.x >> 5) * RW_QCAP;                                                  // [RW_WARPS][RW_QCAP]
-  uint32_t* st_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL)
-                   + RW_WARPS * NEL) + (size_t)RW_WARPS * RW_QCAP) + (size_t)(threadIdx.x >> 5) * 64;        // [RW_WARPS][64] phase-2 ring
-  const int lane = threadIdx.x & 31;
-  const long long slot = (long long)blockIdx.x * RW_WARPS + (threadIdx.x >> 5);
-  if (slot >= n_rows) return;
+  const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* key_s = reinterpret_cast<double*>(rw_smem) + (size_t)wp * NEL;                                       // [RW_WARPS][NEL]
+  uint32_t* id_base = reinterpret_cast<uint32_t*>(reinterpret_cast<double*>(rw_smem) + RW_WARPS * NEL);
+  uint32_t* id_s = id_base + (size_t)wp * NEL;                                                                 // [RW_WARPS][NEL]
+  uint32_t* p2_base = id_base + RW_WARPS * NEL;
+  uint32_t* p2_s = p2_base + (size_t)wp * RW_P2CAP;                                                            // [RW_WARPS][RW_P2CAP]
+  uint16_t* q_s = reinterpret_cast<uint16_t*>(p2_base + RW_WARPS * RW_P2CAP) + (size_t)wp * RW_QCAP;           // [RW_WARPS][RW_QCAP]
+  const long long widx = (long long)blockIdx.x * RW_WARPS + wp;
+  if (widx >= n_rows) return;
+  // rows are visited in the locality order of launch_row_order (neighbouring warps work on neighbouring rows of the
+  // feature space: their gathers hit the same lines of L2 / L1); the lists and the outputs stay indexed by slot / row
+  const long long slot = perm ? (long long)perm[widx] : widx;
   const long long row = q_begin + slot;
   const int k1 = k + 1;
   const int seg_cap = cand_cap >> 2;
@@ -785,85 +824,80 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
     const float range = hi_f - lo_f;
     sc_f = range > 0.f ? 65535.0f / range : 0.f;
   }
-  for (int e = lane; e < n; e += 32) {
-    const float l = __uint_as_float(base[elem(e)].y);
-    q_s[e] = (uint16_t)min(65535u, __float2uint_rz(fmaxf(l - lo_f, 0.f) * sc_f));
+  const int npad = (n + 63) & ~63;                       // whole pairs for every lane; RW_QCAP is a multiple of 64
+  for (int e = lane; e < npad; e += 32) {
+    uint32_t qv = 0xffffu;                               // padding: never below any test value
+    if (e < n) qv = min(65535u, __float2uint_rz(fmaxf(__uint_as_float(base[elem(e)].y) - lo_f, 0.f) * sc_f));
+    q_s[e] = (uint16_t)qv;
   }
   __syncwarp();
   uint32_t res = 0;                                      // the (k+1)-th smallest quantised value, bit by bit
-  for (int bit = 15; bit >= 0; --bit) {
-    const uint32_t t = res | (1u << bit);
-    int cnt = 0;
-    for (int e = lane; e < n; e += 32) cnt += (uint32_t)q_s[e] < t ? 1 : 0;
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (cnt < k1) res = t;
+  {
+    const uint32_t* q2 = reinterpret_cast<const uint32_t*>(q_s);
+    const int np = npad >> 1;                            // multiple of 32
+    for (int bit = 15; bit >= 0; --bit) {
+      const uint32_t t = res | (1u << bit);
+      int cnt = 0;
+#pragma unroll 2
+      for (int i = lane; i < np; i += 32) {
+        const uint32_t w2 = q2[i];
+        cnt += ((w2 & 0xffffu) < t ? 1 : 0) + ((w2 >> 16) < t ? 1 : 0);
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt < k1) res = t;
+    }
   }
-  // A = {q <= res}: at least k+1 members; positions -> rows, compacted into shared memory
+  // A = {q <= res}: at least k+1 members, compacted as positions, then mapped to rows in one parallel pass
   int mA = 0;
   for (int e0 = 0; e0 < n; e0 += 32) {
     const int e = e0 + lane;
     const bool inA = e < n && (uint32_t)q_s[e] <= res;
     const uint32_t bal = __ballot_sync(0xffffffffu, inA);
     const int at = mA + __popc(bal & ((1u << lane) - 1u));
-    if (inA && at < NEL) id_s[at] = (uint32_t)orig[base[elem(e)].x];
+    if (inA && at < NEL) id_s[at] = base[elem(e)].x;
     mA += __popc(bal);
   }
   if (mA > NEL) { hand_back(-1); return; }
   __syncwarp();
+  for (int i = lane; i < mA; i += 32) id_s[i] = (uint32_t)orig[id_s[i]];
+  __syncwarp();
   const int sub = lane & (LPC - 1), g = lane / LPC;
-  WarpDist<T, VEC> wd;
+  WarpDist<T, VEC, FULL> wd;
   wd.load(X + row * ld, d, sub);
   // ---- phase 1 ----
-  const double dmax = rw_warp_max(rw_distances<T, VEC>(X, ld, wd, id_s, key_s, 0, mA, g, 0.0));
+  const double dmax = rw_warp_max(rw_distances<T, VEC, FULL>(X, ld, wd, id_s, key_s, 0, mA, g, 0.0));
   // ---- phase 2: candidates outside A whose lower bound does not exclude d2 <= dmax ----
-  // Streamed: passing candidates are staged (64-entry ring per warp), evaluated eight at a time and only those with
-  // d2 <= dmax are kept (A alone holds k+1 rows within dmax, so nothing farther can be among the k+1 nearest):
-  // dense neighbourhoods put hundreds of candidates inside the slack band, the sort still sees ~k+1 entries.
-  int m = mA;
-  long long n_eval = mA;
+  // Dense neighbourhoods put dozens of candidates inside the slack band: they are listed (positions, one scan with
+  // independent loads), mapped to rows in one parallel pass, evaluated like A, and only those within dmax are kept
+  // (A alone holds k+1 rows within dmax, so nothing farther can be among the k+1 nearest): the sort sees ~k+1 entries.
+  int m = mA, m2 = 0;
   {
-    constexpr int CPI = 32 / LPC;
     const double S = scale[0];
     // L_ij <= S^2 d2_ij - nrm_i + sigma_i; the inflation covers the rounding of dmax and of this expression
     const double cut = S * S * dmax * (1.0 + 1e-12) - nrm[row] * (1.0 - 1e-12) + (double)norms4[row].w + 1e-300;
-    int head = 0, ns = 0;                               // ring state, warp-uniform
-    for (int e0 = 0; e0 < n || ns > 0; e0 += 32) {
-      if (e0 < n) {
-        const int e = e0 + lane;
-        bool take = false; uint32_t pos = 0;
-        if (e < n && (uint32_t)q_s[e] > res) {
-          const uint2 pr = base[elem(e)];
-          take = (double)__uint_as_float(pr.y) <= cut; pos = pr.x;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, take);
-        if (take) st_s[(head + ns + __popc(bal & ((1u << lane) - 1u))) & 63] = (uint32_t)orig[pos];
-        ns += __popc(bal);
-        __syncwarp();
+#pragma unroll 2
+    for (int e0 = 0; e0 < n; e0 += 32) {
+      const int e = e0 + lane;
+      bool take = false; uint32_t pos = 0;
+      if (e < n && (uint32_t)q_s[e] > res) {
+        const uint2 pr = base[elem(e)];
+        take = (double)__uint_as_float(pr.y) <= cut; pos = pr.x;
       }
-      // evaluate full batches of 2 * CPI; at the end of the list also the last partial one
-      while (ns >= 2 * CPI || (e0 + 32 >= n && ns > 0)) {
-        const int nb = min(ns, 2 * CPI);
-        const bool ra = g < nb, rb = CPI + g < nb;
-        const uint32_t ja = st_s[(head + (ra ? g : 0)) & 63], jb = st_s[(head + (rb ? CPI + g : 0)) & 63];
-        T va[WarpDist<T, VEC>::NV], vb[WarpDist<T, VEC>::NV]; T ta, tb;
-        wd.fetch(X + (long long)ja * ld, va, ta);
-        wd.fetch(X + (long long)jb * ld, vb, tb);
-        const double da = wd.reduce(va, ta);
-        const double db = wd.reduce(vb, tb);
-        const bool ka = ra && sub == 0 && da <= dmax, kb = rb && sub == 0 && db <= dmax;
-        const uint32_t bala = __ballot_sync(0xffffffffu, ka), balb = __ballot_sync(0xffffffffu, kb);
-        const int ata = m + __popc(bala & ((1u << lane) - 1u));
-        const int atb = m + __popc(bala) + __popc(balb & ((1u << lane) - 1u));
-        if (ka && ata < NEL) { key_s[ata] = da; id_s[ata] = ja; }
-        if (kb && atb < NEL) { key_s[atb] = db; id_s[atb] = jb; }
-        m += __popc(bala) + __popc(balb);
-        n_eval += nb;
-        head = (head + nb) & 63; ns -= nb;
-        __syncwarp();
-      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, take);
+      const int at = m2 + __popc(bal & ((1u << lane) - 1u));
+      if (take && at < RW_P2CAP) p2_s[at] = pos;
+      m2 += __popc(bal);
     }
   }
-  if (m > NEL) { hand_back(-1); return; }
+  if (m2 > RW_P2CAP) { hand_back(-1); return; }
+  if (m2 > 0) {
+    __syncwarp();
+    for (int i = lane; i < m2; i += 32) p2_s[i] = (uint32_t)orig[p2_s[i]];
+    __syncwarp();
+    m = rw_distances_keep<T, VEC, FULL>(X, ld, wd, p2_s, m2, dmax, key_s, id_s, mA, NEL, g, lane);
+    if (m > NEL) { hand_back(-1); return; }
+  }
+  const long long n_eval = (long long)mA + m2;
   if (lane == 0 && totals) { atomicAdd(&totals[0], (unsigned long long)n); atomicAdd(&totals[1], (unsigned long long)n_eval); }
   __syncwarp();
   // ---- (d2 pattern, row) pairs into registers; the initial placement is irrelevant to a sort ----
@@ -931,20 +965,21 @@ int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with
   return 0;
 }
 
-template <typename T, int EPL, int MINB, bool VEC>
+template <typename T, int EPL, int MINB, bool VEC, bool FULL>
 static int rw_launch(unsigned grid, cudaStream_t stream, const T* X, int d, long long ld, long long q_begin, long long n_rows,
+                     const int32_t* perm,
                      const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                      const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                      T* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                      int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, const PeerOut& peers) {
-  const size_t smem = (size_t)RW_WARPS * (32 * EPL * 12 + RW_QCAP * 2 + 64 * 4);
-  SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_warp_kernel<T, EPL, MINB, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rerank_warp_kernel<T, EPL, MINB, VEC><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr,
-      bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, peers);
+  const size_t smem = rw_smem_bytes(32 * EPL);
+  SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_warp_kernel<T, EPL, MINB, VEC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rerank_warp_kernel<T, EPL, MINB, VEC, FULL><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, perm, cand, cand_count, cand_cap,
+      thr, bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, peers);
   return SBK_OK;
 }
 
-int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
+int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows, const int32_t* perm,
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
@@ -958,16 +993,21 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
   const unsigned grid = (unsigned)((n_rows + RW_WARPS - 1) / RW_WARPS);
   const size_t esz = dtype == SBK_F32 ? 4 : 8;
   const bool vec = ((((uintptr_t)X) & 15) == 0) && (((ld * (long long)esz) & 15) == 0);
+  // every chunk but the last exists for every lane: d above LPC * V * (NCH - 1) columns (96 float32 / 128 float64)
+  const bool full = dtype == SBK_F32 ? d > DistCfg<float>::LPC * DistCfg<float>::V * (DistCfg<float>::NCH - 1)
+                                     : d > DistCfg<double>::LPC * DistCfg<double>::V * (DistCfg<double>::NCH - 1);
   // 2 CTAs (16 warps) per SM at up to 128 registers by default; the probe build can ask for 3 CTAs at 80 registers
   static const int occ = rw_env_int("SBK_RW_OCC", 2);
   int rc = SBK_OK;
-#define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
+#define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, perm, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
       (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, po
-#define SBK_RW_LAUNCH(T, EPL)                                                                                           \
+#define SBK_RW_LAUNCH2(T, EPL, MINB)                                                                                    \
   do {                                                                                                                  \
-    if (occ == 3) rc = vec ? rw_launch<T, EPL, 3, true>(SBK_RW_ARGS(T)) : rw_launch<T, EPL, 3, false>(SBK_RW_ARGS(T)); \
-    else rc = vec ? rw_launch<T, EPL, 2, true>(SBK_RW_ARGS(T)) : rw_launch<T, EPL, 2, false>(SBK_RW_ARGS(T));          \
+    if (vec && full) rc = rw_launch<T, EPL, MINB, true, true>(SBK_RW_ARGS(T));                                          \
+    else if (vec) rc = rw_launch<T, EPL, MINB, true, false>(SBK_RW_ARGS(T));                                            \
+    else rc = rw_launch<T, EPL, MINB, false, false>(SBK_RW_ARGS(T));                                                    \
   } while (0)
+#define SBK_RW_LAUNCH(T, EPL) do { if (occ == 3) SBK_RW_LAUNCH2(T, EPL, 3); else SBK_RW_LAUNCH2(T, EPL, 2); } while (0)
 #define SBK_RW_DISPATCH(T)                                                                                              \
   do {                                                                                                                  \
     if (cap <= 64) SBK_RW_LAUNCH(T, 2); else if (cap <= 128) SBK_RW_LAUNCH(T, 4);                                       \
@@ -976,11 +1016,71 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
   if (dtype == SBK_F32) SBK_RW_DISPATCH(float); else SBK_RW_DISPATCH(double);
 #undef SBK_RW_DISPATCH
 #undef SBK_RW_LAUNCH
+#undef SBK_RW_LAUNCH2
 #undef SBK_RW_ARGS
   if (rc) return rc;
   SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
+
+// ---------------------------------------------------------------------------
+// locality order of the query rows for the rerank
+// ---------------------------------------------------------------------------
+// The rerank gathers ~k+1 reference rows per query; queries that sit close together in the feature space gather
+// (nearly) the same rows.  Visiting the queries grouped by a 16-bit random-hyperplane signature of the centred row
+// turns most of that traffic into L2 / L1 hits instead of 80+ GB of DRAM gathers in input order.  Any order is
+// correct; this one only has to be cheap: one pass over the chunk's rows (16 sign-sums per row) + a 16-bit radix sort.
+__global__ void __launch_bounds__(256)
+row_signature_kernel(const void* __restrict__ Xv, int is_f64, int d, long long ld, long long q_begin, long long n_rows,
+                     const double* __restrict__ centre, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_rows) return;
+  float acc[16];
+#pragma unroll
+  for (int b = 0; b < 16; ++b) acc[b] = 0.f;
+  const long long r = q_begin + s;
+  for (int c = 0; c < d; ++c) {
+    const float v = is_f64 ? (float)(reinterpret_cast<const double*>(Xv)[r * ld + c] - centre[c])
+                           : (float)((double)reinterpret_cast<const float*>(Xv)[r * ld + c] - centre[c]);
+    uint32_t h = (uint32_t)c * 2654435761u;               // 16 pseudo-random signs per column
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+#pragma unroll
+    for (int b = 0; b < 16; ++b) acc[b] += ((h >> b) & 1u) ? v : -v;
+  }
+  uint32_t key = 0;
+#pragma unroll
+  for (int b = 0; b < 16; ++b) key |= (acc[b] > 0.f ? 1u : 0u) << b;
+  keys[s] = key; vals[s] = (int32_t)s;
+}
+
+size_t row_order_workspace_bytes(long long n_rows) {
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)std::max<long long>(n_rows, 1), 0, 16, (cudaStream_t)0);
+  return align_up((size_t)n_rows * 4, 256) * 4 + align_up(tmp, 256) + 1024;
+}
+
+// perm_out[i] = slot visited i-th.  `ws` holds row_order_workspace_bytes(n_rows).
+int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
+                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream) {
+  if (n_rows <= 0) { *perm_out = nullptr; return SBK_OK; }
+  Arena a(ws, ws_bytes);
+  uint32_t* keys_in = a.take<uint32_t>((size_t)n_rows);
+  uint32_t* keys_out = a.take<uint32_t>((size_t)n_rows);
+  int32_t* vals_in = a.take<int32_t>((size_t)n_rows);
+  int32_t* vals_out = a.take<int32_t>((size_t)n_rows);
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, keys_in, keys_out, vals_in, vals_out, (int)n_rows, 0, 16, stream);
+  void* cub_tmp = a.take<char>(tmp);
+  if (!a.ok()) { set_error("row order: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
+  row_signature_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(X, dtype == SBK_F64 ? 1 : 0, d, ld, q_begin, n_rows, centre,
+                                                                           keys_in, vals_in);
+  SBK_LAUNCH_CHECK();
+  SBK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, vals_in, vals_out, (int)n_rows, 0, 16, stream));
+  *perm_out = vals_out;
+  return SBK_OK;
+}
+
 bool rerank_warp_supported(int dtype, int d, int k) {
   return rerank_warp_cap(k) != 0 && d <= (dtype == SBK_F32 ? RegQuery<float>::MAX_D : RegQuery<double>::MAX_D);
 }

@@ -517,7 +517,12 @@ template <int CG> __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, ui
 // CG = 2: a CTA pair (cluster of 2) per 256 query rows, tcgen05.mma.cta_group::2 M=256 N=256; each CTA
 //         stages its own A tile and its 128-row half of every reference tile, the leader issues the MMAs
 //         and multicasts their completion, the peer's MMA warp relays "my operands have landed".
-template <int MODE, int CG>
+// NH = accumulator stages per reference tile: 1 -> two stages of 256 TMEM columns (one N=256 MMA group per tile),
+// 2 -> four stages of 128 columns (two N=128 groups per tile).  The MMA issuer may only reuse a stage once all
+// epilogue warps of the pair have drained it, and that round trip (commit -> epilogue wake-up -> tcgen05.ld ->
+// remote arrive -> issuer wake-up) is longer than one tile's MMAs: with two stages the tile period becomes
+// (T_mma + round trip) / 2, with four half-tile stages (T_mma / 2 + round trip) / 2, which is below T_mma.
+template <int MODE, int CG, int NH>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_kernel(const TcArgs p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -530,9 +535,12 @@ tc_kernel(const TcArgs p) {
   unsigned char* tail = sB + tc_ring_bytes(kpad, p.nstage, CG);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);          // [nstage]
   uint64_t* empty_bar = full_bar + TC_MAX_STAGES;                  // [nstage]
-  uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;                 // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;                            // [2]  (CG = 2: the leader's are used)
-  uint64_t* a_bar = tempty_bar + 2;                                // [1]
+  constexpr int NS = 2 * NH;                                       // TMEM accumulator stages
+  constexpr int SN = TC_BN / NH;                                   // columns per stage = N of one MMA group
+  constexpr int RH = BROWS / NH;                                   // reference rows this CTA feeds into one MMA group
+  uint64_t* tfull_bar = empty_bar + TC_MAX_STAGES;                 // [4]
+  uint64_t* tempty_bar = tfull_bar + 4;                            // [4]  (CG = 2: the leader's are used)
+  uint64_t* a_bar = tempty_bar + 4;                                // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -546,7 +554,7 @@ tc_kernel(const TcArgs p) {
     // CG = 2, leader: a stage is full when its own half has landed (expect_tx arrive) AND the peer's relay has arrived
     const uint32_t nfull = (CG == 2 && leader) ? 2 : 1;
     for (int s = 0; s < p.nstage; ++s) { mbar_init(&full_bar[s], nfull); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CG * TC_EPI_WARPS); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], CG * TC_EPI_WARPS); }
     mbar_init(a_bar, nfull);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -593,30 +601,34 @@ tc_kernel(const TcArgs p) {
     if (leader) {
       // ===== MMA issuer =====
       mbar_wait(a_bar, 0);
-      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)((CG * TC_BM) >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(SN >> 3) << 17) | ((uint32_t)((CG * TC_BM) >> 4) << 24);
       // one k-step = 16 FP16 = two 16-byte chunks; chunk stride = staged rows * 16 B.  The start-address field
-      // of a descriptor counts 16-byte units, so stepping k (or the ring stage) is an add on the low word.
+      // of a descriptor counts 16-byte units, so stepping k (or the ring stage, or the row half) is an add on the low word.
       const uint64_t adesc0 = tc_smem_desc(smem_u32(sA), TC_BM * 16, 128);
       const uint64_t bdesc0 = tc_smem_desc(smem_u32(sB), BROWS * 16, 128);
       constexpr uint32_t a_kstep = (2 * TC_BM * 16) >> 4, b_kstep = (2 * BROWS * 16) >> 4;
       const uint32_t b_stage_step = b_bytes >> 4;
       const int ksteps = kpad / 16;
       int stage = 0; uint32_t phase = 0;
+      uint32_t sidx = 0;                                          // running accumulator-stage counter
       for (long long t = 0; t < n_tiles; ++t) {
-        const int as = (int)(t & 1);
-        mbar_wait(&tempty_bar[as], (uint32_t)(((t >> 1) & 1) ^ 1));
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t d_addr = tmem_base + (uint32_t)as * TC_BN;
-          const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_stage_step);
 #pragma unroll
-          for (int ks = 0; ks < TC_MAX_KPAD / 16; ++ks)
-            if (ks < ksteps) tc_mma_f16<CG>(d_addr, adesc0 + (uint64_t)(ks * a_kstep), bdesc + (uint64_t)(ks * b_kstep), idesc, ks > 0 ? 1u : 0u);
-          tc_commit<CG>(&empty_bar[stage]);      // smem stage reusable once these MMAs retire
-          tc_commit<CG>(&tfull_bar[as]);         // accumulator ready for the epilogue
+        for (int h = 0; h < NH; ++h, ++sidx) {
+          const int as = (int)(sidx % NS);
+          mbar_wait(&tempty_bar[as], (uint32_t)(((sidx / NS) & 1) ^ 1));
+          if (h == 0) mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d_addr = tmem_base + (uint32_t)as * SN;
+            const uint64_t bdesc = bdesc0 + (uint64_t)((uint32_t)stage * b_stage_step + (uint32_t)(h * RH));   // rows h*RH.. : 16 B each
+#pragma unroll
+            for (int ks = 0; ks < TC_MAX_KPAD / 16; ++ks)
+              if (ks < ksteps) tc_mma_f16<CG>(d_addr, adesc0 + (uint64_t)(ks * a_kstep), bdesc + (uint64_t)(ks * b_kstep), idesc, ks > 0 ? 1u : 0u);
+            if (h == NH - 1) tc_commit<CG>(&empty_bar[stage]);   // smem stage reusable once these MMAs retire
+            tc_commit<CG>(&tfull_bar[as]);                       // accumulator stage ready for the epilogue
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
       }
     } else {

@@ -131,13 +131,21 @@ def dbscan(X, eps=0.5, *, min_samples=5, metric='precomputed', metric_params=Non
 
 
 def long_read_features(embedding, depth, n_sample, is_combined):
-    """long_read_cluster.py:72-81."""
+    """long_read_cluster.py:72-81.  A CUDA embedding stays on its device (N3: the reference copies it to the host and
+    back, long_read_cluster.py:70): only the S log-depth columns are computed on the host -- with numpy's float32 log,
+    the reference's own evaluator, so the features are bit-identical -- and uploaded for the concat."""
+    import torch
+    on_device = isinstance(embedding, torch.Tensor) and embedding.is_cuda
     if is_combined:
-        return np.ascontiguousarray(embedding, dtype=np.float32)
+        return embedding.float().contiguous() if on_device else np.ascontiguousarray(embedding, dtype=np.float32)
     depth = np.asarray(depth, dtype=np.float32)
     mean_index = [2 * temp for temp in range(n_sample)]
-    depth = depth[:, mean_index]
-    return np.concatenate((embedding, np.log(np.clip(depth, 1e-6, None))), axis=1)
+    logd = np.log(np.clip(depth[:, mean_index], 1e-6, None))
+    if on_device:
+        return torch.cat((embedding.float(), torch.from_numpy(logd).to(embedding.device)), dim=1).contiguous()
+    if isinstance(embedding, torch.Tensor):
+        embedding = embedding.numpy()
+    return np.concatenate((embedding, logd), axis=1)
 
 
 def long_read_labels(embedding, depth, lengths, *, n_sample, is_combined, eps_list=None, min_samples=5,
@@ -146,11 +154,12 @@ def long_read_labels(embedding, depth, lengths, *, n_sample, is_combined, eps_li
     import torch
     _lib.require_cuda()
     x = long_read_features(embedding, depth, n_sample, is_combined)
-    xd = _as_device_matrix(x)
+    xd = x if (isinstance(x, torch.Tensor) and x.is_cuda) else _as_device_matrix(x)
     k = min(n_neighbors, xd.shape[0] - 1)                 # long_read_cluster.py:110
-    dist, idx = knn(xd, k, algo=algo)
-    res = dbscan_sweep((dist, idx), EPS_GRID if eps_list is None else eps_list, min_samples=min_samples,
-                       sample_weight=lengths)
+    with torch.cuda.device(xd.device):
+        dist, idx = knn(xd, k, algo=algo)
+        res = dbscan_sweep((dist, idx), EPS_GRID if eps_list is None else eps_list, min_samples=min_samples,
+                           sample_weight=lengths)
     return (res, (dist, idx)) if return_graph else res
 
 
@@ -303,7 +312,8 @@ def cluster_long_read(logger, model, data, device, is_combined, n_sample, out, c
     with torch.no_grad():                                            # :67-70
         model.eval()
         net_in = torch.from_numpy(np.ascontiguousarray(_network_input(table, is_combined))).to(device)
-        embedding = model.embedding(net_in.float()).detach().cpu().numpy()
+        embedding = model.embedding(net_in.float()).detach()         # stays on `device` (one batch, as the reference: a
+        #                                                              chunked forward could change GEMM summation order)
     lengths = np.fromiter((len(contig_dict[name]) for name in names), dtype=np.int64, count=len(names))
     depth = None if is_combined else table[:, 136:].astype(np.float32)
     contig2marker = _markers_per_contig(names, contig_dict, out, binned_length, args)
