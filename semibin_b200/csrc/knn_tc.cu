@@ -57,6 +57,7 @@ static constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 4);
 static constexpr int TC_NGROUP = 128;           // group minima per row (4 column quarters x 32 columns)
 static constexpr int TC_MAX_STAGES = 6;
 static constexpr int TC_DEFAULT_CG = 2;
+static constexpr int TC_DEFAULT_NH = 1;         // accumulator stages per tile (2 = four half-tile stages); see tc_kernel
 static constexpr int TC_MAX_KPAD = 176;
 static constexpr int TC_MAX_SPLIT = 12;         // columns that may get an FP16 hi+lo representation
 // instruction descriptor, kind::f16: A,B = F16 (0), D = F32 (1<<4), K-major, N>>3 @17, M>>4 @24 (built in the kernel)
@@ -670,34 +671,44 @@ tc_kernel(const TcArgs p) {
       cnt = min(cnt, seg_cap);
     }
     int probe_hits = 0;
-    // first tile column of this warp's quarter; loop-carried so the append path finds it in a register
-    uint32_t jcol = (uint32_t)(p.bt0 * TC_BN + w4 * 64) - (uint32_t)TC_BN;
+    constexpr int WC = SN / 4;                   // columns of one accumulator stage this warp owns: 64 (NH = 1) or 32
+    constexpr int NCHK = WC / 32;                // 32-column register chunks per stage
+    // reference position of the first column of register chunk hh of half h:  accumulator column cc = w4 * WC + hh * 32
+    // was fed by CTA cc / RH of the pair from row h * RH + cc % RH of its staged BROWS rows
+    auto chunk_off = [&](int h, int hh) -> uint32_t {
+      const int cc = w4 * WC + hh * 32;
+      return (uint32_t)((cc / RH) * BROWS + h * RH + (cc % RH));
+    };
+    uint32_t jtile = (uint32_t)(p.bt0 * TC_BN) - (uint32_t)TC_BN;    // first position of the current tile; loop-carried
+    uint32_t sidx = 0;                                                // running accumulator-stage counter
 
     for (long long t = 0; t < n_tiles; ++t) {
-      const int as = (int)(t & 1);
-      jcol += (uint32_t)TC_BN;
-      mbar_wait(&tfull_bar[as], (uint32_t)((t >> 1) & 1));
+      jtile += (uint32_t)TC_BN;
+#pragma unroll
+      for (int h = 0; h < NH; ++h, ++sidx) {
+      const int as = (int)(sidx % NS);
+      mbar_wait(&tfull_bar[as], (uint32_t)((sidx / NS) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TC_BN + w4 * 64);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SN + w4 * WC);
       if (MODE == TC_PROBE_NOLD) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
         continue;
       }
-      uint32_t va[32], vb[32];
+      uint32_t va[32], vb[NCHK == 2 ? 32 : 1];
       if (MODE == TC_FILTER || MODE == TC_PROBE_NOAPPEND) {
-        // Both 32-column halves go to registers and the accumulator stage is released BEFORE any of it is
+        // The warp's columns go to registers and the accumulator stage is released BEFORE any of it is
         // reduced: the MMA issuer waits for the slowest of the pair's 32 epilogue warps, so whatever a warp
         // does between "accumulator ready" and its release is on the tensor pipe's critical path.
         tmem_ld32(taddr, va);
-        tmem_ld32(taddr + 32, vb);
+        if constexpr (NCHK == 2) tmem_ld32(taddr + 32, vb);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+        for (int hh = 0; hh < NCHK; ++hh) {
           const uint32_t* v = hh ? vb : va;
           // minima of the four groups of 8 columns, then of the chunk: three-input min instructions, no branches
           float m8[4];
@@ -717,7 +728,7 @@ tc_kernel(const TcArgs p) {
             const bool full = cnt > cnt_lim;     // segment (nearly) full: the row goes to the exact filter
             overflow |= hit && full;
             const bool can = hit && !full;
-            const uint32_t j0 = jcol + hh * 32;
+            const uint32_t j0 = jtile + chunk_off(h, hh);
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               const bool hg = can && (m8[g] <= thr);
@@ -734,14 +745,16 @@ tc_kernel(const TcArgs p) {
         continue;
       }
       if (MODE == TC_SAMPLE) {
-        // one 32-column half at a time: with both halves AND the 32 running minima live the kernel exceeds its
+        // one 32-column chunk at a time: with two chunks AND the 32 running minima live the kernel exceeds its
         // 96 registers and spills the minima every tile (50 local-memory accesses per warp and tile)
         tmem_ld32(taddr, va);
         tmem_ld_wait();
+        if constexpr (NCHK == 2) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(va[c]));
-        tmem_ld32(taddr + 32, va);
-        tmem_ld_wait();
+          for (int c = 0; c < 32; ++c) gmin[c] = fminf(gmin[c], __uint_as_float(va[c]));
+          tmem_ld32(taddr + 32, va);
+          tmem_ld_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
@@ -750,24 +763,28 @@ tc_kernel(const TcArgs p) {
         continue;
       }
       tmem_ld32(taddr, va);
-      tmem_ld32(taddr + 32, vb);
+      if constexpr (NCHK == 2) tmem_ld32(taddr + 32, vb);
       tmem_ld_wait();
       // the accumulator stage is free as soon as its values sit in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
       if (MODE == TC_PROBE_LDONLY) {
-        if (va[0] == 0x7fc12345u && vb[31] == 0x7fc12345u) ++probe_hits;   // keeps the loads alive
+        if (va[0] == 0x7fc12345u && vb[0] == 0x7fc12345u) ++probe_hits;   // keeps the loads alive
       } else {   // TC_DUMP: positions -> original columns
         if (row_ok) {
-          const long long j0 = (p.bt0 + t) * TC_BN + w4 * 64;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int32_t o0 = p.orig[j0 + c], o1 = p.orig[j0 + 32 + c];
-            if (o0 != 0x7fffffff) p.dump[slot * p.dump_ld + o0] = __uint_as_float(va[c]);
-            if (o1 != 0x7fffffff) p.dump[slot * p.dump_ld + o1] = __uint_as_float(vb[c]);
+          for (int hh = 0; hh < NCHK; ++hh) {
+            const uint32_t* v = hh ? vb : va;
+            const long long j0 = (long long)(p.bt0 + t) * TC_BN + chunk_off(h, hh);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int32_t o0 = p.orig[j0 + c];
+              if (o0 != 0x7fffffff) p.dump[slot * p.dump_ld + o0] = __uint_as_float(v[c]);
+            }
           }
         }
+      }
       }
     }
 
@@ -1006,10 +1023,10 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   return SBK_OK;
 }
 
-template <int MODE, int CG>
+template <int MODE, int CG, int NH>
 static int tc_launch_cg(const TcArgs& args, long long n_mtiles, cudaStream_t stream) {
   const size_t smem = tc_smem_bytes(args.kpad, args.nstage, CG);
-  SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_kernel<MODE, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_kernel<MODE, CG, NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one CTA per 128-row query tile; CG = 2 launches them as clusters of two (the grid must then be even)
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)((n_mtiles + CG - 1) / CG * CG));
@@ -1020,12 +1037,15 @@ static int tc_launch_cg(const TcArgs& args, long long n_mtiles, cudaStream_t str
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  SBK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, CG>, args));
+  SBK_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_kernel<MODE, CG, NH>, args));
   return SBK_OK;
 }
 template <int MODE>
 static int tc_launch(const TcArgs& args, long long n_mtiles, int cg, cudaStream_t stream) {
-  return cg == 2 ? tc_launch_cg<MODE, 2>(args, n_mtiles, stream) : tc_launch_cg<MODE, 1>(args, n_mtiles, stream);
+  // accumulator stages per tile: four half-tile stages by default (see tc_kernel); SBK_TC_NH=1 (probe build) = two full-tile stages
+  static const int nh = tc_env_int("SBK_TC_NH", TC_DEFAULT_NH);
+  if (nh == 1) return cg == 2 ? tc_launch_cg<MODE, 2, 1>(args, n_mtiles, stream) : tc_launch_cg<MODE, 1, 1>(args, n_mtiles, stream);
+  return cg == 2 ? tc_launch_cg<MODE, 2, 2>(args, n_mtiles, stream) : tc_launch_cg<MODE, 1, 2>(args, n_mtiles, stream);
 }
 
 static void tc_chunk_args(TcState* st, const TcPlan& p, long long row0, long long n_rows, TcArgs& a,
