@@ -813,38 +813,43 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   if (bad || n < k1) { hand_back(bad ? 2 : 3); return; }
   if (n > RW_QCAP) { hand_back(-1); return; }
   const uint2* base = cand + slot * (long long)cand_cap;
-  // ---- select: lower bounds quantised to 16 bits between the row's own score and its final threshold ----
+  // ---- select: lower bounds quantised to 13 bits between the row's own score and its final threshold ----
   // Every candidate of the later launches has L <= thr (the thresholds only ever dropped), the k+1 smallest with
   // the planned confidence; candidates above it (admitted by an earlier, looser threshold) clamp to the top level.
-  // The self score  -||z_i||^2  is the smallest possible lower bound up to the slack.
+  // The self score  -||z_i||^2  is the smallest possible lower bound up to the slack.  8192 levels over that range
+  // are several per neighbour; a coarser level only puts a few more rows into A.
   float lo_f, sc_f;
   {
     const float hi_f = thr[slot];
     lo_f = (float)(-nrm[row]) - 0.125f * fabsf(hi_f + (float)nrm[row]) - 1.0f;
     const float range = hi_f - lo_f;
-    sc_f = range > 0.f ? 65535.0f / range : 0.f;
+    sc_f = range > 0.f ? 8191.0f / range : 0.f;
   }
-  const int npad = (n + 63) & ~63;                       // whole pairs for every lane; RW_QCAP is a multiple of 64
+  const int npad = (n + 127) & ~127;                     // four keys per lane and turn; RW_QCAP is a multiple of 128
   for (int e = lane; e < npad; e += 32) {
-    uint32_t qv = 0xffffu;                               // padding: never below any test value
-    if (e < n) qv = min(65535u, __float2uint_rz(fmaxf(__uint_as_float(base[elem(e)].y) - lo_f, 0.f) * sc_f));
+    uint32_t qv = 8191u;                                 // padding: never below any test value
+    if (e < n) qv = min(8191u, __float2uint_rz(fmaxf(__uint_as_float(base[elem(e)].y) - lo_f, 0.f) * sc_f));
     q_s[e] = (uint16_t)qv;
   }
   __syncwarp();
   uint32_t res = 0;                                      // the (k+1)-th smallest quantised value, bit by bit
   {
-    const uint32_t* q2 = reinterpret_cast<const uint32_t*>(q_s);
-    const int np = npad >> 1;                            // multiple of 32
-    for (int bit = 15; bit >= 0; --bit) {
+    // four 13-bit keys per 8-byte load; "key >= t" for both halves of a word at once: with the guard bit 15 set,
+    // (half - t) keeps bit 15 exactly when half >= t and never borrows from the other half
+    const uint2* q4 = reinterpret_cast<const uint2*>(q_s);
+    const int nw = npad >> 2;                            // multiple of 32
+    for (int bit = 12; bit >= 0; --bit) {
       const uint32_t t = res | (1u << bit);
-      int cnt = 0;
+      const uint32_t tt = t | (t << 16);
+      uint32_t ge = 0;                                   // packed counters (both halves), at most 96 * 2 each
 #pragma unroll 2
-      for (int i = lane; i < np; i += 32) {
-        const uint32_t w2 = q2[i];
-        cnt += ((w2 & 0xffffu) < t ? 1 : 0) + ((w2 >> 16) < t ? 1 : 0);
+      for (int i = lane; i < nw; i += 32) {
+        const uint2 w2 = q4[i];
+        ge += ((((w2.x | 0x80008000u) - tt) >> 15) & 0x00010001u) + ((((w2.y | 0x80008000u) - tt) >> 15) & 0x00010001u);
       }
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt < k1) res = t;
+      int cnt_ge = (int)((ge & 0xffffu) + (ge >> 16));
+      cnt_ge = __reduce_add_sync(0xffffffffu, cnt_ge);
+      if (npad - cnt_ge < k1) res = t;                   // fewer than k+1 keys below t
     }
   }
   // A = {q <= res}: at least k+1 members, compacted as positions, then mapped to rows in one parallel pass

@@ -182,3 +182,38 @@ def test_kneighbors_graph_host_arrays_and_devices():
     e2 = build_edge_list(emb, feat, depth, max_edges=100, max_node=0.9, is_combined=False, n_sample=3, devices=2)
     for a, b in zip(e1, e2):
         assert a.tobytes() == b.tobytes()
+
+
+def test_rerank_mirrors_rows_to_peer_gpu():
+    """sbk_knn_peers: the rerank kernels store every finished row into the peer GPU's full result buffer (P2P stores)
+    as well as into their own; two devices each computing one row block leave BOTH full buffers equal to the
+    single-device result.  (Skipped on a single-GPU box; bench.py --gpus N uses the same entry point under torchrun.)"""
+    import ctypes as C
+    import torch
+    if torch.cuda.device_count() < 2 or not torch.cuda.can_device_access_peer(0, 1):
+        pytest.skip('needs two GPUs with peer access')
+    from semibin_b200 import _lib
+    from semibin_b200.neighbors import knn, _workspace
+    from semibin_b200.dist import row_block
+    lib = _lib.load()
+    N, k = 120000, 50
+    X = synth.embeddings(N, seed=41)
+    d0, i0 = knn(torch.from_numpy(X).cuda(0), k)
+    full_d = [torch.zeros((N, k), dtype=torch.float32, device=f'cuda:{g}') for g in range(2)]
+    full_i = [torch.full((N, k), -1, dtype=torch.int32, device=f'cuda:{g}') for g in range(2)]
+    full_d[1].copy_(full_d[0]); full_d[0].copy_(full_d[1])      # torch enables peer access on the first cross-device copy
+    for g in range(2):
+        with torch.cuda.device(g):
+            Xg = torch.from_numpy(X).cuda(g)
+            lo, hi = row_block(N, g, 2)
+            ws = _workspace(lib.sbk_knn_workspace_bytes(_lib.SBK_F32, N, 100, hi - lo, k, 0), Xg.device)
+            pd = (C.c_void_p * 1)(full_d[1 - g].data_ptr())
+            pi = (C.c_void_p * 1)(full_i[1 - g].data_ptr())
+            st = _lib.KnnStats()
+            rc = lib.sbk_knn_peers(_lib.ptr(Xg), _lib.SBK_F32, N, 100, 100, lo, hi, k, _lib.ptr(full_d[g][lo:hi]),
+                                   _lib.ptr(full_i[g][lo:hi]), 1, pd, pi, _lib.ptr(ws), ws.numel(), 0, C.byref(st),
+                                   _lib.stream_ptr(Xg.device))
+            _lib.check(rc)
+            torch.cuda.synchronize(g)
+    for g in range(2):
+        assert torch.equal(full_d[g].cpu(), d0.cpu()) and torch.equal(full_i[g].cpu(), i0.cpu())
