@@ -132,9 +132,19 @@ class ClockSampler:
         return out
 
 
+_DATA = {'file': None, 'genome_size': 200}
+
+
 def synth_embeddings(n):
+    """The workload matrix: seeded synthetic mixture (default: genomes of ~200 contigs), a heavier-tailed mix
+    (--genome-size), or a matrix from a file (--embedding-file: e.g. synthetic k-mer features pushed through a shipped
+    SemiBin model by scripts/make_real_embeddings.py)."""
     from semibin_b200 import synth
-    return synth.embeddings(n, seed=SEED)
+    if _DATA['file']:
+        X = np.ascontiguousarray(np.load(_DATA['file'])[:n], dtype=np.float32)
+        assert X.shape[0] == n, f'{_DATA["file"]} holds {X.shape[0]} rows, --contigs {n} asked'
+        return X
+    return synth.embeddings(n, seed=SEED, mean_size=_DATA['genome_size'])
 
 
 def reference_knn_block(X, k, rows):
@@ -198,6 +208,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    # host-side barrier for the phases in which ONE process drives every GPU: an NCCL barrier would park a spinning
+    # kernel of the waiting ranks on the very GPUs rank 0 is about to use from its own context
+    cpu_group = dist.new_group(backend='gloo') if world > 1 else None
     _lib.require_cuda()
     n, k = args.n, args.k
     X_host = torch.from_numpy(synth_embeddings(n)).pin_memory()
@@ -249,6 +262,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     for _ in range(args.warmup):
         step()
     sampler = ClockSampler(local_rank)
@@ -279,6 +297,7 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     e2e_ms, g = None, None
     barrier()
+    host_barrier()
     if rank == 0:
         g = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)))     # warm-up (pins the result arrays once)
         t0 = time.perf_counter()
@@ -286,6 +305,7 @@ def run_ours(args):
             g = None        # the caller drops the previous graph: its pinned arrays go back to torch's host allocator
             g, g_stats = kneighbors_graph(X_np, k, mode='distance', p=2, devices=list(range(world)), return_stats=True)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    host_barrier()
     barrier()
     # second figure: the SPMD host-buffer call (one process per GPU, each rank its own row block)
     step_e2e()
@@ -323,7 +343,9 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
             'dtype': 'f16 tensor-core filter + f64 rerank (exact result)', 'data': 'synthetic',
             'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
-                       'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo, 'parallelism': f'row-block x{world}, references replicated', 'gather': gather_mode,
+                       'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo,
+                       'embedding': (f'file {os.path.basename(args.embedding_file)}' if args.embedding_file else
+                                     f'synthetic Gaussian mixture, lognormal genome sizes (mean {args.genome_size} contigs)'), 'parallelism': f'row-block x{world}, references replicated', 'gather': gather_mode,
                        'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
             'clocks': sampler.summary(),
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
@@ -391,7 +413,10 @@ def main():
     ap.add_argument('--algo', default='auto')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl'])
+    ap.add_argument('--embedding-file', default=None, help='.npy float32 [N, 100] matrix instead of the synthetic mixture (realism runs)')
+    ap.add_argument('--genome-size', type=int, default=200, help='mean contigs per synthetic genome (lognormal, sigma 1)')
     args = ap.parse_args()
+    _DATA['file'], _DATA['genome_size'] = args.embedding_file, args.genome_size
     if args.impl == 'reference':
         return run_reference(args)
     return run_ours(args)

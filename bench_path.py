@@ -31,7 +31,7 @@ def timed(fn, reps=1):
     return out, e0.elapsed_time(e1) / reps
 
 
-def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
+def short_read(n, S, combined, k=200, max_node=1, cpu_check=False, sklearn_graphs=False):
     import torch
     from semibin_b200 import synth, cluster
     from semibin_b200.neighbors import knn
@@ -58,8 +58,8 @@ def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
     n_edges = int(X.shape[0])
     kept_dir = n_edges * 2                       # directed edges surviving ~ 2x upper triangle
     res.update(n=n, S=S, combined=combined, k=k, d_feat=int(F.shape[1]), threshold=thr, n_edges=n_edges,
-               stats_emb={k2: st_a[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')},
-               stats_feat={k2: st_b[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols')})
+               stats_emb={k2: st_a[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols', 'n_retry_rows')},
+               stats_feat={k2: st_b[k2] for k2 in ('n_fallback_rows', 'n_candidates', 'n_reranked', 'ms_filter', 'ms_rerank', 'ms_sample', 'ms_prepare', 'ms_fallback', 'kpad', 'n_fail_overflow', 'n_fail_few', 'n_fail_survivors', 'n_fail_certificate', 'cand_capacity', 'order_stat', 'sample_size', 'n_split_cols', 'n_retry_rows')})
     b1 = n * k * (4 + 4 + 4 + 8) + n * ((k + 31) // 32) * 4
     res['stage1_GBps'] = b1 / res['stage1_ms'] / 1e6
     b2 = n * k * 8 + n * ((k + 31) // 32) * 4 + kept_dir * (12 * S if not combined else 0) + n_edges * 16 * 2
@@ -67,13 +67,29 @@ def short_read(n, S, combined, k=200, max_node=1, cpu_check=False):
     res['edge_list_total_ms'] = res['knn_emb_ms'] + res['knn_feat_ms'] + res['stage1_ms'] + res['stage2_ms']
     res['tflops_feat_filter'] = 2.0 * n * n * F.shape[1] / (st_b['ms_filter'] * 1e-3) / 1e12 if st_b['ms_filter'] else None
     if cpu_check:
-        from oracle import edges as oe, compare
+        from oracle import edges as oe, compare, knn as ok
+        if sklearn_graphs:
+            # the reference's OWN graphs: live scikit-learn kneighbors_graph on the host cores for both matrices
+            # (cluster.py:94-105), then the sparse restatement of :109-151 -- nothing of the GPU path feeds the checker
+            t0 = time.perf_counter()
+            ra_d, ra_i = ok.knn_sklearn(emb, k)
+            res['cpu_sklearn_emb_graph_s'] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            rb_d, rb_i = ok.knn_sklearn(np.ascontiguousarray(feat), k)
+            res['cpu_sklearn_feat_graph_s'] = time.perf_counter() - t0
+            res['graphs'] = 'live scikit-learn kneighbors_graph (both), %d host cores' % os.cpu_count()
+            res['knn_parity_emb'] = {kk: vv for kk, vv in compare.compare_knn(ra_d, ra_i, a_d.cpu().numpy().astype(np.float64), a_i.cpu().numpy().astype(np.int64), rtol=1e-6).items() if kk != 'bad_rows'}
+            res['knn_parity_feat'] = {kk: vv for kk, vv in compare.compare_knn(rb_d, rb_i, b_d.cpu().numpy(), b_i.cpu().numpy().astype(np.int64), rtol=1e-9).items() if kk != 'bad_rows'}
+        else:
+            ra_d, ra_i = a_d.cpu().numpy().astype(np.float64), a_i.cpu().numpy().astype(np.int64)
+            rb_d, rb_i = b_d.cpu().numpy(), b_i.cpu().numpy().astype(np.int64)
+            res['graphs'] = "the GPU's own kNN graphs (edge stages only are checked)"
         t0 = time.perf_counter()
-        RX, RY, RV, t = oe.edge_list_restated(a_d.cpu().numpy().astype(np.float64), a_i.cpu().numpy().astype(np.int64),
-                                              b_d.cpu().numpy(), b_i.cpu().numpy().astype(np.int64), depth,
-                                              max_node=max_node, is_combined=combined, n_sample=S)
+        RX, RY, RV, t = oe.edge_list_restated(ra_d, ra_i, rb_d, rb_i, depth, max_node=max_node, is_combined=combined, n_sample=S)
         res['cpu_sparse_restatement_s'] = time.perf_counter() - t0
+        res['threshold_ref'] = t
         res['parity'] = compare.compare_edges((RX, RY, RV), (X.cpu().numpy(), Y.cpu().numpy(), V.cpu().numpy()), explain=8,
+                                              rtol=0.0 if combined else 1e-5,
                                               bound_fn=None if combined else (lambda x, y: oe.kl_weight_bound(depth, S, x, y)))
     return res
 
@@ -229,11 +245,12 @@ def main():
     ap.add_argument('--n', type=int, default=0)
     ap.add_argument('--combined', action='store_true')
     ap.add_argument('--cpu-check', action='store_true')
+    ap.add_argument('--sklearn-graphs', action='store_true', help='cpu-check against live scikit-learn graphs (minutes at 200k)')
     a = ap.parse_args()
     if a.config == 'C2':
-        r = short_read(a.n or 200000, 1, False, cpu_check=a.cpu_check)
+        r = short_read(a.n or 200000, 1, False, cpu_check=a.cpu_check, sklearn_graphs=a.sklearn_graphs)
     elif a.config == 'C3':
-        r = short_read(a.n or 1000000, 10, a.combined, cpu_check=a.cpu_check)
+        r = short_read(a.n or 1000000, 10, a.combined, cpu_check=a.cpu_check, sklearn_graphs=a.sklearn_graphs)
     elif a.config == 'C4':
         r = long_read(a.n or 500000, 1, cpu_check=a.cpu_check)
     elif a.config == 'C5':

@@ -23,12 +23,12 @@ def _genome_assignment(rng, n, mean_size=200):
     return genome, n_genomes
 
 
-def embeddings(n, seed=20240, d=D_EMB, sigma=0.02, dtype=np.float32, return_genome=False):
+def embeddings(n, seed=20240, d=D_EMB, sigma=0.02, dtype=np.float32, return_genome=False, mean_size=200):
     """Gaussian mixture mimicking the contrastive embedding: genome centres
     ~ N(0, 0.16^2 I), within-genome noise sigma per dimension (intra-genome
     distance ~0.28 < 1 <= inter-genome ~2.3)."""
     rng = np.random.default_rng(seed)
-    genome, g = _genome_assignment(rng, n)
+    genome, g = _genome_assignment(rng, n, mean_size)
     centres = rng.normal(0.0, 0.16, size=(g, d)).astype(np.float32)
     x = centres[genome]
     x += rng.standard_normal(size=(n, d), dtype=np.float32) * np.float32(sigma)
