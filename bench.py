@@ -354,11 +354,13 @@ def run_ours(args):
                     'h2d_bytes_per_step': int(X_host.numel() * 4) * world,
                     'd2h_bytes_per_step': int(n * k * 16),
                     'api': "semibin_b200.neighbors.kneighbors_graph(X_numpy, 200, mode='distance', p=2) -> scipy csr_matrix "
-                           '(the call at SemiBin/cluster.py:94-99), one process driving all N GPUs (devices=N / SBK_DEVICES): pageable '
-                           'numpy matrix in, device-widened (float64, int64) row chunks downloaded into the pinned arrays of the '
+                           '(the call at SemiBin/cluster.py:94-99), one process driving all N GPUs (devices=N / SBK_DEVICES): numpy '
+                           'matrix over pinned host memory in, device-widened (float64, int64) row chunks downloaded into the pinned arrays of the '
                            'csr_matrix while the next chunk is computed',
                     'host_split_ms': {'alloc_result': g_stats['host_ms']['alloc_result'], 'build': g_stats['host_ms']['build'],
-                                      'upload': g_stats.get('upload_ms')} if rank == 0 else None,
+                                      'upload': g_stats.get('upload_ms'),
+                                      'per_device': {str(dv): {q: round(v, 2) for q, v in ds.items() if isinstance(v, float)}
+                                                     for dv, ds in g_stats.get('per_device', {}).items()}} if rank == 0 else None,
                     'spmd_host_buffers': {'value': n / (spmd_ms * 1e-3), 'ms_per_step': spmd_ms,
                                           'api': 'semibin_b200.neighbors.knn_host under torchrun (one process per GPU, (dist f32, idx i32) row '
                                                  'blocks into pinned host memory)', 'd2h_bytes_per_step': int(n * k * 8)}},

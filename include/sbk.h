@@ -54,7 +54,10 @@ typedef enum sbk_dtype { SBK_F32 = 0, SBK_F64 = 1 } sbk_dtype;
 typedef enum sbk_knn_algo {
   SBK_KNN_AUTO = 0,              /* tensor-core filter for large n, exact filter otherwise */
   SBK_KNN_EXACT = 1,             /* FP64 CUDA-core filter (also the certificate fallback) */
-  SBK_KNN_TENSOR = 2             /* tcgen05 FP16 filter + FP64 rerank with exactness certificate */
+  SBK_KNN_TENSOR = 2,            /* tcgen05 FP16 filter + FP64 rerank with exactness certificate; a build of ALL rows
+                                    (q_begin = 0, q_end = n_ref) uses the symmetric self-join filter: every tile product
+                                    serves both of its row sets, half the tensor work */
+  SBK_KNN_TENSOR_ONESIDED = 3    /* the same, but never the symmetric filter (row blocks always run one-sided) */
 } sbk_knn_algo;
 
 /* Filled (when non-NULL) after the call's work is complete; passing a non-NULL
@@ -84,7 +87,7 @@ typedef struct sbk_knn_stats {
   int64_t n_fail_survivors;      /* more survivors of the score cut than the sort buffer holds */
   int64_t n_fail_certificate;    /* (k+1)-th exact distance not below the exclusion bound */
   int32_t n_split_cols;          /* high-energy columns given an FP16 hi+lo representation */
-  int32_t reserved2;
+  int32_t symmetric;             /* 1 when the symmetric self-join filter produced the candidate lists */
   int64_t n_retry_rows;          /* rows with more survivors than the warp rerank sorts -> block-per-row rerank */
 } sbk_knn_stats;
 

@@ -12,8 +12,8 @@ PROBES = os.environ.get('SBK_LIB_VARIANT', '') == 'probe'
 LIB_PATH = os.path.join(HERE, 'libsbk_probe.so' if PROBES else 'libsbk.so')
 
 SBK_F32, SBK_F64 = 0, 1
-KNN_AUTO, KNN_EXACT, KNN_TENSOR = 0, 1, 2
-ALGOS = {'auto': KNN_AUTO, 'exact': KNN_EXACT, 'tensor': KNN_TENSOR}
+KNN_AUTO, KNN_EXACT, KNN_TENSOR, KNN_TENSOR_ONESIDED = 0, 1, 2, 3
+ALGOS = {'auto': KNN_AUTO, 'exact': KNN_EXACT, 'tensor': KNN_TENSOR, 'tensor_onesided': KNN_TENSOR_ONESIDED}
 MAX_THRESHOLDS = 32
 
 
@@ -27,7 +27,7 @@ class KnnStats(C.Structure):
                 ('ms_rerank', C.c_float), ('ms_fallback', C.c_float), ('ms_exact_filter', C.c_float),
                 ('n_reranked', C.c_int64), ('n_fail_overflow', C.c_int64), ('n_fail_few', C.c_int64),
                 ('n_fail_survivors', C.c_int64), ('n_fail_certificate', C.c_int64),
-                ('n_split_cols', C.c_int32), ('reserved2', C.c_int32), ('n_retry_rows', C.c_int64)]
+                ('n_split_cols', C.c_int32), ('symmetric', C.c_int32), ('n_retry_rows', C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -49,6 +49,7 @@ struct KnnWs {
 struct KnnShape {
   int algo; long long chunk; long long cand_stride; int n_split; long long fb_rows; int fb_split;
   int tcap; long long retry_cap;                        // warp rerank: sort capacity per row (0 = block rerank only), retry list length
+  bool sym;                                             // symmetric self-join filter (all rows in one call, lists of every row resident)
   TcPlan plan;
 };
 
@@ -64,6 +65,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
   KnnShape s; memset(&s, 0, sizeof(s));
   const int k1 = k + 1;
   if (algo == SBK_KNN_AUTO) algo = (n_ref >= TC_MIN_N && (d + 5 + 15) / 16 * 16 <= 176) ? SBK_KNN_TENSOR : SBK_KNN_EXACT;
+  const bool onesided = algo == SBK_KNN_TENSOR_ONESIDED;
+  if (onesided) algo = SBK_KNN_TENSOR;
   s.algo = algo;
   if (algo == SBK_KNN_EXACT) {
     s.chunk = std::min<long long>(std::max<long long>(n_q, 1), EXACT_CHUNK);
@@ -79,6 +82,10 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     if (n_ref / 2048 < s.fb_split) s.fb_split = (int)std::max<long long>(1, n_ref / 2048);
     while (s.fb_split > 1 && (size_t)s.fb_split * k1 * 12 > 150 * 1024) s.fb_split /= 2;
     s.tcap = rerank_warp_supported(dtype, d, k) ? rerank_warp_cap(k) : 0;
+    // a build of all rows: every tile product is used for both of its row sets (half the tensor work); the candidate
+    // lists of all rows are then live at once, so the whole call is one filter "chunk"
+    s.sym = !onesided && n_q == n_ref && s.tcap > 0 && tc_sym_supported(s.plan, n_ref);
+    if (s.sym) s.chunk = n_q;
     s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 4) : 0;
   }
   return s;
@@ -89,7 +96,7 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, i
   w.cand_idx = s.algo == SBK_KNN_TENSOR ? nullptr : a.take<uint32_t>((size_t)s.chunk * s.cand_stride);
   w.cand_pair = s.algo == SBK_KNN_TENSOR ? a.take<uint2>((size_t)s.chunk * s.cand_stride) : nullptr;
   w.cand_count = a.take<int32_t>((size_t)s.chunk * 4);
-  w.bound = a.take<double>((size_t)s.chunk);
+  w.bound = a.take<double>((size_t)s.chunk + TC_BN);     // + padding positions of the last tile (symmetric filter)
   w.fail_rows = a.take<int32_t>((size_t)n_q + (size_t)s.fb_rows + 1);     // all failing rows of the call, then the fallback's own sink
   w.n_fail = a.take<int>(64);
   w.cand_total = a.take<unsigned long long>(16);  // [0] candidates emitted, [1] reranked in FP64, [2..5] failure classes; [8..] same, retry launches
@@ -100,7 +107,7 @@ static void carve(Arena& a, const KnnShape& s, long long n_ref, long long n_q, i
   w.order_ws = a.take<char>(w.order_bytes);
   w.tc = nullptr; w.tc_bytes = 0;
   if (s.algo == SBK_KNN_TENSOR) {
-    w.tc_bytes = tc_workspace_bytes(s.plan, n_ref, s.chunk);
+    w.tc_bytes = tc_workspace_bytes(s.plan, n_ref, s.chunk, s.sym);
     w.tc = a.take<char>(w.tc_bytes);
   }
 }
@@ -179,7 +186,14 @@ extern "C" size_t sbk_knn_workspace_bytes(int dtype, int64_t n_ref, int32_t d, i
   Arena a(nullptr, 0);
   KnnWs w;
   carve(a, s, n_ref, std::min<int64_t>(n_query, n_ref), k, w);
-  return a.off + 1024;
+  size_t need = a.off;
+  if (s.sym) {                                   // the symmetric build may fall back to the one-sided one in the same workspace
+    KnnShape s1 = knn_shape(dtype, n_ref, d, n_query, k, SBK_KNN_TENSOR_ONESIDED);
+    Arena a1(nullptr, 0);
+    carve(a1, s1, n_ref, std::min<int64_t>(n_query, n_ref), k, w);
+    need = std::max(need, a1.off);
+  }
+  return need + 1024;
 }
 
 // Host sink of sbk_knn_stream / sbk_knn_graph: finished query chunks are copied to host memory on `copy_stream`
@@ -239,11 +253,11 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   const long long n_q = q_end - q_begin;
   const int k1 = k + 1;
   KnnShape s = knn_shape(dtype, n_ref, d, n_q, k, algo);
-  if (sink && sink->chunk_rows > 0)             // smaller chunks only: the workspace was sized for the default
-    s.chunk = std::min<long long>(s.chunk, std::max<long long>(256, sink->chunk_rows / 256 * 256));
   Arena a(workspace, ws_bytes);
   KnnWs w;
   carve(a, s, n_ref, n_q, k, w);
+  if (sink && sink->chunk_rows > 0)             // smaller chunks only: the workspace was sized for the default
+    s.chunk = std::min<long long>(s.chunk, std::max<long long>(256, sink->chunk_rows / 256 * 256));
   if (!a.ok() || workspace == nullptr) { set_error("knn: workspace %zu B < required %zu B", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   sbk_knn_stats st; memset(&st, 0, sizeof(st));
   st.algo_used = s.algo;
@@ -255,13 +269,30 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   TcState tcs; memset(&tcs, 0, sizeof(tcs));
   if (s.algo == SBK_KNN_TENSOR) {
     int h = tm.begin(&st.ms_prepare);
-    rc = tc_prepare(X, dtype, n_ref, d, ld, s.plan, s.chunk, w.tc, w.tc_bytes, &tcs, stream);
+    rc = tc_prepare(X, dtype, n_ref, d, ld, s.plan, s.sym ? n_q : s.chunk, w.tc, w.tc_bytes, &tcs, stream, s.sym);
     tm.end(h);
     st.n_launches += 3;
     if (rc) return rc;
     tm.on = (stats != nullptr);
     st.sample_size = s.plan.sample_size; st.cand_capacity = s.plan.cand_cap;
     st.order_stat = s.plan.order_stat; st.kpad = s.plan.kpad; st.n_split_cols = s.plan.n_split;
+    st.symmetric = s.sym ? 1 : 0;
+    if (s.sym) {
+      // thresholds of every row, then the symmetric filter over all tile pairs: the chunk loop below only reranks
+      h = tm.begin(&st.ms_sample);
+      rc = tc_sample_chunk(&tcs, s.plan, 0, n_q, w.bound, stream);
+      tm.end(h);
+      if (rc) return rc;
+      h = tm.begin(&st.ms_filter);
+      int nfl = 0, naux = 0;
+      rc = tc_filter_sym(&tcs, s.plan, k, w.cand_pair, w.cand_count, w.bound, &nfl, &naux, stream);
+      tm.end(h);
+      if (rc == TC_SYM_POOL_EXHAUSTED)             // more pair records than the pool holds (pathological hub structure): one-sided build
+        return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, SBK_KNN_TENSOR_ONESIDED,
+                        stats, stream, sink, peers);
+      if (rc) return rc;
+      st.n_filter_launches += nfl; st.n_launches += 1 + nfl + naux;
+    }
   }
 
   // The chunk loop never waits for the GPU: rows whose certificate fails are collected over the whole call
@@ -286,7 +317,9 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       st.n_launches += 2;
       if (rc) { drop_events(); return rc; }
     } else {
-      int h = tm.begin(&st.ms_sample);
+      int h = -1;
+      if (!s.sym) {
+      h = tm.begin(&st.ms_sample);
       rc = tc_sample_chunk(&tcs, s.plan, row0, cn, w.bound, stream);
       tm.end(h);
       if (rc) { drop_events(); return rc; }
@@ -301,17 +334,21 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
 #endif
       tm.end(h);
       if (rc) { drop_events(); return rc; }
+      }
+      // symmetric build: lists / thresholds / bounds are indexed by staged position (rpos: row -> position, orig: back)
+      const int32_t* row_slot = s.sym ? tcs.rpos : nullptr;
+      const int32_t* slot_rows = s.sym ? tcs.orig : nullptr;
       h = tm.begin(&st.ms_rerank);
-      if (s.tcap > 0 && !probe_block_rerank()) {
+      if (s.tcap > 0 && (s.sym || !probe_block_rerank())) {
         // warp-per-row rerank straight from the candidate lists, then the block-per-row kernel for the few rows it
         // hands back (device-side list, no host sync)
         SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
         int32_t* perm = nullptr;
         if (!probe_no_row_order()) rc = launch_row_order(X, dtype, d, ld, row0, cn, tcs.centre, w.order_ws, w.order_bytes, &perm, stream);
-        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, perm, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
+        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, row0, cn, perm, row_slot, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound, tcs.nrm, tcs.norms4,
                                 tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.retry, w.n_fail + 2, (int)s.retry_cap,
                                 w.cand_total, stream, peers);
-        if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, nullptr, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+        if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, slot_rows, row0, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
                                     w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, od, oi, row0, w.fail_rows, w.n_fail, w.cand_total + 8, stream,
                                     w.retry, w.n_fail + 2, (int)s.retry_cap, peers);
         st.n_launches += 5;

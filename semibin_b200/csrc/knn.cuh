@@ -35,7 +35,10 @@ size_t row_order_workspace_bytes(long long n_rows);
 // locality order of the chunk's query rows for the warp rerank: perm_out[i] = slot visited i-th (lives in `ws`)
 int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
                      const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream);
+// row_slot (optional): candidate lists, thresholds and bounds are indexed by row_slot[row] instead of row - q_begin
+// (the symmetric filter keeps them in staged-position order)
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows, const int32_t* perm,
+                       const int32_t* row_slot,
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
@@ -89,6 +92,12 @@ struct TcState {
   __half* a_tiles; __half* b_tiles;
   double* centre; double* colsum; double* scale; double* nrm;
   float4* norms4; TcScalars* sc; int32_t* orig; float* thr;   // orig[p] = row staged at reference position p
+  // symmetric self-join filter (queries == references): everything per staged POSITION
+  int sym;                       // A tiles staged in position order too; slots are positions
+  int32_t* rpos;                 // rpos[row] = position
+  float2* cu;                    // (c_p, u_p): ||z||^2 - sigma rounded down / up (moves a score between the two rows' frames)
+  float* t8;                     // per group of 8 positions: max of the column thresholds t_p = thr_p + u_p
+  uint2* pool; int* pool_count; int pool_chunks;   // pair records of one filter launch, in per-warp chunk streams
   unsigned long long* maxabs;
   int nstage; int cg; long long n_ref; int d;   // cg: CTAs per MMA (tcgen05 cta_group)
   long long perm_mult, perm_off, perm_minv;     // reference position p holds row (p * perm_mult + perm_off) mod n_ref
@@ -96,10 +105,18 @@ struct TcState {
 
 TcPlan tc_make_plan(long long n_ref, int d, int k);
 long long tc_chunk_rows(const TcPlan& p, long long n_ref);
-size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query);
+size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query, bool sym = false);
+// whether the symmetric self-join filter can take a build of all n_ref rows (candidate lists of every row resident at once)
+bool tc_sym_supported(const TcPlan& p, long long n_ref);
+static constexpr int TC_SYM_POOL_EXHAUSTED = 1000;   // tc_filter_sym: not an error, the caller falls back to the one-sided filter
 // Stage operands, centre/scale, sample; `chunk` = max query rows per tc_filter_chunk call.
 int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
-               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream);
+               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream, bool sym = false);
+// Symmetric self-join filter: every unordered tile pair is multiplied once and tested for both rows (see knn_tc.cu).
+// Thresholds must have been produced by tc_sample_chunk(st, p, 0, n_ref, ...) on a state prepared with sym = true;
+// cand / cand_count / bound are indexed by staged position.
+int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound,
+                  int* n_launches, int* n_aux_launches, cudaStream_t stream);
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,

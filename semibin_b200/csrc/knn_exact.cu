@@ -762,7 +762,7 @@ static constexpr size_t rw_smem_bytes(int nel) { return (size_t)RW_WARPS * ((siz
 template <typename T, int EPL, int MINB, bool VEC, bool FULL>
 __global__ void __launch_bounds__(RW_WARPS * 32, MINB)
 rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_begin, long long n_rows,
-                   const int32_t* __restrict__ perm,
+                   const int32_t* __restrict__ perm, const int32_t* __restrict__ row_slot,
                    const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
                    const float* __restrict__ thr, const double* __restrict__ bound, const double* __restrict__ nrm,
                    const float4* __restrict__ norms4, const double* __restrict__ scale, const int32_t* __restrict__ orig, int k,
@@ -784,8 +784,10 @@ rerank_warp_kernel(const T* __restrict__ X, int d, long long ld, long long q_beg
   if (widx >= n_rows) return;
   // rows are visited in the locality order of launch_row_order (neighbouring warps work on neighbouring rows of the
   // feature space: their gathers hit the same lines of L2 / L1); the lists and the outputs stay indexed by slot / row
-  const long long slot = perm ? (long long)perm[widx] : widx;
-  const long long row = q_begin + slot;
+  const long long rloc = perm ? (long long)perm[widx] : widx;
+  const long long row = q_begin + rloc;
+  // lists, thresholds and bounds are indexed by slot: the row's offset in the chunk, or (symmetric filter) its staged position
+  const long long slot = row_slot ? (long long)row_slot[row] : rloc;
   const int k1 = k + 1;
   const int seg_cap = cand_cap >> 2;
   // the four segments of the row as one list: element e lives at base[e + adj(segment of e)]
@@ -972,19 +974,20 @@ int rerank_warp_cap(int k) {          // sort capacity (power of two >= k+1 with
 
 template <typename T, int EPL, int MINB, bool VEC, bool FULL>
 static int rw_launch(unsigned grid, cudaStream_t stream, const T* X, int d, long long ld, long long q_begin, long long n_rows,
-                     const int32_t* perm,
+                     const int32_t* perm, const int32_t* row_slot,
                      const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                      const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                      T* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
                      int32_t* retry_slots, int* n_retry, int retry_cap, unsigned long long* totals, const PeerOut& peers) {
   const size_t smem = rw_smem_bytes(32 * EPL);
   SBK_CUDA_CHECK(cudaFuncSetAttribute(rerank_warp_kernel<T, EPL, MINB, VEC, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rerank_warp_kernel<T, EPL, MINB, VEC, FULL><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, perm, cand, cand_count, cand_cap,
+  rerank_warp_kernel<T, EPL, MINB, VEC, FULL><<<grid, RW_WARPS * 32, smem, stream>>>(X, d, ld, q_begin, n_rows, perm, row_slot, cand, cand_count, cand_cap,
       thr, bound, nrm, norms4, scale, orig, k, out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, peers);
   return SBK_OK;
 }
 
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows, const int32_t* perm,
+                       const int32_t* row_slot,
                        const uint2* cand, const int32_t* cand_count, int cand_cap, const float* thr, const double* bound,
                        const double* nrm, const float4* norms4, const double* scale, const int32_t* orig, int k,
                        void* out_dist, int32_t* out_idx, long long out_row0, int32_t* fail_rows, int* n_fail,
@@ -1004,7 +1007,7 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
   // 2 CTAs (16 warps) per SM at up to 128 registers by default; the probe build can ask for 3 CTAs at 80 registers
   static const int occ = rw_env_int("SBK_RW_OCC", 2);
   int rc = SBK_OK;
-#define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, perm, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
+#define SBK_RW_ARGS(T) grid, stream, (const T*)X, d, ld, q_begin, n_rows, perm, row_slot, cand, cand_count, cand_cap, thr, bound, nrm, norms4, scale, orig, k, \
       (T*)out_dist, out_idx, out_row0, fail_rows, n_fail, retry_slots, n_retry, retry_cap, totals, po
 #define SBK_RW_LAUNCH2(T, EPL, MINB)                                                                                    \
   do {                                                                                                                  \

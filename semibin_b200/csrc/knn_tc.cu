@@ -43,6 +43,7 @@
 #include "knn.cuh"
 #include <math.h>
 #include <algorithm>
+#include <vector>
 #include <string.h>
 #include <stdlib.h>
 
@@ -67,7 +68,12 @@ enum TcMode { TC_SAMPLE = 0, TC_FILTER = 1, TC_DUMP = 2,
               // profiling aids (SBK_TC_PROBE=3|4 replaces the filter pass; results are then meaningless):
               TC_PROBE_NOLD = 3,      // epilogue releases the accumulator without reading it: MMA + operand pipeline alone
               TC_PROBE_LDONLY = 4,    // epilogue reads the accumulator (tcgen05.ld) and discards it
-              TC_PROBE_NOAPPEND = 5 };// filter epilogue without the candidate append (min tree + threshold test only)
+              TC_PROBE_NOAPPEND = 5,  // filter epilogue without the candidate append (min tree + threshold test only)
+              TC_FILTER_SYM = 6 };    // symmetric self-join filter: row test AND column test on every tile (see tc_kernel)
+// symmetric filter: ring of per-tile column thresholds, one slot = 256 column thresholds t_j + their 32 group-of-8 maxima
+static constexpr int TC_T8_SLOTS = 10;          // > nstage + 3 (see tc_kernel)
+static constexpr int TC_TT_FLOATS = TC_BN + TC_BN / 8;          // floats per tile (288 = 1152 B)
+static constexpr int TC_POOL_CH = 1024;                         // pair records per pool chunk (+ one header entry)
 
 // bytes of the reference-tile ring; at least the SAMPLE epilogue's scratch
 // ([TC_BM][TC_NGROUP + 1] floats) which reuses it once the pipeline has drained
@@ -115,35 +121,43 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {     
 // block (try_wait, branch, counter): a waiting warp is woken by every barrier event of the CTA, so the
 // instructions per wake-up are what the waiters cost the working warps in issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t timed_out;
-  // four try_waits per turn of the (bounded) counter: a wake-up costs four instructions instead of seven
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " .reg .u32 n;\n"
-      " mov.u32 n, 0;\n"
-      "WAIT_%=:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      " @p bra DONE_%=;\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      " @p bra DONE_%=;\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      " @p bra DONE_%=;\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      " @p bra DONE_%=;\n"
-      " add.u32 n, n, 1;\n"
-      " setp.lt.u32 p, n, 0x800000;\n"
-      " @p bra WAIT_%=;\n"
-      " mov.u32 %0, 1;\n"
-      " bra END_%=;\n"
-      "DONE_%=:\n"
-      " mov.u32 %0, 0;\n"
-      "END_%=:\n"
-      "}"
-      : "=r"(timed_out) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
-  if (timed_out) {
-    printf("sbk: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-    __trap();
+  // four try_waits per turn of the counter: a wake-up costs four instructions instead of seven.  When the counter
+  // runs out the wall clock decides: four seconds without progress is a protocol bug -> trap.
+  unsigned long long t0 = 0;
+  for (;;) {
+    uint32_t timed_out;
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " .reg .u32 n;\n"
+        " mov.u32 n, 0;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " @p bra DONE_%=;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " @p bra DONE_%=;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " @p bra DONE_%=;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        " @p bra DONE_%=;\n"
+        " add.u32 n, n, 1;\n"
+        " setp.lt.u32 p, n, 0x1000;\n"
+        " @p bra WAIT_%=;\n"
+        " mov.u32 %0, 1;\n"
+        " bra END_%=;\n"
+        "DONE_%=:\n"
+        " mov.u32 %0, 0;\n"
+        "END_%=:\n"
+        "}"
+        : "=r"(timed_out) : "r"(smem_u32(bar)), "r"(parity), "r"(100000u) : "memory");
+    if (!timed_out) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) {
+      printf("sbk: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -292,7 +306,7 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld, long 
                 const double* __restrict__ centre, const double* __restrict__ scale, int kpad, int brows,
                 __half* __restrict__ b_tiles, __half* __restrict__ a_tiles, int32_t* __restrict__ orig,
                 double* __restrict__ nrm, float4* __restrict__ norms4,
-                const TcScalars* __restrict__ sc) {
+                const TcScalars* __restrict__ sc, int a_by_pos, int32_t* __restrict__ rpos, float2* __restrict__ cu) {
   const long long row = (long long)blockIdx.x * 128 + threadIdx.x;
   if (row >= n_staged) return;
   const bool real = row < n;
@@ -305,7 +319,9 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld, long 
   orig[pos] = real ? (int32_t)row : 0x7fffffff;
   const long long bt = pos / brows, br = pos % brows;       // brows = reference rows per staged tile (256, or 128 for CTA pairs)
   __half* bdst = b_tiles + bt * (long long)brows * kpad + br * 8;
-  const long long at = row / TC_BM, ar = row % TC_BM;
+  // query-side tiles: in row order, or (symmetric self-join) in the same position order as the reference side
+  const long long apos = a_by_pos ? pos : row;
+  const long long at = apos / TC_BM, ar = apos % TC_BM;
   __half* adst = a_tiles + at * (long long)TC_BM * kpad + ar * 8;
   const long long src = row;
   const double S = scale[0];
@@ -395,7 +411,12 @@ tc_stage_kernel(const T* __restrict__ X, long long n, int d, long long ld, long 
   if (real) {
     nrm[row] = n2;
     norms4[row] = make_float4(nz, nd, na, l2f);
+    if (rpos) rpos[row] = (int32_t)pos;
   }
+  // (c, u) = ||z||^2 - sigma rounded down / up: L_ij + c_i <= S^2 d2_ij, and a lower bound of S^2 d2 minus u_j is a
+  // lower bound in row j's frame (e_ji + sigma_j).  Padding positions: c = +inf (never a column hit), u = 0.
+  if (cu) cu[pos] = real ? make_float2(__double2float_rd((n2 - (double)l2f) - 1e-12 * n2), __double2float_ru((n2 - (double)l2f) + 1e-12 * n2))
+                         : make_float2(INFINITY, 0.f);
 }
 
 // Threshold and certificate bound of one query row from tau, an upper bound (with the planned confidence) of the
@@ -436,7 +457,7 @@ __global__ void __launch_bounds__(256)
 tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ cand_count, int cand_cap,
                  long long row_lo, long long n_rows, int r_stat,
                  const float4* __restrict__ norms4, const double* __restrict__ nrm, const double* __restrict__ scale,
-                 int kpad, int d, float* __restrict__ thr, double* __restrict__ bound) {
+                 int kpad, int d, float* __restrict__ thr, double* __restrict__ bound, const int32_t* __restrict__ slot_row) {
   const long long slot = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (slot >= n_rows) return;
@@ -468,10 +489,125 @@ tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ can
     if (cnt < r_stat) res = t;
   }
   if (lane == 0) {
-    const long long grow = row_lo + slot;
+    const long long grow = slot_row ? (long long)slot_row[slot] : row_lo + slot;
     float thr_new; double bound_new;
     tc_threshold(tc_ord2f(res), norms4[grow], nrm[grow], kpad, d, scale[0], &thr_new, &bound_new);
     if (thr_new < thr[slot]) { thr[slot] = thr_new; bound[slot] = bound_new; }
+  }
+}
+
+// ---- symmetric self-join filter: helpers ----
+// Column thresholds: t_p = thr_p + u_p (rounded up) >= thr_p - sigma_p + ||z_p||^2, per tile of 256 positions followed by
+// the maxima of its 32 groups of 8 (padding positions: -inf).  Rerun after every threshold refinement.
+__global__ void __launch_bounds__(256)
+tc_colthr_kernel(const float* __restrict__ thr, const float2* __restrict__ cu, long long n, float* __restrict__ tt) {
+  const long long pp = (long long)blockIdx.x * TC_BN + threadIdx.x;
+  float t = -INFINITY;
+  if (pp < n) t = __fadd_ru(thr[pp], cu[pp].y);
+  float* dst = tt + (long long)blockIdx.x * TC_TT_FLOATS;
+  dst[threadIdx.x] = t;
+  float m = t;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 7) == 0) dst[TC_BN + (threadIdx.x >> 3)] = m;
+}
+
+// Symmetric filter: the 256 positions of every tile are re-ordered by descending column threshold (known after the
+// sample pass), so that the 8 columns of a group share nearly the same threshold and the group pre-test of the filter
+// epilogue stays tight whatever the spread of neighbourhood sizes in the data.  Tile membership is unchanged (the
+// sample is still the first tiles, windows of tiles are still unbiased); both operand tiles and every per-position
+// array are permuted in place through shared memory.  One CTA of 256 threads per tile.
+__global__ void __launch_bounds__(256)
+tc_sort_tiles_kernel(long long n, int kpad, __half* __restrict__ a_tiles, __half* __restrict__ b_tiles,
+                     float* __restrict__ thr, double* __restrict__ bound, float2* __restrict__ cu,
+                     int32_t* __restrict__ orig, int32_t* __restrict__ rpos) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  __shared__ float s_key[TC_BN];
+  __shared__ int s_src[TC_BN];                     // s_src[r] = old local index of the position that moves to rank r
+  const int tid = threadIdx.x;
+  const long long base = (long long)blockIdx.x * TC_BN;
+  const long long pp = base + tid;
+  const float my_thr = thr[pp];                    // thr / bound / cu / orig are allocated for the padded tiles
+  const double my_bound = bound[pp];
+  const float2 my_cu = cu[pp];
+  const int32_t my_orig = orig[pp];
+  const float key = pp < n ? __fadd_ru(my_thr, my_cu.y) : -INFINITY;
+  s_key[tid] = key;
+  __syncthreads();
+  // rank by (key descending, index ascending): 256 comparisons per thread
+  int rank = 0;
+  for (int o = 0; o < TC_BN; ++o) { const float ko = s_key[o]; rank += (ko > key || (ko == key && o < tid)) ? 1 : 0; }
+  // Groups of 8 consecutive ranks stay together, but the groups are dealt round-robin to the four 64-column quarters
+  // of the tile: a row's candidates (rows of similar threshold) keep spreading evenly over its four list segments,
+  // which belong to the quarters.  The last, partly padded tile keeps the plain order (its real positions must stay
+  // in front of the padding).
+  if (base + TC_BN <= n) { const int gi = rank >> 3; rank = (gi & 3) * 64 + (gi >> 2) * 8 + (rank & 7); }
+  s_src[rank] = tid;
+  thr[base + rank] = my_thr; bound[base + rank] = my_bound; cu[base + rank] = my_cu; orig[base + rank] = my_orig;
+  if (my_orig != 0x7fffffff) rpos[my_orig] = (int32_t)(base + rank);
+  __syncthreads();
+  // operand tiles: two half tiles of 128 rows, layout [kpad/8 chunks][128 rows][8 halves]; 16-byte pieces
+  const int nchunk = kpad / 8;
+  uint4* buf = reinterpret_cast<uint4*>(sort_smem);             // [nchunk][256] pieces of the whole tile
+  for (int side = 0; side < 2; ++side) {
+    uint4* g = reinterpret_cast<uint4*>((side ? b_tiles : a_tiles) + base * kpad);
+    for (int e = tid; e < nchunk * TC_BN; e += 256) {
+      const int half = e / (nchunk * 128), rem = e % (nchunk * 128);          // global piece order: [half][chunk][row]
+      const int ch = rem / 128, row = rem % 128;
+      buf[ch * TC_BN + half * 128 + row] = g[e];
+    }
+    __syncthreads();
+    for (int e = tid; e < nchunk * TC_BN; e += 256) {
+      const int half = e / (nchunk * 128), rem = e % (nchunk * 128);
+      const int ch = rem / 128, row = rem % 128;
+      g[e] = buf[ch * TC_BN + s_src[half * 128 + row]];
+    }
+    __syncthreads();
+  }
+}
+
+// Symmetric filter, after every launch: the PAIR records of the launch sit in pool chunks, one stream per epilogue warp
+// (header = first position of the warp's 32 rows, record count).  A record (lane, j, s) of the warp whose rows start at
+// position r0 says: for i = r0 + lane, s <= S^2 d2_ij is a lower bound of the scaled squared distance, and
+// s <= max(t_i, T8(j)) held in the kernel.  It is resolved here for both of its rows:
+//   row i receives candidate (j, s - u_i) iff s <= t_i   (a lower bound in i's frame: e_ij + sigma_i);
+//   row j receives candidate (i, s - u_j) iff s <= t_j and the pair's tile was column-tested (not the diagonal tile, nor
+//   the opposite tile of an even tile count, which hold both orders of their pairs themselves).
+// Candidates are appended to one of the row's four segments with an atomic counter; a count beyond the segment
+// capacity is the overflow mark the rerank already understands.  One warp per chunk.
+__global__ void __launch_bounds__(256)
+tc_transpose_kernel(const uint2* __restrict__ pool, const int* __restrict__ pool_count, int pool_chunks,
+                    long long n, long long n_tiles, const float* __restrict__ thr, const float2* __restrict__ cu,
+                    uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
+                    unsigned long long* __restrict__ dbg) {
+  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ch >= min(*pool_count, pool_chunks)) return;
+  const uint2* src = pool + (long long)ch * (TC_POOL_CH + 1);
+  const uint2 hdr = src[0];
+  const long long r0 = hdr.x;
+  const int cnt = min((int)hdr.y, TC_POOL_CH);
+  const int seg_cap = cand_cap >> 2;
+  if (dbg && lane == 0) atomicAdd(&dbg[2], (unsigned long long)cnt);
+  for (int e = lane; e < cnt; e += 32) {
+    const uint2 rec = src[1 + e];
+    const long long i = r0 + (rec.x >> 27), j = rec.x & 0x7ffffffu;
+    const float sv = __uint_as_float(rec.y);
+    const float2 cui = cu[i];
+    const int ts = e & 3;
+    if (sv <= __fadd_ru(thr[i], cui.y)) {
+      const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
+      if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, cui.y)));
+      else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+    }
+    long long dt = j / TC_BN - i / TC_BN; if (dt < 0) dt = -dt;
+    if (dt == 0 || dt * 2 == n_tiles) continue;                // row-tested only: the pair appears in both orders already
+    const float2 cuj = cu[j];
+    if (sv <= __fadd_ru(thr[j], cuj.y)) {
+      const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
+      if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, cuj.y)));
+      else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+    }
   }
 }
 
@@ -495,6 +631,14 @@ struct TcArgs {
   uint2* cand; int32_t* cand_count; int cand_cap;   // (column, score) pairs: 4 segments of cand_cap/4 per row
   // DUMP
   float* dump; long long dump_ld; const int32_t* orig;
+  // slots -> rows (NULL: slot s of the launch is row row_lo + s); set when the query side is staged in position order
+  const int32_t* slot_row;
+  // FILTER_SYM: bt0 / n_btiles are the first circulant step and the number of steps of this launch; the CTA pair of
+  // query tile I multiplies reference tiles (I + step) mod n_tiles_total
+  long long n_tiles_total;
+  const float* t8;            // [n_tiles_total * 32] group maxima of the column thresholds
+  const float2* cu;           // [positions] (c, u)
+  uint2* pool; int* pool_count; int pool_chunks; int* pool_fail;    // pair-record pool (chunks of TC_POOL_CH + 1)
 };
 
 template <int CG> __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -543,6 +687,11 @@ tc_kernel(const TcArgs p) {
   uint64_t* tempty_bar = tfull_bar + 4;                            // [4]  (CG = 2: the leader's are used)
   uint64_t* a_bar = tempty_bar + 4;                                // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_bar + 1);
+  // FILTER_SYM: ring of the reference tiles' column thresholds (256 t_j + 32 group maxima per tile), filled by the
+  // producer with the tile itself.  A slot is rewritten TC_T8_SLOTS tiles later: the producer runs at most nstage <= 6
+  // tiles ahead of the retired MMAs and an MMA is only issued once every epilogue warp has finished the tile three
+  // before it, so by then nobody reads the slot any more.
+  float* t8ring = reinterpret_cast<float*>(tail + 256);            // [TC_T8_SLOTS][TC_TT_FLOATS]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -572,12 +721,18 @@ tc_kernel(const TcArgs p) {
   if (CG == 2) cluster_sync_all(); else __syncthreads();           // barriers (of both CTAs) are initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Register budget by role (setmaxnreg, per warpgroup of 4 warps): the producer / MMA / TMEM warpgroup gives registers
+  // back, the four epilogue warpgroups take them: the symmetric epilogue keeps 64 accumulator values per thread live
+  // next to two candidate lists and spilled at the kernel-wide 96.
+  // (each setmaxnreg sits at the head of its role's branch below, so the compiler sees which budget applies where)
 
   // Producer and MMA warps run their loops with all 32 lanes converged (waits included) and elect one lane
   // only for the asynchronous instructions: everything stays warp-uniform, so the descriptors live in
   // uniform registers and the issue sequence per tile is a few dozen instructions.  (With the loop under
   // `if (lane == 0)` the compiler wrapped every tcgen05.mma in an election loop: ~170 dependent
   // instructions per tile, and the MMA warp spent 85 % of its time issuing instead of waiting.)
+  if (warp >= TC_EPI_WARPS) {
+  if (MODE == TC_FILTER_SYM) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
   if (warp == TC_WARP_TMA) {
     // ===== producer: own A tile once, then the ring of reference (half) tiles =====
     if (elect_one()) {
@@ -585,17 +740,25 @@ tc_kernel(const TcArgs p) {
       bulk_g2s(sA, p.a_tiles + tile_m * (long long)TC_BM * kpad, a_bytes, a_bar);
     }
     __syncwarp();
-    const __half* src = p.b_tiles + (CG * p.bt0 + cta_rank) * (long long)BROWS * kpad;
     const long long src_step = (long long)CG * BROWS * kpad;
+    // FILTER_SYM: the pair of query tile I starts at reference tile (I + first step) mod T and wraps around
+    long long jt = MODE == TC_FILTER_SYM ? ((tile_m >> 1) + p.bt0) % p.n_tiles_total : p.bt0;
+    const __half* src = p.b_tiles + (CG * jt + cta_rank) * (long long)BROWS * kpad;
     int stage = 0; uint32_t phase = 0;
+    int tslot = 0;
     for (long long t = 0; t < n_tiles; ++t) {
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&full_bar[stage], b_bytes);
+        mbar_expect_tx(&full_bar[stage], b_bytes + (MODE == TC_FILTER_SYM ? (uint32_t)(TC_TT_FLOATS * 4) : 0u));
         bulk_g2s(sB + (size_t)stage * b_bytes, src, b_bytes, &full_bar[stage]);
+        if (MODE == TC_FILTER_SYM) bulk_g2s(t8ring + tslot * TC_TT_FLOATS, p.t8 + jt * TC_TT_FLOATS, (uint32_t)(TC_TT_FLOATS * 4), &full_bar[stage]);
       }
       __syncwarp();
       src += src_step;
+      if (MODE == TC_FILTER_SYM) {
+        if (++jt == p.n_tiles_total) { jt = 0; src = p.b_tiles + (long long)cta_rank * BROWS * kpad; }
+        if (++tslot == TC_T8_SLOTS) tslot = 0;
+      }
       if (++stage == p.nstage) { stage = 0; phase ^= 1; }
     }
   } else if (warp == TC_WARP_MMA) {
@@ -643,8 +806,10 @@ tc_kernel(const TcArgs p) {
         if (++stage == p.nstage) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp < TC_EPI_WARPS) {
+  }
+  } else {
     // ===== epilogue =====
+    if (MODE == TC_FILTER_SYM) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     const int w4 = warp >> 2;                    // which 64-column quarter of the 256-wide tile
     const int r_in_tile = q * 32 + lane;
@@ -663,12 +828,42 @@ tc_kernel(const TcArgs p) {
     int cnt = 0;                                                // candidates in the segment so far
     const int cnt_lim = seg_cap - 32;                           // a 32-column chunk is appended only if it fits entirely
     bool overflow = false;
+    if (MODE == TC_FILTER_SYM && row_ok) thr = p.thr[slot];
     if ((MODE == TC_FILTER || MODE == TC_PROBE_NOAPPEND) && row_ok) {
       thr = p.thr[slot];
       seg = p.cand + slot * (long long)p.cand_cap + (long long)w4 * seg_cap;
       if (p.bt0 > 0) cnt = p.cand_count[slot * 4 + w4];         // continue the segment of the earlier reference chunks
       overflow = cnt > seg_cap;
       cnt = min(cnt, seg_cap);
+    }
+    // FILTER_SYM: one PAIR record (lane, j, s) per passing element, s = L_ij + c_i <= S^2 d2_ij; it passes when
+    // s <= max(t_i, T8(group of j)), i.e. when row i OR (possibly) row j wants the pair.  The records of a warp form one
+    // stream in chunks of a global pool (a new chunk costs one atomic per TC_POOL_CH records); nothing per row is kept
+    // in the kernel, so a row that is a candidate of thousands of others costs nothing special.  tc_transpose_kernel
+    // hands the records to the candidate lists of both rows after the launch.
+    float cadd = INFINITY;                                      // c_i: L_ij + c_i <= S^2 d2_ij
+    float trow = -INFINITY;                                     // t_i = thr_i + u_i >= thr_i - sigma_i + ||z_i||^2
+    int jt_sym = 0, tslot = 0;
+    uint2* chunk = nullptr;                                     // warp-uniform: the warp's current pool chunk ...
+    int wcnt = 0;                                               // ... and the records in it
+    auto close_chunk = [&]() {
+      if (lane == 0) chunk[0] = make_uint2((uint32_t)(tile_m * TC_BM + q * 32), (uint32_t)wcnt);
+    };
+    auto new_chunk = [&]() {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(p.pool_count, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if (c >= p.pool_chunks) { c = p.pool_chunks - 1; if (lane == 0) *p.pool_fail = 1; }   // pool exhausted: the host redoes the build one-sided
+      chunk = p.pool + (long long)c * (TC_POOL_CH + 1);
+      wcnt = 0;
+    };
+    if (MODE == TC_FILTER_SYM) {
+      if (row_ok) {
+        const float2 cui = p.cu[slot];
+        cadd = cui.x; trow = __fadd_ru(thr, cui.y);
+      }
+      jt_sym = (int)(((tile_m >> 1) + p.bt0) % p.n_tiles_total);
+      new_chunk();
     }
     int probe_hits = 0;
     constexpr int WC = SN / 4;                   // columns of one accumulator stage this warp owns: 64 (NH = 1) or 32
@@ -697,6 +892,75 @@ tc_kernel(const TcArgs p) {
         continue;
       }
       uint32_t va[32], vb[NCHK == 2 ? 32 : 1];
+      if constexpr (MODE == TC_FILTER_SYM && NH == 1 && CG == 2) {
+        // ---- symmetric self-join: tile (I, J) serves the rows of I (row test, as FILTER) AND the rows of J: column j
+        // gets row i as a candidate iff  L_ij + c_i <= t_j  (both sides are lower / upper bounds of S^2 d2_ij and of
+        // thr_j - sigma_j + ||z_j||^2, so whatever is not emitted has d2 > bound_j).  The group minimum is tested first
+        // against the largest t_j of the group of 8 columns: one add and one compare per group; the positions of a
+        // tile are sorted by threshold (tc_sort_tiles_kernel), so that maximum is close to every t_j of its group.
+        const int step = (int)p.bt0 + (int)t;
+        const int jt = jt_sym;
+        if (++jt_sym == (int)p.n_tiles_total) jt_sym = 0;
+        // the diagonal tile holds both orders of every pair already; for an even tile count the opposite tile is
+        // multiplied by both of its pairs: row test only in either case
+        const bool col_on = step > 0 && step * 2 != (int)p.n_tiles_total;
+        tmem_ld32(taddr, va);
+        tmem_ld32(taddr + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
+        const float* tt = t8ring + tslot * TC_TT_FLOATS;          // [256 column thresholds][32 group maxima]
+        if (++tslot == TC_T8_SLOTS) tslot = 0;
+        // group minima (three-input min instructions), then one bit per group of 8 columns: "some column of the group
+        // may pass": the group's minimum against max(t_i, largest t_j of the group)
+        uint32_t lm = 0;
+        float tmx[8];
+        {
+          const float4 tq0 = *reinterpret_cast<const float4*>(tt + TC_BN + w4 * 8);       // warp-uniform (broadcast) reads
+          const float4 tq1 = *reinterpret_cast<const float4*>(tt + TC_BN + w4 * 8 + 4);
+          const float tg[8] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w};
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const uint32_t* v = g < 4 ? va + 8 * g : vb + 8 * (g - 4);
+            const float a0 = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+            const float a1 = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+            const float m = fminf(fminf(a0, a1), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+            tmx[g] = col_on ? fmaxf(trow, tg[g]) : trow;
+            lm |= (__fadd_rd(m, cadd) <= tmx[g]) ? (1u << g) : 0u;
+          }
+        }
+        // The walk is ONE copy of the 8-column code, run for every group some lane flagged (warp-uniform loop; the
+        // group's registers are selected by a uniform switch).  Unrolled per group the epilogue was 4000 instructions
+        // and the warps spent their time on instruction-cache misses (ncu: 19 no-instruction stalls per issue).
+        uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
+        const uint32_t jbase = (uint32_t)jt * (uint32_t)TC_BN + (uint32_t)(w4 * 64);
+        while (wm) {
+          const int g = __ffs(wm) - 1;
+          wm &= wm - 1;
+          uint32_t w[8]; float tm;
+          switch (g) {
+#define SBK_PICK(G, SRC, OFF) case G: tm = tmx[G]; _Pragma("unroll") for (int c = 0; c < 8; ++c) w[c] = SRC[OFF + c]; break;
+            SBK_PICK(0, va, 0) SBK_PICK(1, va, 8) SBK_PICK(2, va, 16) SBK_PICK(3, va, 24)
+            SBK_PICK(4, vb, 0) SBK_PICK(5, vb, 8) SBK_PICK(6, vb, 16)
+            default: tm = tmx[7]; _Pragma("unroll") for (int c = 0; c < 8; ++c) w[c] = vb[24 + c]; break;
+#undef SBK_PICK
+          }
+          const uint32_t jj = jbase + 8u * (uint32_t)g + ((uint32_t)lane << 27);
+          if (wcnt > TC_POOL_CH - 256) { close_chunk(); new_chunk(); }      // a group appends at most 8 x 32 records
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float sv = __fadd_rd(__uint_as_float(w[c]), cadd);
+            const bool ps = sv <= tm;
+            const uint32_t bal = __ballot_sync(0xffffffffu, ps);
+            if (bal) {
+              if (ps) chunk[1 + wcnt + __popc(bal & ((1u << lane) - 1u))] = make_uint2(jj + c, __float_as_uint(sv));
+              wcnt += __popc(bal);
+            }
+          }
+        }
+        continue;
+      }
       if (MODE == TC_FILTER || MODE == TC_PROBE_NOAPPEND) {
         // The warp's columns go to registers and the accumulator stage is released BEFORE any of it is
         // reduced: the MMA issuer waits for the slowest of the pair's 32 epilogue warps, so whatever a warp
@@ -789,9 +1053,10 @@ tc_kernel(const TcArgs p) {
     }
 
     // ---- per-row results ----
-    if (MODE == TC_FILTER) {
+    if (MODE == TC_FILTER || MODE == TC_FILTER_SYM) {
       // a count above the segment capacity marks the segment as overflowed (the rerank sends the row to the exact filter)
-      if (row_ok) p.cand_count[slot * 4 + w4] = overflow ? seg_cap + 1 : cnt;
+      if (MODE == TC_FILTER && row_ok) p.cand_count[slot * 4 + w4] = overflow ? seg_cap + 1 : cnt;
+      if (MODE == TC_FILTER_SYM) close_chunk();
     }
     if ((MODE == TC_PROBE_NOAPPEND || MODE == TC_PROBE_LDONLY) && row_ok && probe_hits == 0x7fffffff) p.cand_count[slot * 4 + w4] = 1;
     if (MODE == TC_SAMPLE) {
@@ -823,7 +1088,8 @@ tc_kernel(const TcArgs p) {
         }
         if (lane == 0) {
           float thr_f; double bound_f;
-          tc_threshold(tc_ord2f(res), p.norms4[grow_sel], p.nrm[grow_sel], kpad, p.d, p.scale[0], &thr_f, &bound_f);
+          const long long rid = p.slot_row ? (long long)p.slot_row[grow_sel] : grow_sel;
+          tc_threshold(tc_ord2f(res), p.norms4[rid], p.nrm[rid], kpad, p.d, p.scale[0], &thr_f, &bound_f);
           p.thr[grow_sel - p.row_lo] = thr_f;
           p.bound[grow_sel - p.row_lo] = bound_f;
         }
@@ -908,7 +1174,20 @@ long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
   return std::min<long long>(rows, 1 << 20);
 }
 
-static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk, TcState* st) {
+// chunks of the pair-record pool: one partly filled chunk per epilogue warp of a launch (2T CTAs x 16 warps) plus the
+// records of the busiest launch (about a quarter of all candidates; sized for 4x the planned list volume)
+static int tc_pool_chunks(const TcPlan& p, long long n_ref) {
+  const double recs = (double)n_ref * (double)p.cand_cap / 4.0;
+  const double c = 32.0 * (double)p.n_tiles + recs / TC_POOL_CH + 1024.0;
+  return (int)std::min(c, 4.0e6);
+}
+static constexpr double TC_SYM_MAX_BYTES = 64e9;    // candidate lists + outboxes of all rows must be resident at once
+bool tc_sym_supported(const TcPlan& p, long long n_ref) {
+  return TC_DEFAULT_CG == 2 && TC_DEFAULT_NH == 1 && p.n_tiles >= 8 &&
+         (double)n_ref * (double)p.cand_cap * 8.0 <= TC_SYM_MAX_BYTES;
+}
+
+static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk, TcState* st, bool sym) {
   const long long n_a = (n_ref + TC_BM - 1) / TC_BM * TC_BM;
   const long long n_b = p.n_tiles * TC_BN;
   (void)n_a;   // A tiles are staged by the same kernel that walks the n_b padded rows
@@ -921,19 +1200,30 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
   st->norms4 = a.take<float4>((size_t)n_b);
   st->sc = a.take<TcScalars>(2);
   st->orig = a.take<int32_t>((size_t)n_b);
-  st->thr = a.take<float>((size_t)chunk + TC_BM);
+  st->thr = a.take<float>((size_t)chunk + TC_BN);        // + padding positions of the last tile (symmetric filter)
   st->maxabs = a.take<unsigned long long>(8);
+  st->sym = sym ? 1 : 0;
+  st->rpos = nullptr; st->cu = nullptr; st->t8 = nullptr; st->pool = nullptr; st->pool_count = nullptr; st->pool_chunks = 0;
+  if (sym) {
+    st->rpos = a.take<int32_t>((size_t)n_b);
+    st->cu = a.take<float2>((size_t)n_b);
+    st->t8 = a.take<float>((size_t)p.n_tiles * TC_TT_FLOATS);
+    st->pool_chunks = tc_pool_chunks(p, n_ref);
+    st->pool = a.take<uint2>((size_t)st->pool_chunks * (TC_POOL_CH + 1));
+    st->pool_count = a.take<int>(64);                    // [0] chunks handed out, [1] pool exhausted
+  }
 }
 
-size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query) {
+size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query, bool sym) {
   Arena a(nullptr, 0);
   TcState st;
-  tc_carve(a, p, n_ref, n_query, &st);
+  tc_carve(a, p, n_ref, n_query, &st, sym);
   return a.off + 1024;
 }
 
 static size_t tc_smem_bytes(int kpad, int nstage, int cg) {
-  return (size_t)TC_BM * kpad * 2 + tc_ring_bytes(kpad, nstage, cg) + 256 /* barriers, TMEM slot */ + 64;
+  return (size_t)TC_BM * kpad * 2 + tc_ring_bytes(kpad, nstage, cg) + 256 /* barriers, TMEM slot */ +
+         TC_T8_SLOTS * TC_TT_FLOATS * 4 /* column-threshold ring of the symmetric filter */ + 64;
 }
 
 static int tc_pick_stages(int kpad, int cg) {
@@ -975,13 +1265,13 @@ static long long mod_inverse(long long a, long long n) {
 }
 
 int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,
-               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream) {
+               long long chunk, void* ws, size_t ws_bytes, TcState* st, cudaStream_t stream, bool sym) {
   if ((d + 5 + 15) / 16 * 16 > TC_MAX_KPAD || d > 4096) {
     set_error("tensor kNN path supports feature width <= %d (got %d); use SBK_KNN_EXACT", TC_MAX_KPAD - 5, d);
     return SBK_ERR_INVALID;
   }
   Arena a(ws, ws_bytes);
-  tc_carve(a, p, n_ref, chunk, st);
+  tc_carve(a, p, n_ref, chunk, st, sym);
   if (!a.ok()) { set_error("tensor kNN: staging workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   st->n_ref = n_ref; st->d = d;
   SBK_CUDA_CHECK(cudaMemsetAsync(st->colsum, 0, 2 * 4096 * sizeof(double), stream));
@@ -1015,11 +1305,14 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
   const unsigned sb = (unsigned)((n_b + 127) / 128);
   if (dtype == SBK_F32)
     tc_stage_kernel<float><<<sb, 128, 0, stream>>>((const float*)X, n_ref, d, ld, n_b, st->perm_minv, st->perm_off, st->centre, st->scale,
-                                                   p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc);
+                                                   p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc,
+                                                   st->sym, st->rpos, st->cu);
   else
     tc_stage_kernel<double><<<sb, 128, 0, stream>>>((const double*)X, n_ref, d, ld, n_b, st->perm_minv, st->perm_off, st->centre, st->scale,
-                                                    p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc);
+                                                    p.kpad, TC_BN / st->cg, st->b_tiles, st->a_tiles, st->orig, st->nrm, st->norms4, st->sc,
+                                                    st->sym, st->rpos, st->cu);
   SBK_LAUNCH_CHECK();
+  if (st->sym && st->cg != 2) { set_error("tensor kNN: the symmetric filter needs CTA pairs"); return SBK_ERR_INTERNAL; }
   return SBK_OK;
 }
 
@@ -1059,6 +1352,7 @@ static void tc_chunk_args(TcState* st, const TcPlan& p, long long row0, long lon
   a.order_stat = p.order_stat;
   a.norms4 = st->norms4; a.nrm = st->nrm; a.sc = st->sc; a.scale = st->scale; a.d = st->d;
   a.thr = st->thr; a.cand_cap = p.cand_cap;
+  a.slot_row = st->sym ? st->orig : nullptr;      // symmetric build: slots are staged positions
 }
 
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,
@@ -1109,12 +1403,115 @@ int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
       const int r = binom_quantile(k, f, 2e-6) + 1;       // +1: the row itself is always among the seen or unseen k+1
       if (r <= TC_REFINE_MAX / 2) {
         tc_refine_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, row0, n_rows, r,
-                                                                          st->norms4, st->nrm, st->scale, p.kpad, st->d, st->thr, bound);
+                                                                          st->norms4, st->nrm, st->scale, p.kpad, st->d, st->thr, bound, nullptr);
         SBK_LAUNCH_CHECK();
         if (n_refines) ++*n_refines;
       }
     }
   }
+  return SBK_OK;
+}
+
+// Symmetric self-join filter.  With both operands in the same (pseudo-random) position order, the CTA pair of query
+// tile I multiplies reference tiles I, I+1, ..., I+floor(T/2) (mod T): every unordered pair of tiles exactly once
+// (the opposite tile twice when T is even; it is then row-tested only, like the diagonal).  Each product serves the
+// rows of I directly and the rows of J through the column test; the column hits of a launch sit in per-row outboxes
+// and tc_transpose_kernel appends them to the candidate lists of their rows before anything reads those lists.
+// Half the tensor work of the one-sided filter for the same candidate lists.
+// The steps are cut into launches (a) at 1/14, 1/7 and 2/7 of T, after which every row has seen a window of 1/7, 2/7
+// and 4/7 of the (pseudo-randomly ordered) references around its own tile -- the same threshold refinement as the
+// one-sided filter -- and (b) so that the reference tiles a launch walks stay L2-resident.
+int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound,
+                  int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+  if (!st->sym || st->cg != 2) { set_error("tensor kNN: state not prepared for the symmetric filter"); return SBK_ERR_INTERNAL; }
+  const long long n = st->n_ref, T = p.n_tiles;
+  TcArgs a; long long n_mtiles;
+  tc_chunk_args(st, p, 0, n, a, n_mtiles);
+  a.cand = cand; a.cand_count = cand_count; a.b_tiles = st->b_tiles;
+  a.n_tiles_total = T; a.t8 = st->t8; a.cu = st->cu;
+  a.pool = st->pool; a.pool_count = st->pool_count; a.pool_chunks = st->pool_chunks; a.pool_fail = st->pool_count + 1;
+  n_mtiles = 2 * T;                                            // every CTA pair exists, padding rows included
+  SBK_CUDA_CHECK(cudaMemsetAsync(cand_count, 0, (size_t)n * 4 * sizeof(int32_t), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, 64 * sizeof(int), stream));
+  // positions of every tile in descending-threshold order, then the column thresholds of that order
+  {
+    const size_t sm = (size_t)TC_BN * p.kpad * 2;
+    SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    tc_sort_tiles_kernel<<<(unsigned)T, 256, sm, stream>>>(n, p.kpad, st->a_tiles, st->b_tiles, st->thr, bound, st->cu, st->orig, st->rpos);
+    SBK_LAUNCH_CHECK();
+  }
+  const unsigned cgrid = (unsigned)T;
+  tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8);
+  SBK_LAUNCH_CHECK();
+  if (n_aux_launches) *n_aux_launches += 2;
+  const long long n_steps = T / 2 + 1;                         // steps 0 .. floor(T/2)
+  static const long long l2_bytes = (long long)tc_env_int("SBK_TC_L2_MB", (int)(TC_L2_CHUNK_BYTES >> 20)) << 20;
+  const long long max_steps = std::max<long long>(16, l2_bytes / (long long)p.stage_bytes);
+  static const int refine = tc_env_int("SBK_TC_REFINE", 1);
+  // launch boundaries: the refinement points, then an even split of whatever is still longer than max_steps
+  std::vector<long long> cuts;
+  std::vector<char> refine_at;
+  {
+    const long long marks[3] = {(T + 13) / 14, (T + 6) / 7, (2 * T + 6) / 7};
+    long long prev = 0;
+    auto add_range = [&](long long end, bool is_mark) {
+      if (end <= prev) return;
+      const long long len = end - prev, parts = (len + max_steps - 1) / max_steps;
+      for (long long q = 1; q <= parts; ++q) {
+        cuts.push_back(prev + len * q / parts);
+        refine_at.push_back(is_mark && q == parts);
+      }
+      prev = end;
+    };
+    for (int m = 0; m < 3; ++m) if (marks[m] < n_steps) add_range(marks[m], true);
+    add_range(n_steps, false);
+  }
+  long long s0 = 0;
+  for (size_t li = 0; li < cuts.size(); ++li) {
+    a.bt0 = s0; a.n_btiles = cuts[li] - s0;
+    int rc = tc_launch_cg<TC_FILTER_SYM, 2, 1>(a, n_mtiles, stream);
+    if (rc) return rc;
+    if (n_launches) ++*n_launches;
+    unsigned long long* dbg = nullptr;
+#ifdef SBK_ENABLE_PROBES
+    static const int sym_debug = tc_env_int("SBK_SYM_DEBUG", 0);
+    if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
+#endif
+    tc_transpose_kernel<<<(unsigned)((st->pool_chunks + 7) / 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, n, T, st->thr, st->cu,
+                                                                                  cand, cand_count, p.cand_cap, dbg);
+    SBK_LAUNCH_CHECK();
+    SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, sizeof(int), stream));      // [1], the exhaustion flag, stays
+    SBK_LAUNCH_CHECK();
+#ifdef SBK_ENABLE_PROBES
+    if (sym_debug) {
+      unsigned long long h[4];
+      SBK_CUDA_CHECK(cudaMemcpyAsync(h, dbg, 32, cudaMemcpyDeviceToHost, stream));
+      SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+      fprintf(stderr, "sym launch %zu steps [%lld,%lld): list-segment overflows %llu, pair records %llu, pool of %d chunks\n",
+              li, s0, cuts[li], h[1], h[2], st->pool_chunks);
+    }
+#endif
+    if (n_aux_launches) ++*n_aux_launches;
+    s0 = cuts[li];
+    if (refine && refine_at[li] && s0 < n_steps) {
+      // rows of tile I have now seen tiles I-s0+1 .. I+s0-1
+      const double f = std::min(1.0, (double)(2 * s0 - 1) * TC_BN / (double)n);
+      const int r = binom_quantile(k, f, 2e-6) + 1;
+      if (r <= TC_REFINE_MAX / 2 && f < 1.0) {
+        tc_refine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, 0, n, r, st->norms4, st->nrm, st->scale,
+                                                                     p.kpad, st->d, st->thr, bound, st->orig);
+        SBK_LAUNCH_CHECK();
+        tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8);
+        SBK_LAUNCH_CHECK();
+        if (n_aux_launches) *n_aux_launches += 2;
+      }
+    }
+  }
+  // a launch that ran out of pool chunks lost pair records: the caller redoes the build with the one-sided filter
+  int h_fail = 0;
+  SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fail, st->pool_count + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (h_fail) return TC_SYM_POOL_EXHAUSTED;
   return SBK_OK;
 }
 

@@ -315,11 +315,14 @@ def _graph_rows_one(Xt, k, dev, lo, hi, data, indices, algo, n_blocks, keep_devi
             st = _lib.KnnStats()
             hd = None if data is None else C.c_void_p(data.data_ptr() + lo * k * 8)
             hi_ptr = C.c_void_p(indices.data_ptr() + lo * k * 8)
+            t1 = time.perf_counter()
             rc = lib.sbk_knn_graph(_lib.ptr(Xd), dtype, N, D, Xd.stride(0), lo, hi, k, hd, hi_ptr, chunk,
                                    _lib.ptr(ws), ws.numel(), a, C.byref(st), _lib.stream_ptr(device), copy.cuda_stream)
             _lib.check(rc)
             res = st.as_dict()
             res['upload_ms'] = t_up
+            res['setup_ms'] = (t1 - t0) * 1e3 - t_up
+            res['call_ms'] = (time.perf_counter() - t1) * 1e3
             if keep_device:
                 # the device outputs sit at the head of the workspace (graph_carve in api.cu): copy them out
                 esz = 4 if dtype == _lib.SBK_F32 else 8

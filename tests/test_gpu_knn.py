@@ -97,6 +97,42 @@ def test_tensor_path_20k_vs_exact():
     np.testing.assert_array_equal(d1, d2)
 
 
+@pytest.mark.parametrize('n,k', [(20000, 200), (33000, 64), (50177, 31)])
+def test_symmetric_filter_equals_onesided_and_exact(n, k):
+    """A build of all rows runs the symmetric self-join filter (every tile product tested for both of its row sets);
+    the result must be the one-sided filter's and the FP64 exact path's, bit for bit.  Tile counts: even (n = 20000 ->
+    79 tiles is odd; 33000 -> 129 odd; 50177 -> 197 odd) and, below, an even one."""
+    X = synth.embeddings(n, seed=20260 + n)
+    d0, i0 = _gpu_knn(X, k, 'exact')
+    d1, i1, st1 = _gpu_knn(X, k, 'tensor', return_stats=True)
+    d2, i2, st2 = _gpu_knn(X, k, 'tensor_onesided', return_stats=True)
+    assert st1['algo_used'] == 2 and st1['symmetric'] == 1, st1
+    assert st2['algo_used'] == 2 and st2['symmetric'] == 0, st2
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0, d1)
+    np.testing.assert_array_equal(i0, i2)
+    np.testing.assert_array_equal(d0, d2)
+    assert st1['n_fallback_rows'] < 0.05 * n, st1
+
+
+def test_symmetric_filter_even_tile_count_and_features():
+    """Even tile count (the opposite tile is multiplied by both of its pairs and row-tested only) on the float64
+    k-mer features (split precision columns), against the exact path."""
+    n = 256 * 80
+    F = synth.kmer_features(n, seed=20262)
+    d0, i0 = _gpu_knn(F, 50, 'exact')
+    d1, i1, st = _gpu_knn(F, 50, 'tensor', return_stats=True)
+    assert st['symmetric'] == 1, st
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0, d1)
+    X = synth.tie_grid(n, d=24, seed=5, n_dup=300)
+    d0, i0 = _gpu_knn(X, 20, 'exact')
+    d1, i1, st = _gpu_knn(X, 20, 'tensor', return_stats=True)
+    assert st['symmetric'] == 1, st
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0, d1)
+
+
 def test_live_sklearn_sampled_rows_200k():
     """Scale check: random query rows of a 200k set against live sklearn."""
     sk = pytest.importorskip('sklearn.neighbors')
