@@ -97,7 +97,7 @@ struct TcState {
   int32_t* rpos;                 // rpos[row] = position
   float2* cu;                    // (c_p, u_p): ||z||^2 - sigma rounded down / up (moves a score between the two rows' frames)
   float* t8;                     // per group of 8 positions: max of the column thresholds t_p = thr_p + u_p
-  uint2* pool; int* pool_count; int pool_chunks;   // pair records of one filter launch, in per-warp chunk streams
+  uint4* pool; int* pool_count; int pool_chunks;   // group records of one filter launch, in per-warp chunk streams
   unsigned long long* maxabs;
   int nstage; int cg; long long n_ref; int d;   // cg: CTAs per MMA (tcgen05 cta_group)
   long long perm_mult, perm_off, perm_minv;     // reference position p holds row (p * perm_mult + perm_off) mod n_ref

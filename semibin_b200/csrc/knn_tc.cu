@@ -72,8 +72,11 @@ enum TcMode { TC_SAMPLE = 0, TC_FILTER = 1, TC_DUMP = 2,
               TC_FILTER_SYM = 6 };    // symmetric self-join filter: row test AND column test on every tile (see tc_kernel)
 // symmetric filter: ring of per-tile column thresholds, one slot = 256 column thresholds t_j + their 32 group-of-8 maxima
 static constexpr int TC_T8_SLOTS = 10;          // > nstage + 3 (see tc_kernel)
-static constexpr int TC_TT_FLOATS = TC_BN + TC_BN / 8;          // floats per tile (288 = 1152 B)
-static constexpr int TC_POOL_CH = 1024;                         // pair records per pool chunk (+ one header entry)
+static constexpr int TC_TT_FLOATS = TC_BN / 8;                  // floats per tile: the maxima of its 32 groups of 8 column thresholds (128 B)
+// pool of group records (symmetric filter): chunks of 512 uint4 = 8 KB: [0] = (record count, ..), then 170 records of
+// three uint4: (row position, first column position, -, -), the row's 8 accumulator values of the group
+static constexpr int TC_POOL_CH = 170;
+static constexpr int TC_POOL_STRIDE = 512;                      // uint4 per chunk
 
 // bytes of the reference-tile ring; at least the SAMPLE epilogue's scratch
 // ([TC_BM][TC_NGROUP + 1] floats) which reuses it once the pipeline has drained
@@ -497,19 +500,16 @@ tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ can
 }
 
 // ---- symmetric self-join filter: helpers ----
-// Column thresholds: t_p = thr_p + u_p (rounded up) >= thr_p - sigma_p + ||z_p||^2, per tile of 256 positions followed by
-// the maxima of its 32 groups of 8 (padding positions: -inf).  Rerun after every threshold refinement.
+// Column thresholds t_p = thr_p + u_p (rounded up) >= thr_p - sigma_p + ||z_p||^2: t8[g] = the largest of group g of 8
+// positions (padding positions: -inf).  Rerun after every threshold refinement.
 __global__ void __launch_bounds__(256)
-tc_colthr_kernel(const float* __restrict__ thr, const float2* __restrict__ cu, long long n, float* __restrict__ tt) {
+tc_colthr_kernel(const float* __restrict__ thr, const float2* __restrict__ cu, long long n, float* __restrict__ t8) {
   const long long pp = (long long)blockIdx.x * TC_BN + threadIdx.x;
-  float t = -INFINITY;
-  if (pp < n) t = __fadd_ru(thr[pp], cu[pp].y);
-  float* dst = tt + (long long)blockIdx.x * TC_TT_FLOATS;
-  dst[threadIdx.x] = t;
-  float m = t;
+  float m = -INFINITY;
+  if (pp < n) m = __fadd_ru(thr[pp], cu[pp].y);
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 7) == 0) dst[TC_BN + (threadIdx.x >> 3)] = m;
+  if ((threadIdx.x & 7) == 0) t8[(long long)blockIdx.x * TC_TT_FLOATS + (threadIdx.x >> 3)] = m;
 }
 
 // Symmetric filter: the 256 positions of every tile are re-ordered by descending column threshold (known after the
@@ -566,47 +566,55 @@ tc_sort_tiles_kernel(long long n, int kpad, __half* __restrict__ a_tiles, __half
   }
 }
 
-// Symmetric filter, after every launch: the PAIR records of the launch sit in pool chunks, one stream per epilogue warp
-// (header = first position of the warp's 32 rows, record count).  A record (lane, j, s) of the warp whose rows start at
-// position r0 says: for i = r0 + lane, s <= S^2 d2_ij is a lower bound of the scaled squared distance, and
-// s <= max(t_i, T8(j)) held in the kernel.  It is resolved here for both of its rows:
+// Symmetric filter, after every launch: the GROUP records of the launch sit in pool chunks, one stream per epilogue
+// warp.  A record (i, j0, v[8]) holds the accumulator values L_ij of row position i for the 8 column positions j0..j0+7,
+// written because the group's minimum passed the pre-test.  Here every element is resolved for both of its rows, with
+// s = L_ij + c_i <= S^2 d2_ij:
 //   row i receives candidate (j, s - u_i) iff s <= t_i   (a lower bound in i's frame: e_ij + sigma_i);
 //   row j receives candidate (i, s - u_j) iff s <= t_j and the pair's tile was column-tested (not the diagonal tile, nor
 //   the opposite tile of an even tile count, which hold both orders of their pairs themselves).
-// Candidates are appended to one of the row's four segments with an atomic counter; a count beyond the segment
-// capacity is the overflow mark the rerank already understands.  One warp per chunk.
+// t = thr + u >= thr - sigma + ||z||^2, so whatever is not delivered to a row has d2 > its bound.  Candidates are
+// appended to one of the row's four segments with an atomic counter; a count beyond the segment capacity is the
+// overflow mark the rerank already understands.  One warp per chunk, one record per lane and turn.
 __global__ void __launch_bounds__(256)
-tc_transpose_kernel(const uint2* __restrict__ pool, const int* __restrict__ pool_count, int pool_chunks,
+tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool_count, int pool_chunks,
                     long long n, long long n_tiles, const float* __restrict__ thr, const float2* __restrict__ cu,
                     uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
                     unsigned long long* __restrict__ dbg) {
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (ch >= min(*pool_count, pool_chunks)) return;
-  const uint2* src = pool + (long long)ch * (TC_POOL_CH + 1);
-  const uint2 hdr = src[0];
-  const long long r0 = hdr.x;
-  const int cnt = min((int)hdr.y, TC_POOL_CH);
+  const uint4* src = pool + (long long)ch * TC_POOL_STRIDE;
+  const int cnt = min((int)src[0].x, TC_POOL_CH);
   const int seg_cap = cand_cap >> 2;
   if (dbg && lane == 0) atomicAdd(&dbg[2], (unsigned long long)cnt);
   for (int e = lane; e < cnt; e += 32) {
-    const uint2 rec = src[1 + e];
-    const long long i = r0 + (rec.x >> 27), j = rec.x & 0x7ffffffu;
-    const float sv = __uint_as_float(rec.y);
+    const uint4 hd = src[1 + 3 * e], q0 = src[2 + 3 * e], q1 = src[3 + 3 * e];
+    const long long i = hd.x, j0 = hd.y;
+    const float v[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
+                        __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
     const float2 cui = cu[i];
-    const int ts = e & 3;
-    if (sv <= __fadd_ru(thr[i], cui.y)) {
-      const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
-      if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, cui.y)));
-      else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
-    }
-    long long dt = j / TC_BN - i / TC_BN; if (dt < 0) dt = -dt;
-    if (dt == 0 || dt * 2 == n_tiles) continue;                // row-tested only: the pair appears in both orders already
-    const float2 cuj = cu[j];
-    if (sv <= __fadd_ru(thr[j], cuj.y)) {
-      const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
-      if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, cuj.y)));
-      else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+    const float ti = __fadd_ru(thr[i], cui.y);
+    long long dt = j0 / TC_BN - i / TC_BN; if (dt < 0) dt = -dt;
+    const bool col_on = !(dt == 0 || dt * 2 == n_tiles);        // else row-tested only: the pair appears in both orders already
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float sv = __fadd_rd(v[c], cui.x);
+      const long long j = j0 + c;
+      const int ts = (e + c) & 3;
+      if (sv <= ti) {
+        const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
+        if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, cui.y)));
+        else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+      }
+      if (col_on && j < n) {
+        const float2 cuj = cu[j];
+        if (sv <= __fadd_ru(thr[j], cuj.y)) {
+          const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
+          if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, cuj.y)));
+          else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+        }
+      }
     }
   }
 }
@@ -638,7 +646,7 @@ struct TcArgs {
   long long n_tiles_total;
   const float* t8;            // [n_tiles_total * 32] group maxima of the column thresholds
   const float2* cu;           // [positions] (c, u)
-  uint2* pool; int* pool_count; int pool_chunks; int* pool_fail;    // pair-record pool (chunks of TC_POOL_CH + 1)
+  uint4* pool; int* pool_count; int pool_chunks; int* pool_fail;    // group-record pool (chunks of TC_POOL_STRIDE uint4)
 };
 
 template <int CG> __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -751,7 +759,7 @@ tc_kernel(const TcArgs p) {
       if (elect_one()) {
         mbar_expect_tx(&full_bar[stage], b_bytes + (MODE == TC_FILTER_SYM ? (uint32_t)(TC_TT_FLOATS * 4) : 0u));
         bulk_g2s(sB + (size_t)stage * b_bytes, src, b_bytes, &full_bar[stage]);
-        if (MODE == TC_FILTER_SYM) bulk_g2s(t8ring + tslot * TC_TT_FLOATS, p.t8 + jt * TC_TT_FLOATS, (uint32_t)(TC_TT_FLOATS * 4), &full_bar[stage]);
+        if (MODE == TC_FILTER_SYM) bulk_g2s(t8ring + tslot * TC_TT_FLOATS, p.t8 + jt * TC_TT_FLOATS, (uint32_t)(TC_TT_FLOATS * 4), &full_bar[stage]);   // 128 B
       }
       __syncwarp();
       src += src_step;
@@ -836,25 +844,25 @@ tc_kernel(const TcArgs p) {
       overflow = cnt > seg_cap;
       cnt = min(cnt, seg_cap);
     }
-    // FILTER_SYM: one PAIR record (lane, j, s) per passing element, s = L_ij + c_i <= S^2 d2_ij; it passes when
-    // s <= max(t_i, T8(group of j)), i.e. when row i OR (possibly) row j wants the pair.  The records of a warp form one
-    // stream in chunks of a global pool (a new chunk costs one atomic per TC_POOL_CH records); nothing per row is kept
-    // in the kernel, so a row that is a candidate of thousands of others costs nothing special.  tc_transpose_kernel
-    // hands the records to the candidate lists of both rows after the launch.
+    // FILTER_SYM: the epilogue only PRE-tests groups of 8 columns (minimum of the group against max(t_i, T8(group))) and
+    // dumps the 8 accumulator values of a passing (row, group) as one record into the warp's stream of pool chunks (a new
+    // chunk costs one atomic per TC_POOL_CH records).  The element tests, for both rows of every pair, happen in
+    // tc_transpose_kernel after the launch: per tile the epilogue then costs what the one-sided filter's does, nothing per
+    // row is kept in the kernel, and a row that is a candidate of thousands of others costs nothing special.
     float cadd = INFINITY;                                      // c_i: L_ij + c_i <= S^2 d2_ij
     float trow = -INFINITY;                                     // t_i = thr_i + u_i >= thr_i - sigma_i + ||z_i||^2
     int jt_sym = 0, tslot = 0;
-    uint2* chunk = nullptr;                                     // warp-uniform: the warp's current pool chunk ...
+    uint4* chunk = nullptr;                                     // warp-uniform: the warp's current pool chunk ...
     int wcnt = 0;                                               // ... and the records in it
     auto close_chunk = [&]() {
-      if (lane == 0) chunk[0] = make_uint2((uint32_t)(tile_m * TC_BM + q * 32), (uint32_t)wcnt);
+      if (lane == 0) chunk[0] = make_uint4((uint32_t)wcnt, 0u, 0u, 0u);
     };
     auto new_chunk = [&]() {
       int c = 0;
       if (lane == 0) c = atomicAdd(p.pool_count, 1);
       c = __shfl_sync(0xffffffffu, c, 0);
       if (c >= p.pool_chunks) { c = p.pool_chunks - 1; if (lane == 0) *p.pool_fail = 1; }   // pool exhausted: the host redoes the build one-sided
-      chunk = p.pool + (long long)c * (TC_POOL_CH + 1);
+      chunk = p.pool + (long long)c * TC_POOL_STRIDE;
       wcnt = 0;
     };
     if (MODE == TC_FILTER_SYM) {
@@ -910,15 +918,14 @@ tc_kernel(const TcArgs p) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
-        const float* tt = t8ring + tslot * TC_TT_FLOATS;          // [256 column thresholds][32 group maxima]
+        const float* tt = t8ring + tslot * TC_TT_FLOATS;          // the tile's 32 group maxima of the column thresholds
         if (++tslot == TC_T8_SLOTS) tslot = 0;
         // group minima (three-input min instructions), then one bit per group of 8 columns: "some column of the group
         // may pass": the group's minimum against max(t_i, largest t_j of the group)
         uint32_t lm = 0;
-        float tmx[8];
         {
-          const float4 tq0 = *reinterpret_cast<const float4*>(tt + TC_BN + w4 * 8);       // warp-uniform (broadcast) reads
-          const float4 tq1 = *reinterpret_cast<const float4*>(tt + TC_BN + w4 * 8 + 4);
+          const float4 tq0 = *reinterpret_cast<const float4*>(tt + w4 * 8);       // warp-uniform (broadcast) reads
+          const float4 tq1 = *reinterpret_cast<const float4*>(tt + w4 * 8 + 4);
           const float tg[8] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w};
 #pragma unroll
           for (int g = 0; g < 8; ++g) {
@@ -926,35 +933,26 @@ tc_kernel(const TcArgs p) {
             const float a0 = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
             const float a1 = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
             const float m = fminf(fminf(a0, a1), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-            tmx[g] = col_on ? fmaxf(trow, tg[g]) : trow;
-            lm |= (__fadd_rd(m, cadd) <= tmx[g]) ? (1u << g) : 0u;
+            const float tm = col_on ? fmaxf(trow, tg[g]) : trow;
+            lm |= (__fadd_rd(m, cadd) <= tm) ? (1u << g) : 0u;
           }
         }
-        // The walk is ONE copy of the 8-column code, run for every group some lane flagged (warp-uniform loop; the
-        // group's registers are selected by a uniform switch).  Unrolled per group the epilogue was 4000 instructions
-        // and the warps spent their time on instruction-cache misses (ncu: 19 no-instruction stalls per issue).
-        uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
-        const uint32_t jbase = (uint32_t)jt * (uint32_t)TC_BN + (uint32_t)(w4 * 64);
-        while (wm) {
-          const int g = __ffs(wm) - 1;
-          wm &= wm - 1;
-          uint32_t w[8]; float tm;
-          switch (g) {
-#define SBK_PICK(G, SRC, OFF) case G: tm = tmx[G]; _Pragma("unroll") for (int c = 0; c < 8; ++c) w[c] = SRC[OFF + c]; break;
-            SBK_PICK(0, va, 0) SBK_PICK(1, va, 8) SBK_PICK(2, va, 16) SBK_PICK(3, va, 24)
-            SBK_PICK(4, vb, 0) SBK_PICK(5, vb, 8) SBK_PICK(6, vb, 16)
-            default: tm = tmx[7]; _Pragma("unroll") for (int c = 0; c < 8; ++c) w[c] = vb[24 + c]; break;
-#undef SBK_PICK
-          }
-          const uint32_t jj = jbase + 8u * (uint32_t)g + ((uint32_t)lane << 27);
-          if (wcnt > TC_POOL_CH - 256) { close_chunk(); new_chunk(); }      // a group appends at most 8 x 32 records
+        const uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
+        if (wm) {
+          const uint32_t jbase = (uint32_t)jt * (uint32_t)TC_BN + (uint32_t)(w4 * 64);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float sv = __fadd_rd(__uint_as_float(w[c]), cadd);
-            const bool ps = sv <= tm;
-            const uint32_t bal = __ballot_sync(0xffffffffu, ps);
-            if (bal) {
-              if (ps) chunk[1 + wcnt + __popc(bal & ((1u << lane) - 1u))] = make_uint2(jj + c, __float_as_uint(sv));
+          for (int g = 0; g < 8; ++g) {
+            if (wm & (1u << g)) {                                    // warp-uniform
+              const uint32_t* v = g < 4 ? va + 8 * g : vb + 8 * (g - 4);
+              const bool mine = (lm >> g) & 1u;
+              const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+              if (wcnt > TC_POOL_CH - 32) { close_chunk(); new_chunk(); }
+              if (mine) {
+                uint4* r = chunk + 1 + 3 * (wcnt + __popc(bal & ((1u << lane) - 1u)));
+                r[0] = make_uint4((uint32_t)grow, jbase + 8u * g, 0u, 0u);
+                r[1] = make_uint4(v[0], v[1], v[2], v[3]);
+                r[2] = make_uint4(v[4], v[5], v[6], v[7]);
+              }
               wcnt += __popc(bal);
             }
           }
@@ -1174,12 +1172,12 @@ long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
   return std::min<long long>(rows, 1 << 20);
 }
 
-// chunks of the pair-record pool: one partly filled chunk per epilogue warp of a launch (2T CTAs x 16 warps) plus the
-// records of the busiest launch (about a quarter of all candidates; sized for 4x the planned list volume)
+// chunks of the group-record pool: one partly filled chunk per epilogue warp of a launch (2T CTAs x 16 warps) plus the
+// records of the busiest launch (a quarter of the steps; sized for a quarter of the planned list capacity)
 static int tc_pool_chunks(const TcPlan& p, long long n_ref) {
-  const double recs = (double)n_ref * (double)p.cand_cap / 4.0;
+  const double recs = (double)n_ref * (double)p.cand_cap / 16.0;
   const double c = 32.0 * (double)p.n_tiles + recs / TC_POOL_CH + 1024.0;
-  return (int)std::min(c, 4.0e6);
+  return (int)std::min(c, 2.0e6);
 }
 static constexpr double TC_SYM_MAX_BYTES = 64e9;    // candidate lists + outboxes of all rows must be resident at once
 bool tc_sym_supported(const TcPlan& p, long long n_ref) {
@@ -1209,7 +1207,7 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
     st->cu = a.take<float2>((size_t)n_b);
     st->t8 = a.take<float>((size_t)p.n_tiles * TC_TT_FLOATS);
     st->pool_chunks = tc_pool_chunks(p, n_ref);
-    st->pool = a.take<uint2>((size_t)st->pool_chunks * (TC_POOL_CH + 1));
+    st->pool = a.take<uint4>((size_t)st->pool_chunks * TC_POOL_STRIDE);
     st->pool_count = a.take<int>(64);                    // [0] chunks handed out, [1] pool exhausted
   }
 }
