@@ -917,44 +917,33 @@ tc_kernel(const TcArgs p) {
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { if (leader) mbar_arrive(&tempty_bar[as]); else mbar_arrive_remote(&tempty_bar[as], 0); }
+        if (lane == 0) mbar_arrive_remote(&tempty_bar[as], 0);       // the leader's barrier, from either CTA of the pair
         const float* tt = t8ring + tslot * TC_TT_FLOATS;          // the tile's 32 group maxima of the column thresholds
         if (++tslot == TC_T8_SLOTS) tslot = 0;
-        // group minima (three-input min instructions), then one bit per group of 8 columns: "some column of the group
-        // may pass": the group's minimum against max(t_i, largest t_j of the group)
-        uint32_t lm = 0;
-        {
-          const float4 tq0 = *reinterpret_cast<const float4*>(tt + w4 * 8);       // warp-uniform (broadcast) reads
-          const float4 tq1 = *reinterpret_cast<const float4*>(tt + w4 * 8 + 4);
-          const float tg[8] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w};
+        // per group of 8 columns: minimum (three-input min instructions) against max(t_i, largest t_j of the group); the
+        // warp's vote decides (uniformly) whether anything is dumped, its bit pattern where each lane's record goes
+        const float4 tq0 = *reinterpret_cast<const float4*>(tt + w4 * 8);         // warp-uniform (broadcast) reads
+        const float4 tq1 = *reinterpret_cast<const float4*>(tt + w4 * 8 + 4);
+        const float tg[8] = {tq0.x, tq0.y, tq0.z, tq0.w, tq1.x, tq1.y, tq1.z, tq1.w};
+        const uint32_t jbase = (uint32_t)jt * (uint32_t)TC_BN + (uint32_t)(w4 * 64);
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t* v = g < 4 ? va + 8 * g : vb + 8 * (g - 4);
-            const float a0 = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
-            const float a1 = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
-            const float m = fminf(fminf(a0, a1), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-            const float tm = col_on ? fmaxf(trow, tg[g]) : trow;
-            lm |= (__fadd_rd(m, cadd) <= tm) ? (1u << g) : 0u;
-          }
-        }
-        const uint32_t wm = __reduce_or_sync(0xffffffffu, lm);
-        if (wm) {
-          const uint32_t jbase = (uint32_t)jt * (uint32_t)TC_BN + (uint32_t)(w4 * 64);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (wm & (1u << g)) {                                    // warp-uniform
-              const uint32_t* v = g < 4 ? va + 8 * g : vb + 8 * (g - 4);
-              const bool mine = (lm >> g) & 1u;
-              const uint32_t bal = __ballot_sync(0xffffffffu, mine);
-              if (wcnt > TC_POOL_CH - 32) { close_chunk(); new_chunk(); }
-              if (mine) {
-                uint4* r = chunk + 1 + 3 * (wcnt + __popc(bal & ((1u << lane) - 1u)));
-                r[0] = make_uint4((uint32_t)grow, jbase + 8u * g, 0u, 0u);
-                r[1] = make_uint4(v[0], v[1], v[2], v[3]);
-                r[2] = make_uint4(v[4], v[5], v[6], v[7]);
-              }
-              wcnt += __popc(bal);
+        for (int g = 0; g < 8; ++g) {
+          const uint32_t* v = g < 4 ? va + 8 * g : vb + 8 * (g - 4);
+          const float a0 = fminf(fminf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+          const float a1 = fminf(fminf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+          const float m = fminf(fminf(a0, a1), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+          const float tm = col_on ? fmaxf(trow, tg[g]) : trow;
+          const bool mine = __fadd_rd(m, cadd) <= tm;
+          const uint32_t bal = __ballot_sync(0xffffffffu, mine);
+          if (bal) {                                                  // warp-uniform, about one group in six
+            if (wcnt > TC_POOL_CH - 32) { close_chunk(); new_chunk(); }
+            if (mine) {
+              uint4* r = chunk + 1 + 3 * (wcnt + __popc(bal & ((1u << lane) - 1u)));
+              r[0] = make_uint4((uint32_t)grow, jbase + 8u * g, 0u, 0u);
+              r[1] = make_uint4(v[0], v[1], v[2], v[3]);
+              r[2] = make_uint4(v[4], v[5], v[6], v[7]);
             }
+            wcnt += __popc(bal);
           }
         }
         continue;
