@@ -11,5 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 $CMD > gpurun_out/${tag}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:tc_kernel -s 9 -c 1 -o gpurun_out/${tag}_filter -f $CMD > gpurun_out/${tag}_ncu_filter.log 2>&1
 $CMD > gpurun_out/${tag}_plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'rerank_warp|row_signature' -s 2 -c 2 -o gpurun_out/${tag}_rerank -f $CMD > gpurun_out/${tag}_ncu_rerank.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'rerank_warp|tc_transpose|tc_sort_tiles' -s 7 -c 4 -o gpurun_out/${tag}_rerank -f $CMD > gpurun_out/${tag}_ncu_rerank.log 2>&1
 ls -la gpurun_out/${tag}_*

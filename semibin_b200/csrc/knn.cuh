@@ -96,6 +96,7 @@ struct TcState {
   int sym;                       // A tiles staged in position order too; slots are positions
   int32_t* rpos;                 // rpos[row] = position
   float2* cu;                    // (c_p, u_p): ||z||^2 - sigma rounded down / up (moves a score between the two rows' frames)
+  float4* tq;                    // (c_p, u_p, t_p = thr_p + u_p, -) per position, refreshed with the thresholds
   float* t8;                     // per group of 8 positions: max of the column thresholds t_p = thr_p + u_p
   uint4* pool; int* pool_count; int pool_chunks;   // group records of one filter launch, in per-warp chunk streams
   unsigned long long* maxabs;

@@ -501,12 +501,16 @@ tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ can
 
 // ---- symmetric self-join filter: helpers ----
 // Column thresholds t_p = thr_p + u_p (rounded up) >= thr_p - sigma_p + ||z_p||^2: t8[g] = the largest of group g of 8
-// positions (padding positions: -inf).  Rerun after every threshold refinement.
+// positions (padding positions: -inf), and tq[p] = (c_p, u_p, t_p, -) for the transpose kernel.  Rerun after every
+// threshold refinement.
 __global__ void __launch_bounds__(256)
-tc_colthr_kernel(const float* __restrict__ thr, const float2* __restrict__ cu, long long n, float* __restrict__ t8) {
+tc_colthr_kernel(const float* __restrict__ thr, const float2* __restrict__ cu, long long n, float* __restrict__ t8,
+                 float4* __restrict__ tq) {
   const long long pp = (long long)blockIdx.x * TC_BN + threadIdx.x;
   float m = -INFINITY;
-  if (pp < n) m = __fadd_ru(thr[pp], cu[pp].y);
+  const float2 c = cu[pp];
+  if (pp < n) m = __fadd_ru(thr[pp], c.y);
+  tq[pp] = make_float4(c.x, c.y, m, 0.f);
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 7) == 0) t8[(long long)blockIdx.x * TC_TT_FLOATS + (threadIdx.x >> 3)] = m;
@@ -575,10 +579,11 @@ tc_sort_tiles_kernel(long long n, int kpad, __half* __restrict__ a_tiles, __half
 //   the opposite tile of an even tile count, which hold both orders of their pairs themselves).
 // t = thr + u >= thr - sigma + ||z||^2, so whatever is not delivered to a row has d2 > its bound.  Candidates are
 // appended to one of the row's four segments with an atomic counter; a count beyond the segment capacity is the
-// overflow mark the rerank already understands.  One warp per chunk, one record per lane and turn.
+// overflow mark the rerank already understands.  One warp per chunk, one record per lane and turn (eight lanes per
+// record with coalesced reads measured 15 % slower: the kernel is bound by the scattered 8-byte candidate stores).
 __global__ void __launch_bounds__(256)
 tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool_count, int pool_chunks,
-                    long long n, long long n_tiles, const float* __restrict__ thr, const float2* __restrict__ cu,
+                    long long n, long long n_tiles, const float4* __restrict__ tq,
                     uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
                     unsigned long long* __restrict__ dbg) {
   const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -593,25 +598,24 @@ tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool
     const long long i = hd.x, j0 = hd.y;
     const float v[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
                         __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
-    const float2 cui = cu[i];
-    const float ti = __fadd_ru(thr[i], cui.y);
+    const float4 qi = tq[i];                                   // (c_i, u_i, t_i)
     long long dt = j0 / TC_BN - i / TC_BN; if (dt < 0) dt = -dt;
     const bool col_on = !(dt == 0 || dt * 2 == n_tiles);        // else row-tested only: the pair appears in both orders already
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float sv = __fadd_rd(v[c], cui.x);
+      const float sv = __fadd_rd(v[c], qi.x);
       const long long j = j0 + c;
       const int ts = (e + c) & 3;
-      if (sv <= ti) {
+      if (sv <= qi.z) {
         const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
-        if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, cui.y)));
+        if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, qi.y)));
         else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
       }
-      if (col_on && j < n) {
-        const float2 cuj = cu[j];
-        if (sv <= __fadd_ru(thr[j], cuj.y)) {
+      if (col_on) {
+        const float4 qj = tq[j];                               // padding positions: t = -inf
+        if (sv <= qj.z) {
           const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
-          if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, cuj.y)));
+          if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, qj.y)));
           else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
         }
       }
@@ -885,7 +889,7 @@ tc_kernel(const TcArgs p) {
     uint32_t jtile = (uint32_t)(p.bt0 * TC_BN) - (uint32_t)TC_BN;    // first position of the current tile; loop-carried
     uint32_t sidx = 0;                                                // running accumulator-stage counter
 
-    for (long long t = 0; t < n_tiles; ++t) {
+    for (int t = 0, nt = (int)n_tiles; t < nt; ++t) {      // 32-bit loop state: fewer uniform-datapath instructions per tile
       jtile += (uint32_t)TC_BN;
 #pragma unroll
       for (int h = 0; h < NH; ++h, ++sidx) {
@@ -934,8 +938,8 @@ tc_kernel(const TcArgs p) {
           const float m = fminf(fminf(a0, a1), fminf(__uint_as_float(v[6]), __uint_as_float(v[7])));
           const float tm = col_on ? fmaxf(trow, tg[g]) : trow;
           const bool mine = __fadd_rd(m, cadd) <= tm;
-          const uint32_t bal = __ballot_sync(0xffffffffu, mine);
-          if (bal) {                                                  // warp-uniform, about one group in six
+          if (__any_sync(0xffffffffu, mine)) {                        // warp-uniform, about one group in six
+            const uint32_t bal = __ballot_sync(0xffffffffu, mine);
             if (wcnt > TC_POOL_CH - 32) { close_chunk(); new_chunk(); }
             if (mine) {
               uint4* r = chunk + 1 + 3 * (wcnt + __popc(bal & ((1u << lane) - 1u)));
@@ -1162,11 +1166,12 @@ long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
 }
 
 // chunks of the group-record pool: one partly filled chunk per epilogue warp of a launch (2T CTAs x 16 warps) plus the
-// records of the busiest launch (a quarter of the steps; sized for a quarter of the planned list capacity)
+// records of the busiest launch (sized for an eighth of the planned list capacity of every row: the first launches run on
+// the loosest thresholds, 3-4x the measured volume at 200k and 1M rows)
 static int tc_pool_chunks(const TcPlan& p, long long n_ref) {
-  const double recs = (double)n_ref * (double)p.cand_cap / 16.0;
+  const double recs = (double)n_ref * (double)p.cand_cap / 8.0;
   const double c = 32.0 * (double)p.n_tiles + recs / TC_POOL_CH + 1024.0;
-  return (int)std::min(c, 2.0e6);
+  return (int)std::min(c, 3.0e6);
 }
 static constexpr double TC_SYM_MAX_BYTES = 64e9;    // candidate lists + outboxes of all rows must be resident at once
 bool tc_sym_supported(const TcPlan& p, long long n_ref) {
@@ -1194,6 +1199,7 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
   if (sym) {
     st->rpos = a.take<int32_t>((size_t)n_b);
     st->cu = a.take<float2>((size_t)n_b);
+    st->tq = a.take<float4>((size_t)n_b);
     st->t8 = a.take<float>((size_t)p.n_tiles * TC_TT_FLOATS);
     st->pool_chunks = tc_pool_chunks(p, n_ref);
     st->pool = a.take<uint4>((size_t)st->pool_chunks * TC_POOL_STRIDE);
@@ -1428,7 +1434,7 @@ int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* can
     SBK_LAUNCH_CHECK();
   }
   const unsigned cgrid = (unsigned)T;
-  tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8);
+  tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
   SBK_LAUNCH_CHECK();
   if (n_aux_launches) *n_aux_launches += 2;
   const long long n_steps = T / 2 + 1;                         // steps 0 .. floor(T/2)
@@ -1464,7 +1470,7 @@ int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* can
     static const int sym_debug = tc_env_int("SBK_SYM_DEBUG", 0);
     if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
 #endif
-    tc_transpose_kernel<<<(unsigned)((st->pool_chunks + 7) / 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, n, T, st->thr, st->cu,
+    tc_transpose_kernel<<<(unsigned)((st->pool_chunks + 7) / 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, n, T, st->tq,
                                                                                   cand, cand_count, p.cand_cap, dbg);
     SBK_LAUNCH_CHECK();
     SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, sizeof(int), stream));      // [1], the exhaustion flag, stays
@@ -1488,7 +1494,7 @@ int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* can
         tc_refine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, 0, n, r, st->norms4, st->nrm, st->scale,
                                                                      p.kpad, st->d, st->thr, bound, st->orig);
         SBK_LAUNCH_CHECK();
-        tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8);
+        tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
         SBK_LAUNCH_CHECK();
         if (n_aux_launches) *n_aux_launches += 2;
       }
