@@ -55,9 +55,10 @@ typedef enum sbk_knn_algo {
   SBK_KNN_AUTO = 0,              /* tensor-core filter for large n, exact filter otherwise */
   SBK_KNN_EXACT = 1,             /* FP64 CUDA-core filter (also the certificate fallback) */
   SBK_KNN_TENSOR = 2,            /* tcgen05 FP16 filter + FP64 rerank with exactness certificate; a build of ALL rows
-                                    (q_begin = 0, q_end = n_ref) uses the symmetric self-join filter: every tile product
-                                    serves both of its row sets, half the tensor work */
-  SBK_KNN_TENSOR_ONESIDED = 3    /* the same, but never the symmetric filter (row blocks always run one-sided) */
+                                    (q_begin = 0, q_end = n_ref) of at least ~400k rows uses the symmetric self-join
+                                    filter: every tile product serves both of its row sets, half the tensor work */
+  SBK_KNN_TENSOR_ONESIDED = 3,   /* the same, but never the symmetric filter (row blocks always run one-sided) */
+  SBK_KNN_TENSOR_SYMMETRIC = 4   /* the same, symmetric filter whenever the call covers all rows (any size >= 2048 rows) */
 } sbk_knn_algo;
 
 /* Filled (when non-NULL) after the call's work is complete; passing a non-NULL

@@ -65,8 +65,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
   KnnShape s; memset(&s, 0, sizeof(s));
   const int k1 = k + 1;
   if (algo == SBK_KNN_AUTO) algo = (n_ref >= TC_MIN_N && (d + 5 + 15) / 16 * 16 <= 176) ? SBK_KNN_TENSOR : SBK_KNN_EXACT;
-  const bool onesided = algo == SBK_KNN_TENSOR_ONESIDED;
-  if (onesided) algo = SBK_KNN_TENSOR;
+  const bool onesided = algo == SBK_KNN_TENSOR_ONESIDED, force_sym = algo == SBK_KNN_TENSOR_SYMMETRIC;
+  if (onesided || force_sym) algo = SBK_KNN_TENSOR;
   s.algo = algo;
   if (algo == SBK_KNN_EXACT) {
     s.chunk = std::min<long long>(std::max<long long>(n_q, 1), EXACT_CHUNK);
@@ -84,7 +84,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     s.tcap = rerank_warp_supported(dtype, d, k) ? rerank_warp_cap(k) : 0;
     // a build of all rows: every tile product is used for both of its row sets (half the tensor work); the candidate
     // lists of all rows are then live at once, so the whole call is one filter "chunk"
-    s.sym = !onesided && n_q == n_ref && s.tcap > 0 && tc_sym_supported(s.plan, n_ref);
+    // (below ~400k rows its extra launches, record transposes and refinements cost what the halved tensor work saves)
+    s.sym = !onesided && n_q == n_ref && s.tcap > 0 && tc_sym_supported(s.plan, n_ref) && (force_sym || s.plan.n_tiles >= TC_SYM_MIN_TILES);
     if (s.sym) s.chunk = n_q;
     s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 4) : 0;
   }

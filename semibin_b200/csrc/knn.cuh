@@ -109,6 +109,7 @@ long long tc_chunk_rows(const TcPlan& p, long long n_ref);
 size_t tc_workspace_bytes(const TcPlan& p, long long n_ref, long long n_query, bool sym = false);
 // whether the symmetric self-join filter can take a build of all n_ref rows (candidate lists of every row resident at once)
 bool tc_sym_supported(const TcPlan& p, long long n_ref);
+static constexpr long long TC_SYM_MIN_TILES = 1600;   // AUTO / TENSOR pick the symmetric filter from this many 256-row tiles on
 static constexpr int TC_SYM_POOL_EXHAUSTED = 1000;   // tc_filter_sym: not an error, the caller falls back to the one-sided filter
 // Stage operands, centre/scale, sample; `chunk` = max query rows per tc_filter_chunk call.
 int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, TcPlan& p,

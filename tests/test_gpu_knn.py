@@ -99,12 +99,12 @@ def test_tensor_path_20k_vs_exact():
 
 @pytest.mark.parametrize('n,k', [(20000, 200), (33000, 64), (50177, 31)])
 def test_symmetric_filter_equals_onesided_and_exact(n, k):
-    """A build of all rows runs the symmetric self-join filter (every tile product tested for both of its row sets);
-    the result must be the one-sided filter's and the FP64 exact path's, bit for bit.  Tile counts: even (n = 20000 ->
-    79 tiles is odd; 33000 -> 129 odd; 50177 -> 197 odd) and, below, an even one."""
+    """The symmetric self-join filter (every tile product tested for both of its row sets; the default for builds of
+    all rows from ~400k rows on, forced here) must give the one-sided filter's and the FP64 exact path's result, bit
+    for bit.  Odd tile counts here (79, 129, 197), an even one below."""
     X = synth.embeddings(n, seed=20260 + n)
     d0, i0 = _gpu_knn(X, k, 'exact')
-    d1, i1, st1 = _gpu_knn(X, k, 'tensor', return_stats=True)
+    d1, i1, st1 = _gpu_knn(X, k, 'tensor_symmetric', return_stats=True)
     d2, i2, st2 = _gpu_knn(X, k, 'tensor_onesided', return_stats=True)
     assert st1['algo_used'] == 2 and st1['symmetric'] == 1, st1
     assert st2['algo_used'] == 2 and st2['symmetric'] == 0, st2
@@ -121,13 +121,13 @@ def test_symmetric_filter_even_tile_count_and_features():
     n = 256 * 80
     F = synth.kmer_features(n, seed=20262)
     d0, i0 = _gpu_knn(F, 50, 'exact')
-    d1, i1, st = _gpu_knn(F, 50, 'tensor', return_stats=True)
+    d1, i1, st = _gpu_knn(F, 50, 'tensor_symmetric', return_stats=True)
     assert st['symmetric'] == 1, st
     np.testing.assert_array_equal(i0, i1)
     np.testing.assert_array_equal(d0, d1)
     X = synth.tie_grid(n, d=24, seed=5, n_dup=300)
     d0, i0 = _gpu_knn(X, 20, 'exact')
-    d1, i1, st = _gpu_knn(X, 20, 'tensor', return_stats=True)
+    d1, i1, st = _gpu_knn(X, 20, 'tensor_symmetric', return_stats=True)
     assert st['symmetric'] == 1, st
     np.testing.assert_array_equal(i0, i1)
     np.testing.assert_array_equal(d0, d1)
@@ -153,6 +153,29 @@ def test_live_sklearn_sampled_rows_200k():
     # size-independent properties at full size
     assert (np.diff(d, axis=1) >= 0).all()                      # rows sorted
     assert (i != np.arange(N)[:, None]).all()                   # self excluded
+    assert i.min() >= 0 and i.max() < N
+
+
+def test_default_symmetric_build_450k_vs_live_sklearn():
+    """A build of all rows above ~400k rows takes the symmetric filter by default: sampled rows against live sklearn
+    (float32 embedding, k = 100), plus the full-size properties.  (The float64 feature graph at that size:
+    tests/test_gpu_scale.py.)"""
+    sk = pytest.importorskip('sklearn.neighbors')
+    N, k = 450000, 100
+    X = synth.embeddings(N, seed=20270)
+    rows = np.sort(np.random.default_rng(7).choice(N, 384, replace=False))
+    d, i, st = _gpu_knn(X, k, 'auto', return_stats=True)
+    assert st['algo_used'] == 2 and st['symmetric'] == 1, st
+    nn = sk.NearestNeighbors(n_neighbors=k + 1, algorithm='brute').fit(X)
+    rd, ri = nn.kneighbors(X[rows])
+    for t, r in enumerate(rows):
+        m = ri[t] != r
+        if m.all():
+            m[0] = False
+        compare.assert_knn_parity(rd[t][m][None], ri[t][m][None], d[r][None], i[r][None], rtol=1e-6)
+    assert st['n_fallback_rows'] < 0.01 * N, st
+    assert (np.diff(d, axis=1) >= 0).all()
+    assert (i != np.arange(N)[:, None]).all()
     assert i.min() >= 0 and i.max() < N
 
 

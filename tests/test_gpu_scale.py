@@ -54,6 +54,25 @@ def test_feature_graph_200k_vs_live_sklearn(width):
     assert (np.diff(d, axis=1) >= 0).all() and (i != np.arange(N)[:, None]).all() and i.min() >= 0 and i.max() < N
 
 
+def test_feature_graph_450k_symmetric_vs_live_sklearn():
+    """a4 above the size from which a build of all rows takes the symmetric filter: combined features (D = 146, float64,
+    split precision columns) at 450k through algo='auto', 384 sampled rows against live scikit-learn."""
+    import torch
+    from semibin_b200.neighbors import knn
+    N, k = 450000, 100
+    emb, feat, depth, L = synth.short_read_case(N, n_sample=10, seed=20243)
+    F = _combined_features(feat, depth)
+    d, i, st = knn(torch.from_numpy(F).cuda(), k, algo='auto', return_stats=True)
+    assert st['algo_used'] == 2 and st['symmetric'] == 1, st
+    d = d.cpu().numpy(); i = i.cpu().numpy().astype(np.int64)
+    rows = np.sort(np.random.default_rng(12).choice(N, 384, replace=False))
+    rd, ri = _sk_rows(F, k, rows)
+    res = compare.assert_knn_parity(rd, ri, d[rows], i[rows], rtol=1e-6)
+    print(res, {kk: st[kk] for kk in ('n_fallback_rows', 'n_retry_rows', 'n_fail_few', 'n_fail_certificate', 'n_split_cols', 'kpad')})
+    assert st['n_fallback_rows'] < 0.01 * N, st
+    assert (np.diff(d, axis=1) >= 0).all() and (i != np.arange(N)[:, None]).all() and i.min() >= 0 and i.max() < N
+
+
 def test_c4_labels_300k_vs_live_sklearn():
     """a13 + a14 at scale: long-read kNN graph (D = 101) and DBSCAN labels of 300k contigs; the labels of three eps
     values against live sklearn.cluster.dbscan on the graph of the GPU (the graph itself is checked on sampled rows
