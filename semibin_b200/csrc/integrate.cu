@@ -98,12 +98,14 @@ __device__ __forceinline__ void ig_stats_body(const IgConst& c, const int32_t* _
                                               const int32_t* __restrict__ bend, const unsigned char* __restrict__ alive,
                                               const long long* __restrict__ lengths, const unsigned long long* __restrict__ masks,
                                               const int32_t* __restrict__ list, long long n_items,
-                                              IgBin* __restrict__ bins, unsigned int* __restrict__ dirty) {
+                                              IgBin* __restrict__ bins, unsigned int* __restrict__ dirty,
+                                              bool whole_list = false) {
   __shared__ long long s_w[8];
   __shared__ unsigned long long s_m[8][IG_MAX_WORDS];
   __shared__ int s_t[8], s_f[8], s_c[8];
   const int nwarp = blockDim.x >> 5;
-  for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
+  // whole_list: this CTA re-reduces every item of the (CTA-private) list; else the items are dealt round-robin to the CTAs
+  for (long long it = whole_list ? 0 : blockIdx.x; it < n_items; it += whole_list ? 1 : gridDim.x) {
     const long long g = list ? (long long)list[it] : it;
     const int r = ig_result_of(c, g);
     const int32_t* mem = order + (long long)r * c.N;
@@ -156,11 +158,13 @@ ig_stats_kernel(IgConst c, const int32_t* __restrict__ order, const int32_t* __r
 
 // Bins that can ever be chosen (long_read_cluster.py:26-34): both quantities only shrink as contigs retire.
 __global__ void ig_eligible_kernel(const IgBin* __restrict__ bins, long long n_bins, long long minfasta,
-                                   int32_t* __restrict__ elig, int* __restrict__ n_elig) {
+                                   int32_t* __restrict__ elig, int* __restrict__ n_elig, int32_t* __restrict__ elig_pos) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_bins) return;
   const IgBin b = bins[g];
-  if (b.weight >= minfasta && b.total > 0) elig[atomicAdd(n_elig, 1)] = (int32_t)g;
+  int pos = -1;
+  if (b.weight >= minfasta && b.total > 0) { pos = atomicAdd(n_elig, 1); elig[pos] = (int32_t)g; }
+  elig_pos[g] = pos;                             // where the bin sits in the eligible list (-1: it can never be chosen)
 }
 
 __device__ __forceinline__ IgKey ig_key_of(const IgConst& c, const IgBin& b, int g) {
@@ -184,58 +188,117 @@ __device__ __forceinline__ IgKey ig_shfl_key(const IgKey& k, int o) {
   return x;
 }
 
+static constexpr int IG_OWN_MAX = 256;    // touched bins of one extraction a CTA lists in shared memory
+
+// Grid barrier of the persistent loop (all CTAs co-resident: cooperative launch, one CTA per SM).  One arrival counter
+// and a generation word; against cooperative_groups' grid.sync() it took 9 ms off the 85 ms of the 500k-contig case (two
+// barriers per extracted bin, 2336 bins).
+__device__ __forceinline__ void ig_grid_barrier(unsigned int* bar, unsigned int n_blocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int gen;
+    asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    __threadfence();
+    if (atomicAdd(bar, 1u) == n_blocks - 1u) {
+      bar[0] = 0u;
+      __threadfence();
+      asm volatile("st.release.gpu.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
+    } else {
+      unsigned int now;
+      do { asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory"); } while (now == gen);
+    }
+  }
+  __syncthreads();
+}
 // The extraction loop of long_read_cluster.py:122-143 as one persistent cooperative kernel (one CTA per SM).
-// Per extracted bin:
-//   1. every CTA: arg-max over its share of the eligible bins -> partial[blockIdx]           | grid barrier
-//   2. every CTA combines ALL partials itself (the decision and the loop state are replicated, no second barrier),
-//      evaluates the loop conditions of :123-134, retires the winner's live members and lists the bins they
-//      belong to (:136-141)                                                                   | grid barrier
-//   3. the listed bins are re-reduced                                                         | grid barrier
+// Every CTA OWNS a contiguous slice of the eligible-bin list: it keeps the best key of its slice, re-reduces the bins of
+// its slice that the last extraction touched and rescans the slice only then (a few dozen bins change per extraction,
+// most CTAs have nothing to do).  Per extracted bin, two grid barriers:
+//   1. owners: re-reduce their touched bins, rescan their slice if anything changed -> partial[blockIdx]   | grid barrier
+//   2. every CTA combines ALL partials itself (the decision and the loop state are replicated), evaluates the loop
+//      conditions of :123-134, retires the winner's live members and lists the bins they belong to (:136-141);
+//      the lists of consecutive extractions alternate between two buffers                                     | grid barrier
 __global__ void __launch_bounds__(256)
 ig_loop_kernel(IgConst c, const long long* __restrict__ labels, const int32_t* __restrict__ order,
                const int32_t* __restrict__ bstart, const int32_t* __restrict__ bend,
                unsigned char* __restrict__ alive, const long long* __restrict__ lengths,
                const unsigned long long* __restrict__ masks, IgBin* __restrict__ bins, unsigned int* __restrict__ dirty,
-               int32_t* __restrict__ dirty_list, const int32_t* __restrict__ elig, const int* __restrict__ n_elig,
-               IgKey* __restrict__ partial, IgStatus* __restrict__ status, long long* __restrict__ out_labels,
-               long long max_iter) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
+               int32_t* __restrict__ dirty_list, long long dirty_cap, const int32_t* __restrict__ elig, const int* __restrict__ n_elig,
+               const int32_t* __restrict__ elig_pos, IgKey* __restrict__ partial, IgStatus* __restrict__ status,
+               int* __restrict__ n_dirty2, long long* __restrict__ out_labels, long long max_iter) {
+  unsigned int* gbar = reinterpret_cast<unsigned int*>(n_dirty2 + 2);      // [arrivals, generation], zeroed by the host
   __shared__ IgKey s_k[8];
   __shared__ int s_best;
+  __shared__ int s_own[IG_OWN_MAX];
+  __shared__ int s_nown;
   // loop state, replicated in every thread of every CTA (identical by construction)
   long long remaining_weight = status->remaining_weight, remaining_count = status->remaining_count;
   int n_extracted = 0;
   const int n = *n_elig;
+  const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int e_lo = min(n, (int)blockIdx.x * per), e_hi = min(n, e_lo + per);
   bool done = false;
   for (long long iter = 0; iter < max_iter && !done; ++iter) {
-    // ---- 1. partial arg-max ----
-    IgKey best; best.bin = -1; best.cls = 9; best.f1 = 0; best.w = 0; best.r = 0; best.first = 0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-      const int g = elig[e];
-      const IgKey kk = ig_key_of(c, bins[g], g);
-      if (ig_better(kk, best)) best = kk;
+    const int cur = (int)(iter & 1);                       // dirty-list buffer this extraction fills
+    // ---- 1. owners: re-reduce what the previous extraction touched, rescan the slice if anything changed ----
+    bool rescan = iter == 0;
+    if (iter > 0) {
+      // which of the touched bins are mine: one list entry per thread (independent loads), owned ones into shared memory
+      const int32_t* dl = dirty_list + (long long)(cur ^ 1) * dirty_cap;
+      const int nd = n_dirty2[cur ^ 1];
+      if (threadIdx.x == 0) s_nown = 0;
+      __syncthreads();
+      for (int it = threadIdx.x; it < nd; it += blockDim.x) {
+        const int g = dl[it];
+        const int e = elig_pos[g];
+        if (e >= e_lo && e < e_hi) { const int at = atomicAdd(&s_nown, 1); if (at < IG_OWN_MAX) s_own[at] = g; }
+      }
+      __syncthreads();
+      const int nown = s_nown;
+      if (nown > IG_OWN_MAX) {                             // more than the shared list holds (never seen): walk the global list
+        for (int it = 0; it < nd; ++it) {
+          const int g = dl[it];
+          const int e = elig_pos[g];
+          if (e < e_lo || e >= e_hi) continue;             // block-uniform
+          ig_stats_body(c, order, bstart, bend, alive, lengths, masks, dl + it, 1, bins, dirty, true);
+        }
+      } else if (nown > 0) {
+        ig_stats_body(c, order, bstart, bend, alive, lengths, masks, s_own, (long long)nown, bins, dirty, true);
+      }
+      rescan = nown > 0;
     }
+    if (rescan) {                                          // block-uniform
+      IgKey best; best.bin = -1; best.cls = 9; best.f1 = 0; best.w = 0; best.r = 0; best.first = 0;
+      for (int e = e_lo + threadIdx.x; e < e_hi; e += blockDim.x) {
+        const int g = elig[e];
+        const IgKey kk = ig_key_of(c, bins[g], g);
+        if (ig_better(kk, best)) best = kk;
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const IgKey x = ig_shfl_key(best, o); if (ig_better(x, best)) best = x; }
-    if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = best;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int q = 1; q < (int)(blockDim.x >> 5); ++q) if (ig_better(s_k[q], best)) best = s_k[q];
-      partial[blockIdx.x] = best;
-      if (blockIdx.x == 0) status->n_dirty = 0;              // the previous extraction's dirty list has been consumed
+      for (int o = 16; o > 0; o >>= 1) { const IgKey x = ig_shfl_key(best, o); if (ig_better(x, best)) best = x; }
+      if ((threadIdx.x & 31) == 0) s_k[threadIdx.x >> 5] = best;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) if (ig_better(s_k[q], best)) best = s_k[q];
+        partial[blockIdx.x] = best;
+      }
     }
-    grid.sync();
-    // ---- 2. decision (replicated), retire the winner ----
-    if (threadIdx.x == 0) {
-      IgKey b = partial[0];
-      for (int q = 1; q < (int)gridDim.x; ++q) if (ig_better(partial[q], b)) b = partial[q];
-      int choice;
-      if (remaining_weight < c.minfasta) choice = -1;                                    // :123
-      else if (remaining_count == 1) choice = -2;                                        // :124-126
-      else if (b.bin < 0) choice = -1;                                                   // :133-134
-      else choice = b.bin;
-      s_best = choice;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_dirty2[cur] = 0;     // its last readers passed two barriers ago
+    ig_grid_barrier(gbar, gridDim.x);
+    // ---- 2. decision (replicated: one warp per CTA combines the partials), retire the winner ----
+    if (threadIdx.x < 32) {
+      IgKey b; b.bin = -1; b.cls = 9; b.f1 = 0; b.w = 0; b.r = 0; b.first = 0;
+      for (int q = threadIdx.x; q < (int)gridDim.x; q += 32) { const IgKey x = partial[q]; if (ig_better(x, b)) b = x; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const IgKey x = ig_shfl_key(b, o); if (ig_better(x, b)) b = x; }
+      if (threadIdx.x == 0) {
+        int choice;
+        if (remaining_weight < c.minfasta) choice = -1;                                    // :123
+        else if (remaining_count == 1) choice = -2;                                        // :124-126
+        else if (b.bin < 0) choice = -1;                                                   // :133-134
+        else choice = b.bin;
+        s_best = choice;
+      }
     }
     __syncthreads();
     const int choice = s_best;
@@ -256,23 +319,33 @@ ig_loop_kernel(IgConst c, const long long* __restrict__ labels, const int32_t* _
       const int r = ig_result_of(c, choice);
       const int32_t* mem = order + (long long)r * c.N;
       const int lo = bstart[choice], hi = bend[choice];
+      int32_t* dl = dirty_list + (long long)cur * dirty_cap;
       for (long long p = lo + t0; p < hi; p += stride) {
         const int i = mem[p];
         if (!alive[i]) continue;
         alive[i] = 0;
         out_labels[i] = cur_label;
-        for (int q = 0; q < c.R; ++q) {
-          const long long l = labels[(long long)q * c.N + i];
-          if (l < 0) continue;
-          const long long g = c.base[q] + l;
-          if (dirty[g] == 0u && atomicExch(&dirty[g], 1u) == 0u) dirty_list[atomicAdd(&status->n_dirty, 1)] = (int32_t)g;
+        // the member's bins in all results, eight results at a time: the label, position and flag loads of a batch are
+        // independent of each other (one result after the other this chain of dependent loads was most of an extraction)
+        for (int q0 = 0; q0 < c.R; q0 += 8) {
+          long long gg[8]; int ep[8]; unsigned int fl[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int q = q0 + u;
+            const long long l = q < c.R ? labels[(long long)q * c.N + i] : -1;
+            gg[u] = l >= 0 ? c.base[q < c.R ? q : 0] + l : -1;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) ep[u] = gg[u] >= 0 ? elig_pos[gg[u]] : -1;      // bins that can never be chosen are not listed
+#pragma unroll
+          for (int u = 0; u < 8; ++u) fl[u] = ep[u] >= 0 ? dirty[gg[u]] : 1u;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (fl[u] == 0u && atomicExch(&dirty[gg[u]], 1u) == 0u) dl[atomicAdd(&n_dirty2[cur], 1)] = (int32_t)gg[u];
         }
       }
     }
-    grid.sync();
-    // ---- 3. re-reduce the touched bins ----
-    ig_stats_body(c, order, bstart, bend, alive, lengths, masks, dirty_list, (long long)status->n_dirty, bins, dirty);
-    grid.sync();
+    ig_grid_barrier(gbar, gridDim.x);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) { status->n_extracted = n_extracted; status->done = done ? 1 : 0; }
 }
@@ -282,6 +355,7 @@ struct IgWs {
   int32_t* order; int32_t* keys_in; int32_t* keys_out; int32_t* vals_in; int* maxlab;
   int32_t* bstart; int32_t* bend; IgBin* bins; unsigned int* dirty; int32_t* dirty_list; int32_t* elig; int* n_elig;
   unsigned char* alive; IgKey* partial; IgStatus* status; void* cub_tmp; size_t cub_bytes;
+  int32_t* elig_pos; int* n_dirty2; long long dirty_cap;
 };
 
 static size_t ig_cub_bytes(long long n) {
@@ -298,7 +372,10 @@ static void ig_carve(Arena& a, long long n, int R, IgWs& w) {
   w.maxlab = a.take<int>(IG_MAX_R);
   w.bstart = a.take<int32_t>(max_bins); w.bend = a.take<int32_t>(max_bins);
   w.bins = a.take<IgBin>(max_bins);
-  w.dirty = a.take<unsigned int>(max_bins); w.dirty_list = a.take<int32_t>(max_bins);
+  w.dirty = a.take<unsigned int>(max_bins);
+  w.dirty_cap = (long long)max_bins;                       // two alternating lists (consecutive extractions)
+  w.dirty_list = a.take<int32_t>(2 * max_bins);
+  w.elig_pos = a.take<int32_t>(max_bins); w.n_dirty2 = a.take<int>(4);
   w.elig = a.take<int32_t>(max_bins); w.n_elig = a.take<int>(4);
   w.alive = a.take<unsigned char>((size_t)n);
   w.partial = a.take<IgKey>(IG_SEL_BLOCKS * 4);
@@ -364,6 +441,7 @@ extern "C" int sbk_integrate(const long long* labels, int32_t n_results, int64_t
   SBK_CUDA_CHECK(cudaMemsetAsync(w.alive, 1, (size_t)n, stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(out_labels, 0xff, (size_t)n * sizeof(long long), stream));           // -1
   SBK_CUDA_CHECK(cudaMemsetAsync(w.n_elig, 0, 4 * sizeof(int), stream));
+  SBK_CUDA_CHECK(cudaMemsetAsync(w.n_dirty2, 0, 4 * sizeof(int), stream));
   if (n_bins > 0) SBK_CUDA_CHECK(cudaMemsetAsync(w.dirty, 0, (size_t)n_bins * sizeof(unsigned int), stream));
   // total length of all contigs (loop condition :123): reuse the reduction of a one-bin view is overkill -> host sum
   std::vector<long long> hl((size_t)n);
@@ -378,7 +456,7 @@ extern "C" int sbk_integrate(const long long* labels, int32_t n_results, int64_t
     const unsigned sg = (unsigned)std::min<long long>(n_bins, 148 * 64);
     ig_stats_kernel<<<sg, 256, 0, stream>>>(c, w.order, w.bstart, w.bend, w.alive, lengths, marker_masks, n_bins, w.bins, w.dirty);
     SBK_LAUNCH_CHECK();
-    ig_eligible_kernel<<<(unsigned)((n_bins + 255) / 256), 256, 0, stream>>>(w.bins, n_bins, minfasta, w.elig, w.n_elig);
+    ig_eligible_kernel<<<(unsigned)((n_bins + 255) / 256), 256, 0, stream>>>(w.bins, n_bins, minfasta, w.elig, w.n_elig, w.elig_pos);
     SBK_LAUNCH_CHECK();
   }
   // ---- extraction loop: one persistent cooperative kernel, one CTA per SM ----
@@ -392,8 +470,9 @@ extern "C" int sbk_integrate(const long long* labels, int32_t n_results, int64_t
     long long max_iter = n + 2;
     const long long* labels_p = labels; const long long* lengths_p = lengths; const unsigned long long* masks_p = marker_masks;
     void* args[] = {(void*)&c, (void*)&labels_p, (void*)&w.order, (void*)&w.bstart, (void*)&w.bend, (void*)&w.alive,
-                    (void*)&lengths_p, (void*)&masks_p, (void*)&w.bins, (void*)&w.dirty, (void*)&w.dirty_list, (void*)&w.elig,
-                    (void*)&w.n_elig, (void*)&w.partial, (void*)&w.status, (void*)&out_labels, (void*)&max_iter};
+                    (void*)&lengths_p, (void*)&masks_p, (void*)&w.bins, (void*)&w.dirty, (void*)&w.dirty_list, (void*)&w.dirty_cap,
+                    (void*)&w.elig, (void*)&w.n_elig, (void*)&w.elig_pos, (void*)&w.partial, (void*)&w.status, (void*)&w.n_dirty2,
+                    (void*)&out_labels, (void*)&max_iter};
     SBK_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)ig_loop_kernel, dim3(grid), dim3(256), args, 0, stream));
   }
   SBK_CUDA_CHECK(cudaMemcpyAsync(&st, w.status, sizeof(st), cudaMemcpyDeviceToHost, stream));
