@@ -239,6 +239,45 @@ def short_read_sharded(n, S, combined, k=200, max_node=1):
     return res if rank == 0 else None
 
 
+def recluster_case(n_total, cpu_bins=60):
+    """Row N4 (SemiBin/cluster.py:229-246): the per-bin seeded / weighted KMeans of the re-clustering step for a sample
+    of ~n_total binned contigs (bins of 50..6000 contigs, D = 103, 2..8 seeds each) as ONE batched launch; beside it live
+    scikit-learn called bin after bin the way the reference calls it, on the first `cpu_bins` bins, with the label check."""
+    import torch
+    from semibin_b200.recluster import kmeans_batch
+    from semibin_b200 import synth
+    from oracle import kmeans as okm
+    rng = np.random.default_rng(123)
+    probs, tot = [], 0
+    while tot < n_total:
+        n = int(min(6000, max(50, rng.lognormal(6.0, 0.9)))); K = int(rng.integers(2, 9))
+        probs.append(synth.recluster_problem(9000 + len(probs), n, 103, K, float(rng.uniform(0.1, 0.4)), float(rng.uniform(0.04, 0.3))))
+        tot += n
+    X = torch.from_numpy(np.concatenate([p[0] for p in probs])).cuda()
+    w = torch.from_numpy(np.concatenate([p[1] for p in probs]).astype(np.float32)).cuda()
+    C0 = torch.from_numpy(np.concatenate([p[0][p[2]] for p in probs])).cuda()
+    po = np.concatenate([[0], np.cumsum([len(p[0]) for p in probs])]).astype(np.int64)
+    co = np.concatenate([[0], np.cumsum([len(p[2]) for p in probs])]).astype(np.int32)
+    kmeans_batch(X, w, po, C0, co)
+    (lab, nit), ms = timed(lambda: kmeans_batch(X, w, po, C0, co), reps=3)
+    lab = lab.cpu().numpy(); nit = nit.cpu().numpy()
+    res = dict(n_contigs=int(tot), n_bins=len(probs), d=103, kmeans_batch_ms=ms, lloyd_iterations_total=int(nit.sum()),
+               largest_bin=int(max(len(p[0]) for p in probs)), max_iterations=int(nit.max()))
+    try:
+        from sklearn.cluster import KMeans
+        t0 = time.perf_counter(); n_cpu = 0; n_diff = 0; n_bad = 0
+        for t, (Xb, wb, sb) in enumerate(probs[:cpu_bins]):
+            km = KMeans(n_clusters=len(sb), init=Xb[sb], n_init=1, random_state=0).fit(Xb, sample_weight=wb)
+            c = okm.compare_labels(Xb, km.cluster_centers_, km.labels_, lab[po[t]:po[t + 1]])
+            n_diff += c['n_differ']; n_bad += c['n_unexplained']; n_cpu += len(Xb)
+        dt = time.perf_counter() - t0
+        res.update(cpu_sklearn_bins=min(cpu_bins, len(probs)), cpu_sklearn_contigs=n_cpu, cpu_sklearn_s=dt,
+                   cpu_sklearn_extrapolated_s=dt * tot / max(n_cpu, 1), labels_differ=n_diff, labels_unexplained=n_bad)
+    except ImportError:
+        pass
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--config', default='C2')
@@ -255,6 +294,8 @@ def main():
         r = long_read(a.n or 500000, 1, cpu_check=a.cpu_check)
     elif a.config == 'C5':
         r = scaling_case(a.n or 4000000)
+    elif a.config == 'N4':
+        r = recluster_case(a.n or 1000000)
     elif a.config == 'C3dist':
         r = short_read_sharded(a.n or 1000000, 10, a.combined)
         if r is None:

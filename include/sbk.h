@@ -239,6 +239,32 @@ int sbk_integrate(const long long* labels, int32_t n_results, int64_t n, const l
                   int64_t minfasta, long long* out_labels, int32_t* n_extracted,
                   void* workspace, size_t ws_bytes, void* cuda_stream);
 
+size_t sbk_kmeans_batch_workspace_bytes(int64_t n_total, int32_t d, int32_t n_problems, int64_t k_total);
+
+/* Re-clustering step, SemiBin/cluster.py:229-246: for every bin with more than one seed the reference calls
+ *   KMeans(n_clusters=num_bin, init=seeds_embedding, n_init=1, random_state=seed).fit(re_bin_features,
+ *          sample_weight=length_weight)                         (scikit-learn 1.9.0, algorithm 'lloyd')
+ * one bin after the other; this entry point solves ALL bins of a sample in one launch (one CTA per bin runs the whole
+ * Lloyd loop: E-step, weighted M-step, empty-cluster relocation, the two convergence tests, the final E-step).
+ *   X              : float[n_total, ld >= d], the rows of every problem CONTIGUOUS (problem p = rows
+ *                    [point_offsets[p], point_offsets[p+1])), device
+ *   weight         : float[n_total], sample weights (contig lengths), device
+ *   point_offsets  : int64[n_problems + 1], HOST
+ *   cluster_offsets: int32[n_problems + 1], HOST: problem p has cluster_offsets[p+1] - cluster_offsets[p] clusters
+ *   centers_init   : float[cluster_offsets[n_problems], d], the seed rows (init=...), device
+ *   max_iter, tol  : KMeans defaults 300 and 1e-4 (tol is relative to the mean column variance, _kmeans.py:_tolerance)
+ *   labels         : int32[n_total] out, cluster index within the problem (KMeans.labels_), device
+ *   n_iter         : int32[n_problems] out (KMeans.n_iter_), device
+ *   centers_out    : double[cluster_offsets[n_problems], d] out (KMeans.cluster_centers_) or NULL, device
+ * With an array init and n_init = 1 nothing is random.  Sums are FP64 in index order on the float32 data centred by
+ * its float32 column mean (as fit() does); labels equal scikit-learn's except where a point's two nearest final
+ * centres tie to ~1e-4 relative.  n_samples < n_clusters in a problem -> SBK_ERR_INVALID with sklearn's message. */
+int sbk_kmeans_batch(const float* X, int64_t ld, int32_t d, const float* weight, int64_t n_total,
+                     const int64_t* point_offsets, const int32_t* cluster_offsets, int32_t n_problems,
+                     const float* centers_init, int32_t max_iter, double tol,
+                     int32_t* labels, int32_t* n_iter, double* centers_out,
+                     void* workspace, size_t ws_bytes, void* cuda_stream);
+
 /* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
  * MMA pipeline as the tensor filter and returns the accumulator values
  *   L[i,j] <= S^2 d2_ij - nrm_i + norms4[i].w      (i < n_q, j < n_ref <= 65536)

@@ -159,13 +159,30 @@ def integrate():
     np.savez_compressed(os.path.join(OUT, 'integrate.npz'), **out)
 
 
+def kmeans_cases():
+    """Live scikit-learn KMeans exactly as the reference calls it (cluster.py:236-241)."""
+    from sklearn.cluster import KMeans
+    out = {}
+    cases = dict(separated=(11, 1500, 103, 4, 0.05, 0.5, 0), overlapping=(12, 2000, 110, 6, 0.35, 0.06, 0),
+                 many=(13, 1800, 101, 12, 0.2, 0.05, 0), dupseeds=(14, 900, 103, 3, 0.15, 0.5, 2),
+                 tiny=(15, 40, 103, 3, 0.3, 0.3, 0))
+    for name, (seed, n, d, K, spread, sep, dup) in cases.items():
+        X, w, seeds = synth.recluster_problem(seed, n, d, K, spread, sep, dup)
+        km = KMeans(n_clusters=len(seeds), init=X[seeds], n_init=1, random_state=0)
+        km.fit(X, sample_weight=w)
+        out[f'{name}_X'] = X; out[f'{name}_w'] = w; out[f'{name}_seeds'] = seeds
+        out[f'{name}_labels'] = km.labels_.astype(np.int32); out[f'{name}_centers'] = km.cluster_centers_
+        out[f'{name}_n_iter'] = np.int64(km.n_iter_)
+    np.savez_compressed(os.path.join(OUT, 'kmeans_cases.npz'), **out)
+
+
 if __name__ == '__main__':
     warnings.simplefilter('ignore')
     os.makedirs(OUT, exist_ok=True)
     import sklearn
     assert sklearn.__version__.startswith('1.9'), sklearn.__version__
     only = sys.argv[1:]
-    for fn in (bin_data, ties, synth_knn, synth_edges, synth_dbscan, cal_kl, integrate):
+    for fn in (bin_data, ties, synth_knn, synth_edges, synth_dbscan, cal_kl, integrate, kmeans_cases):
         if only and fn.__name__ not in only:
             continue
         fn(); print('wrote', fn.__name__)

@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 HEADER = os.path.normpath(os.path.join(HERE, '..', 'include', 'sbk.h'))
-SOURCES = ['api.cu', 'knn_exact.cu', 'knn_tc.cu', 'edges.cu', 'radius.cu', 'scan.cu', 'integrate.cu']
+SOURCES = ['api.cu', 'knn_exact.cu', 'knn_tc.cu', 'edges.cu', 'radius.cu', 'scan.cu', 'integrate.cu', 'kmeans.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 HASH_MARK = 'SBK_SOURCE_HASH='

@@ -75,6 +75,10 @@ SIGNATURES = {
     'sbk_integrate_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_integrate': (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                 C.c_int64, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sbk_kmeans_batch_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32, C.c_int64]),
+    'sbk_kmeans_batch': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                   C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_size_t, C.c_void_p]),
     'sbk_debug_tc_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_debug_tc_scores': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

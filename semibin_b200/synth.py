@@ -129,3 +129,21 @@ def marker_table(genome, lengths, seed=20240, n_markers=107, completeness=(0.4, 
             if int(m) not in per_contig[c]:
                 per_contig[c].append(int(m))
     return [np.array(sorted(v), dtype=np.int32) for v in per_contig]
+
+
+def recluster_problem(seed, n, d, K, spread, sep, dup_seeds=0):
+    """One re-clustering problem in the shape of SemiBin/cluster.py:229-243: float32 features (embedding + scaled depth
+    columns), K seed contigs picked from the data, integer contig lengths as weights."""
+    rng = np.random.default_rng(seed)
+    centres = rng.normal(size=(K, d)) * sep
+    sizes = rng.multinomial(n - K, rng.dirichlet(np.ones(K) * 2.0)) + 1
+    lab = np.repeat(np.arange(K), sizes)
+    X = (centres[lab] + rng.normal(size=(n, d)) * spread).astype(np.float32)
+    perm = rng.permutation(n)
+    X, lab = X[perm], lab[perm]
+    seeds = np.array([np.where(lab == j)[0][0] for j in range(K)])
+    if dup_seeds:                              # several seeds from the same true cluster (over-estimated bin count)
+        extra = np.where(lab == 0)[0][1:1 + dup_seeds]
+        seeds = np.concatenate([seeds, extra])
+    w = np.exp(rng.normal(8.5, 1.0, size=n)).astype(np.int64) + 1000
+    return X, w, seeds

@@ -167,3 +167,64 @@ def test_run_embed_infomap_handoff_matches_reference(monkeypatch):
     np.testing.assert_array_equal(cap['edges'], np.stack([X, Y], axis=1))
     np.testing.assert_array_equal(cap['edge_weights'], V)        # the oracle stands in for the GPU stages here: bit-equal
     np.testing.assert_array_equal(cap['vertex_weights'], ref_cap['vertex_weights'])
+
+
+def test_recluster_bins_matches_reference(monkeypatch):
+    """Row N4: semibin_b200.recluster.recluster_bins against the UNMODIFIED SemiBin.cluster.recluster_bins (live
+    scikit-learn KMeans per bin) on a synthetic sample: depth scaling of the features (:185-195), the concatenated-bin
+    fasta handed to the seed search (:202-214), which bins are split, label bookkeeping (:221-253).  The seed search
+    (ORF finder + hmmsearch, absent) is stubbed identically on both sides; the batched GPU launch is replaced by the
+    CPU oracle here (its parity with scikit-learn is tests/test_oracle.py and the -m gpu tier)."""
+    import pandas as pd
+    sys.path.insert(0, REF)
+    import SemiBin.cluster as ref_cluster
+    import semibin_b200.recluster as ours
+    from semibin_b200 import synth
+    from oracle import kmeans as okm
+    rng = np.random.default_rng(9)
+    n_sample = 3
+    embs, bins, names = [], [], []
+    seeds = {}
+    for b in range(12):
+        n = int(rng.integers(4, 400)); K = int(rng.integers(1, 5))
+        X, w, s = synth.recluster_problem(500 + b, max(n, K + 1), 100, K, 0.15, 0.3)
+        nm = [f'contig_{b}_{i}' for i in range(len(X))]
+        embs.append(X); bins += [b] * len(X); names += nm
+        if b != 5:
+            seeds[f'bin{b:06}'] = [nm[i] for i in s]
+    emb = np.concatenate(embs)
+    perm = rng.permutation(len(emb))
+    emb = emb[perm]; bins = np.asarray(bins)[perm]; names = [names[i] for i in perm]
+    lengths = rng.integers(1000, 30000, len(emb))
+    contig_dict = {nm: 'A' * int(ell) for nm, ell in zip(names, lengths)}
+    depth = np.abs(rng.normal(40, 25, (len(emb), 2 * n_sample)))
+    data = pd.DataFrame(np.concatenate([rng.random((len(emb), 136)), depth], axis=1), index=names)
+    total = {b: int(lengths[bins == b].sum()) for b in range(12)}
+    minfasta = int(sorted(total.values())[2]) + 1              # the two smallest bins stay below minfasta
+    seen = {}
+
+    def fake_estimate_seeds(fasta, binned_length, num_process, multi_mode=False, orf_finder=None):
+        assert multi_mode
+        seen.setdefault('fasta', []).append(open(fasta).read())
+        return seeds
+    monkeypatch.setattr(ref_cluster, 'estimate_seeds', fake_estimate_seeds)
+    kw = dict(n_sample=n_sample, embedding=emb, is_combined=False, contig_labels=bins.copy(), minfasta=minfasta,
+              contig_dict=contig_dict, binned_length=1000, orf_finder='prodigal', num_process=1, random_seed=7)
+    ref = ref_cluster.recluster_bins(logging.getLogger('t'), data, **kw)
+
+    def cpu_problems(embedding_new, rows, po, seed_rows, co, lengths_, device=None):
+        out = np.empty(len(rows), np.int32)
+        for t in range(len(po) - 1):
+            r = rows[po[t]:po[t + 1]]
+            out[po[t]:po[t + 1]], _, _ = okm.lloyd_seeded(embedding_new[r], np.asarray(lengths_)[r], embedding_new[seed_rows[co[t]:co[t + 1]]])
+        return out
+    monkeypatch.setattr(ours, '_kmeans_problems', cpu_problems)
+    got = ours.recluster_bins(logging.getLogger('t'), data, **kw, estimate_seeds=fake_estimate_seeds)
+    np.testing.assert_array_equal(np.asarray(ref), got)
+    assert seen['fasta'][0] == seen['fasta'][1]                # the same concatenated fasta went to the seed search
+    assert got.max() + 1 > 12                                  # some bins were split
+    # no seeds at all: the labels come back untouched, as :215-217
+    monkeypatch.setattr(ref_cluster, 'estimate_seeds', lambda *a, **k: {})
+    r0 = ref_cluster.recluster_bins(logging.getLogger('t'), data, **kw)
+    g0 = ours.recluster_bins(logging.getLogger('t'), data, **kw, estimate_seeds=lambda *a, **k: {})
+    np.testing.assert_array_equal(np.asarray(r0), g0)

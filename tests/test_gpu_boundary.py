@@ -94,6 +94,7 @@ def _fake_semibin(monkeypatch, markers_by_name, written):
     ut = types.ModuleType('SemiBin.utils')
     mk = types.ModuleType('SemiBin.markers')
     cl.run_embed_infomap = lambda *a, **k: 'reference run_embed_infomap'
+    cl.recluster_bins = lambda *a, **k: 'reference recluster_bins'
     lr.kneighbors_graph = lambda *a, **k: 'reference kneighbors_graph'
     lr.dbscan = lambda *a, **k: 'reference dbscan'
     lr.cluster_long_read = lambda *a, **k: 'reference cluster_long_read'
@@ -171,6 +172,7 @@ def test_patch_install_serves_reference_call_sites(golden, monkeypatch):
     patch.install()
     try:
         assert rc.run_embed_infomap.__module__ == 'semibin_b200.cluster'
+        assert rc.recluster_bins.__module__ == 'semibin_b200.recluster'
         assert rl.cluster_long_read.__module__ == 'semibin_b200.long_read'
         L = g['lengths']
         dist_matrix = rl.kneighbors_graph(g['long_emb_new'], n_neighbors=min(200, 39), mode='distance', p=2, n_jobs=4)

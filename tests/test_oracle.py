@@ -237,3 +237,17 @@ def test_kl_bound_covers_log_evaluators(S):
     assert (diff > 0).any()                                   # the evaluators do differ
     assert (diff <= bound).all(), float((diff / bound).max())
     assert np.median(bound) < 1e-5 and bound.max() < 1e-4     # a few float32 ulps, not a blanket tolerance
+
+
+def test_kmeans_restatement_matches_sklearn_golden(golden):
+    """Row N4: the seeded, weighted Lloyd restatement against scikit-learn's own labels / centres / iteration counts
+    (tests/golden/kmeans_cases.npz, KMeans called as SemiBin/cluster.py:236-241 calls it)."""
+    from oracle import kmeans as okm
+    g = golden('kmeans_cases')
+    for name in ('separated', 'overlapping', 'many', 'dupseeds', 'tiny'):
+        X, w, seeds = g[name + '_X'], g[name + '_w'], g[name + '_seeds']
+        lab, cen, it = okm.lloyd_seeded(X, w, X[seeds])
+        res = okm.compare_labels(X, g[name + '_centers'], g[name + '_labels'], lab)
+        assert res['n_unexplained'] == 0 and res['n_differ'] == 0, (name, res)
+        assert it == int(g[name + '_n_iter'])
+        np.testing.assert_allclose(cen, g[name + '_centers'], rtol=0, atol=2e-6)
