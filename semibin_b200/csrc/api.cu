@@ -24,6 +24,7 @@ void set_error(const char* fmt, ...) {
 static constexpr int KNN_MAX_K = 1023;
 static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk (exact path)
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
+static constexpr int SYM_SINK_BLOCKS = 8;               // block rows of the symmetric build when the result streams to host memory
 
 // Profiling switches exist only in the probe build (-DSBK_ENABLE_PROBES, libsbk_probe.so): the product library
 // never reads the environment, so a stray variable cannot change or corrupt a result.
@@ -217,6 +218,35 @@ widen_kernel(const T* __restrict__ d, const int32_t* __restrict__ i, long long n
   }
 }
 
+// Finished rows of the symmetric block-row build, straight into (mapped, pinned) host memory: one warp per row at a
+// time, the row's k entries as consecutive 4/8-byte stores (zero-copy over PCIe; WIDE: scikit-learn's float64 / int64
+// CSR dtypes).  `rows` lists row ids in any order; the device result (d, i) and the host arrays are in row order.
+// The kernel runs NEXT TO the filter of the following block rows and is bound by PCIe for milliseconds.  A filter CTA
+// owns its SM (218 KB of shared memory, 61 440 registers), so every scatter block takes an SM -- and with it the CTA
+// pair of its TPC -- away from the filter for as long as it lives.  Measured at 1M (end to end / filter stage, ms):
+// 148 blocks of 128 threads 227 / 173, 64: 210 / 156, 16: 201 / 144, and with 512-thread blocks 12: 198 / 143,
+// 8: 197 / 141, 4: 193 / 137, 2: 204 / 135 (two SMs no longer keep up with the block rows).  Four blocks it is.
+static constexpr int SCATTER_BLOCKS = 4;
+static constexpr int SCATTER_THREADS = 512;
+template <typename T, bool WIDE>
+__global__ void __launch_bounds__(SCATTER_THREADS)
+scatter_rows_kernel(const int32_t* __restrict__ rows, long long n_rows, int k, const T* __restrict__ d,
+                    const int32_t* __restrict__ i, void* __restrict__ host_d, void* __restrict__ host_i) {
+  const int wpb = SCATTER_THREADS / 32;
+  for (long long w = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); w < n_rows; w += (long long)gridDim.x * wpb) {
+    const long long o = (long long)rows[w] * k;
+    for (int c = threadIdx.x & 31; c < k; c += 32) {
+      if (WIDE) {
+        if (host_d) reinterpret_cast<double*>(host_d)[o + c] = (double)d[o + c];
+        reinterpret_cast<long long*>(host_i)[o + c] = (long long)i[o + c];
+      } else {
+        if (host_d) reinterpret_cast<T*>(host_d)[o + c] = d[o + c];
+        reinterpret_cast<int32_t*>(host_i)[o + c] = i[o + c];
+      }
+    }
+  }
+}
+
 // rows [r0, r0 + n_rows) of the device result (od / oi point at row r0) -> host rows [r0, ...); enqueued on the copy stream
 static int sink_rows(const HostSink* sk, int dtype, int k, const void* od, const int32_t* oi, long long r0, long long n_rows) {
   const size_t esz = dtype == SBK_F32 ? 4 : 8;
@@ -268,6 +298,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
 
   StageTimer tm(stream, stats != nullptr);
   TcState tcs; memset(&tcs, 0, sizeof(tcs));
+  bool blocks_done = false;                      // symmetric block-row build: every row already reranked and written out
   if (s.algo == SBK_KNN_TENSOR) {
     int h = tm.begin(&st.ms_prepare);
     rc = tc_prepare(X, dtype, n_ref, d, ld, s.plan, s.sym ? n_q : s.chunk, w.tc, w.tc_bytes, &tcs, stream, s.sym);
@@ -278,7 +309,81 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
     st.sample_size = s.plan.sample_size; st.cand_capacity = s.plan.cand_cap;
     st.order_stat = s.plan.order_stat; st.kpad = s.plan.kpad; st.n_split_cols = s.plan.n_split;
     st.symmetric = s.sym ? 1 : 0;
-    if (s.sym) {
+    // host-buffer build: the block-row schedule finishes the rows block by block, each block is reranked and written to
+    // the (mapped) host arrays while the later block rows are multiplied
+    void* zc_dist = nullptr; void* zc_idx = nullptr;
+    if (s.sym && sink) {
+      const bool ok_i = cudaHostGetDevicePointer(&zc_idx, sink->idx, 0) == cudaSuccess;
+      const bool ok_d = !sink->dist || cudaHostGetDevicePointer(&zc_dist, sink->dist, 0) == cudaSuccess;
+      if (!ok_i || !ok_d) { cudaGetLastError(); zc_idx = nullptr; zc_dist = nullptr; }    // not mapped: chunked copies at the end
+    }
+    if (s.sym && zc_idx) {
+      h = tm.begin(&st.ms_sample);
+      rc = tc_sample_chunk(&tcs, s.plan, 0, n_q, w.bound, stream);
+      tm.end(h);
+      if (rc) return rc;
+      int nfl = 0, naux = 0;
+      h = tm.begin(&st.ms_filter);
+      rc = tc_sym_begin(&tcs, s.plan, w.cand_pair, w.cand_count, w.bound, &naux, stream);
+      tm.end(h);
+      if (rc) return rc;
+      const int n_blocks = SYM_SINK_BLOCKS;
+      const long long tb = tc_sym_block_tiles(s.plan, n_blocks);
+      std::vector<cudaEvent_t> bev;
+      auto drop_bev = [&]() { for (cudaEvent_t e : bev) cudaEventDestroy(e); bev.clear(); };
+      for (int r = 0; r < n_blocks && (long long)r * tb < s.plan.n_tiles; ++r) {
+        h = tm.begin(&st.ms_filter);
+        rc = tc_sym_block(&tcs, s.plan, k, w.cand_pair, w.cand_count, w.bound, n_blocks, r, &nfl, &naux, stream);
+        tm.end(h);
+        if (rc) { drop_bev(); return rc; }
+        const long long slot_lo = (long long)r * tb * TC_BN, slot_hi = std::min<long long>(n_q, ((long long)r + 1) * tb * TC_BN);
+        const long long cn = slot_hi - slot_lo;
+        if (cn <= 0) continue;
+        h = tm.begin(&st.ms_rerank);
+        SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
+        int32_t* perm = nullptr;                             // the block's rows (orig[positions]) in locality order
+        rc = launch_row_order(X, dtype, d, ld, q_begin, cn, tcs.centre, w.order_ws, w.order_bytes, &perm, stream, tcs.orig + slot_lo);
+        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, q_begin, cn, perm, tcs.rpos, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound,
+                                         tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, out_dist, out_idx, q_begin, w.fail_rows, w.n_fail, w.retry,
+                                         w.n_fail + 2, (int)s.retry_cap, w.cand_total, stream, peers);
+        if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, tcs.orig, q_begin, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+                                    w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, out_dist, out_idx, q_begin, w.fail_rows, w.n_fail,
+                                    w.cand_total + 8, stream, w.retry, w.n_fail + 2, (int)s.retry_cap, peers);
+        tm.end(h);
+        st.n_launches += 5;
+        if (rc) { drop_bev(); return rc; }
+        cudaEvent_t ev;
+        SBK_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        bev.push_back(ev);
+        SBK_CUDA_CHECK(cudaEventRecord(ev, stream));
+        SBK_CUDA_CHECK(cudaStreamWaitEvent(sink->copy_stream, ev, 0));
+        unsigned sg = (unsigned)std::min<long long>((cn + 15) / 16, SCATTER_BLOCKS);
+#ifdef SBK_ENABLE_PROBES
+        { static const int pg = getenv("SBK_SCATTER_GRID") ? atoi(getenv("SBK_SCATTER_GRID")) : -1; if (pg == 0) continue; if (pg > 0) sg = (unsigned)pg; }
+#endif
+        const int32_t* rl = tcs.orig + slot_lo;               // row ids (q_begin = 0 in a build of all rows)
+        if (sink->wide) {
+          if (dtype == SBK_F32) scatter_rows_kernel<float, true><<<sg, SCATTER_THREADS, 0, sink->copy_stream>>>(rl, cn, k, (const float*)out_dist, out_idx, zc_dist, zc_idx);
+          else scatter_rows_kernel<double, true><<<sg, SCATTER_THREADS, 0, sink->copy_stream>>>(rl, cn, k, (const double*)out_dist, out_idx, zc_dist, zc_idx);
+        } else {
+          if (dtype == SBK_F32) scatter_rows_kernel<float, false><<<sg, SCATTER_THREADS, 0, sink->copy_stream>>>(rl, cn, k, (const float*)out_dist, out_idx, zc_dist, zc_idx);
+          else scatter_rows_kernel<double, false><<<sg, SCATTER_THREADS, 0, sink->copy_stream>>>(rl, cn, k, (const double*)out_dist, out_idx, zc_dist, zc_idx);
+        }
+        SBK_LAUNCH_CHECK();
+        st.n_launches += 1;
+        st.n_chunks++;
+      }
+      rc = tc_sym_end(&tcs, stream);
+      drop_bev();
+      st.n_filter_launches += nfl; st.n_launches += 1 + nfl + naux;
+      if (rc == TC_SYM_POOL_EXHAUSTED) {
+        SBK_CUDA_CHECK(cudaStreamSynchronize(sink->copy_stream));
+        return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, SBK_KNN_TENSOR_ONESIDED,
+                        stats, stream, sink, peers);
+      }
+      if (rc) return rc;
+      blocks_done = true;
+    } else if (s.sym) {
       // thresholds of every row, then the symmetric filter over all tile pairs: the chunk loop below only reranks
       h = tm.begin(&st.ms_sample);
       rc = tc_sample_chunk(&tcs, s.plan, 0, n_q, w.bound, stream);
@@ -300,7 +405,7 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
   // (their output rows stay untouched) and recomputed once at the end.
   std::vector<cudaEvent_t> events;
   auto drop_events = [&]() { for (cudaEvent_t e : events) cudaEventDestroy(e); events.clear(); };
-  for (long long c0 = 0; c0 < n_q; c0 += s.chunk) {
+  for (long long c0 = 0; c0 < n_q && !blocks_done; c0 += s.chunk) {
     const long long cn = std::min(s.chunk, n_q - c0);
     const long long row0 = q_begin + c0;
     void* od = (char*)out_dist + (size_t)c0 * k * esz;

@@ -32,9 +32,11 @@ int launch_rerank(const void* X, int dtype, long long n_ref, int d, long long ld
 int rerank_warp_cap(int k);
 bool rerank_warp_supported(int dtype, int d, int k);
 size_t row_order_workspace_bytes(long long n_rows);
-// locality order of the chunk's query rows for the warp rerank: perm_out[i] = slot visited i-th (lives in `ws`)
+// locality order of the chunk's query rows for the warp rerank: perm_out[i] = slot visited i-th (lives in `ws`);
+// with a row list (`rows`, n_rows global row ids) the order is over those rows and perm_out holds row ids - q_begin
 int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream);
+                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream,
+                     const int32_t* rows = nullptr);
 // row_slot (optional): candidate lists, thresholds and bounds are indexed by row_slot[row] instead of row - q_begin
 // (the symmetric filter keeps them in staged-position order)
 int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows, const int32_t* perm,
@@ -119,6 +121,14 @@ int tc_prepare(const void* X, int dtype, long long n_ref, int d, long long ld, T
 // cand / cand_count / bound are indexed by staged position.
 int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound,
                   int* n_launches, int* n_aux_launches, cudaStream_t stream);
+// The same filter block row by block row (tc_sym_begin, tc_sym_block for r = 0 .. n_blocks-1, tc_sym_end): after block
+// row r the rows at positions [r, r+1) * tc_sym_block_tiles * 256 are finished (complete candidate lists).
+long long tc_sym_block_tiles(const TcPlan& p, int n_blocks);
+int tc_sym_begin(TcState* st, const TcPlan& p, uint2* cand, int32_t* cand_count, double* bound, int* n_aux_launches,
+                 cudaStream_t stream);
+int tc_sym_block(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound, int n_blocks, int r,
+                 int* n_launches, int* n_aux_launches, cudaStream_t stream);
+int tc_sym_end(TcState* st, cudaStream_t stream);
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,

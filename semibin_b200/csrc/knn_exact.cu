@@ -1040,13 +1040,14 @@ int launch_rerank_warp(const void* X, int dtype, int d, long long ld, long long 
 // correct; this one only has to be cheap: one pass over the chunk's rows (16 sign-sums per row) + a 16-bit radix sort.
 __global__ void __launch_bounds__(256)
 row_signature_kernel(const void* __restrict__ Xv, int is_f64, int d, long long ld, long long q_begin, long long n_rows,
-                     const double* __restrict__ centre, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                     const double* __restrict__ centre, uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                     const int32_t* __restrict__ rows) {
   const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_rows) return;
   float acc[16];
 #pragma unroll
   for (int b = 0; b < 16; ++b) acc[b] = 0.f;
-  const long long r = q_begin + s;
+  const long long r = rows ? (long long)rows[s] : q_begin + s;      // a row list: the order is over those rows, values = row ids - q_begin
   for (int c = 0; c < d; ++c) {
     const float v = is_f64 ? (float)(reinterpret_cast<const double*>(Xv)[r * ld + c] - centre[c])
                            : (float)((double)reinterpret_cast<const float*>(Xv)[r * ld + c] - centre[c]);
@@ -1058,7 +1059,7 @@ row_signature_kernel(const void* __restrict__ Xv, int is_f64, int d, long long l
   uint32_t key = 0;
 #pragma unroll
   for (int b = 0; b < 16; ++b) key |= (acc[b] > 0.f ? 1u : 0u) << b;
-  keys[s] = key; vals[s] = (int32_t)s;
+  keys[s] = key; vals[s] = rows ? (int32_t)(r - q_begin) : (int32_t)s;
 }
 
 size_t row_order_workspace_bytes(long long n_rows) {
@@ -1070,7 +1071,8 @@ size_t row_order_workspace_bytes(long long n_rows) {
 
 // perm_out[i] = slot visited i-th.  `ws` holds row_order_workspace_bytes(n_rows).
 int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_begin, long long n_rows,
-                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream) {
+                     const double* centre, void* ws, size_t ws_bytes, int32_t** perm_out, cudaStream_t stream,
+                     const int32_t* rows) {
   if (n_rows <= 0) { *perm_out = nullptr; return SBK_OK; }
   Arena a(ws, ws_bytes);
   uint32_t* keys_in = a.take<uint32_t>((size_t)n_rows);
@@ -1082,7 +1084,7 @@ int launch_row_order(const void* X, int dtype, int d, long long ld, long long q_
   void* cub_tmp = a.take<char>(tmp);
   if (!a.ok()) { set_error("row order: workspace %zu < %zu", ws_bytes, a.off); return SBK_ERR_WORKSPACE; }
   row_signature_kernel<<<(unsigned)((n_rows + 255) / 256), 256, 0, stream>>>(X, dtype == SBK_F64 ? 1 : 0, d, ld, q_begin, n_rows, centre,
-                                                                           keys_in, vals_in);
+                                                                           keys_in, vals_in, rows);
   SBK_LAUNCH_CHECK();
   SBK_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, keys_in, keys_out, vals_in, vals_out, (int)n_rows, 0, 16, stream));
   *perm_out = vals_out;

@@ -582,16 +582,22 @@ tc_sort_tiles_kernel(long long n, int kpad, __half* __restrict__ a_tiles, __half
 // overflow mark the rerank already understands.  One warp per chunk, one record per lane and turn (eight lanes per
 // record with coalesced reads measured 15 % slower: the kernel is bound by the scattered 8-byte candidate stores).
 __global__ void __launch_bounds__(256)
-tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool_count, int pool_chunks,
-                    long long n, long long n_tiles, const float4* __restrict__ tq,
+tc_transpose_kernel(const uint4* __restrict__ pool, int* __restrict__ pool_count, int pool_chunks,
+                    long long n, long long n_tiles, long long blk_tiles, const float4* __restrict__ tq,
                     uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
                     unsigned long long* __restrict__ dbg) {
-  const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (ch >= min(*pool_count, pool_chunks)) return;
+  const int n_chunks = min(*pool_count, pool_chunks);
+  const int seg_cap = cand_cap >> 2;
+  // a fixed grid of warps takes the chunks handed out one by one (their number is only known on the device, and they
+  // are unevenly filled: a static split left a tail)
+  for (;;) {
+  int ch = 0;
+  if (lane == 0) ch = atomicAdd(pool_count + 1, 1);
+  ch = __shfl_sync(0xffffffffu, ch, 0);
+  if (ch >= n_chunks) break;
   const uint4* src = pool + (long long)ch * TC_POOL_STRIDE;
   const int cnt = min((int)src[0].x, TC_POOL_CH);
-  const int seg_cap = cand_cap >> 2;
   if (dbg && lane == 0) atomicAdd(&dbg[2], (unsigned long long)cnt);
   for (int e = lane; e < cnt; e += 32) {
     const uint4 hd = src[1 + 3 * e], q0 = src[2 + 3 * e], q1 = src[3 + 3 * e];
@@ -599,8 +605,15 @@ tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool
     const float v[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
                         __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
     const float4 qi = tq[i];                                   // (c_i, u_i, t_i)
-    long long dt = j0 / TC_BN - i / TC_BN; if (dt < 0) dt = -dt;
-    const bool col_on = !(dt == 0 || dt * 2 == n_tiles);        // else row-tested only: the pair appears in both orders already
+    // pairs of one tile block are multiplied circulantly inside the block: its diagonal tiles, and the opposite tiles of an
+    // even block length, hold both orders of their pairs themselves and were row-tested only
+    const long long ti = i / TC_BN, tj = j0 / TC_BN;
+    bool col_on = true;
+    if (ti / blk_tiles == tj / blk_tiles) {
+      const long long len = min(blk_tiles, n_tiles - (ti / blk_tiles) * blk_tiles);
+      long long dt = tj - ti; if (dt < 0) dt = -dt;
+      col_on = !(dt == 0 || dt * 2 == len);
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float sv = __fadd_rd(v[c], qi.x);
@@ -620,6 +633,7 @@ tc_transpose_kernel(const uint4* __restrict__ pool, const int* __restrict__ pool
         }
       }
     }
+  }
   }
 }
 
@@ -646,9 +660,11 @@ struct TcArgs {
   // slots -> rows (NULL: slot s of the launch is row row_lo + s); set when the query side is staged in position order
   const int32_t* slot_row;
   // FILTER_SYM: bt0 / n_btiles are the first circulant step and the number of steps of this launch; the CTA pair of
-  // query tile I multiplies reference tiles (I + step) mod n_tiles_total
-  long long n_tiles_total;
-  const float* t8;            // [n_tiles_total * 32] group maxima of the column thresholds
+  // query tile I of the tile block [blk_lo, blk_lo + blk_len) multiplies reference tiles blk_lo + (I - blk_lo + step) mod
+  // blk_len (circulant inside the block; the whole matrix is the block [0, T)), or -- sym_linear -- every pair of the
+  // launch walks the same tiles bt0, bt0 + 1, ... (a block of query tiles against a block of other reference tiles)
+  long long blk_lo, blk_len; int sym_linear;
+  const float* t8;            // [tiles * 32] group maxima of the column thresholds
   const float2* cu;           // [positions] (c, u)
   uint4* pool; int* pool_count; int pool_chunks; int* pool_fail;    // group-record pool (chunks of TC_POOL_STRIDE uint4)
 };
@@ -754,7 +770,7 @@ tc_kernel(const TcArgs p) {
     __syncwarp();
     const long long src_step = (long long)CG * BROWS * kpad;
     // FILTER_SYM: the pair of query tile I starts at reference tile (I + first step) mod T and wraps around
-    long long jt = MODE == TC_FILTER_SYM ? ((tile_m >> 1) + p.bt0) % p.n_tiles_total : p.bt0;
+    long long jt = (MODE == TC_FILTER_SYM && !p.sym_linear) ? p.blk_lo + ((tile_m >> 1) - p.blk_lo + p.bt0) % p.blk_len : p.bt0;
     const __half* src = p.b_tiles + (CG * jt + cta_rank) * (long long)BROWS * kpad;
     int stage = 0; uint32_t phase = 0;
     int tslot = 0;
@@ -768,7 +784,7 @@ tc_kernel(const TcArgs p) {
       __syncwarp();
       src += src_step;
       if (MODE == TC_FILTER_SYM) {
-        if (++jt == p.n_tiles_total) { jt = 0; src = p.b_tiles + (long long)cta_rank * BROWS * kpad; }
+        if (++jt == p.blk_lo + p.blk_len && !p.sym_linear) { jt = p.blk_lo; src = p.b_tiles + (CG * jt + cta_rank) * (long long)BROWS * kpad; }
         if (++tslot == TC_T8_SLOTS) tslot = 0;
       }
       if (++stage == p.nstage) { stage = 0; phase ^= 1; }
@@ -874,7 +890,7 @@ tc_kernel(const TcArgs p) {
         const float2 cui = p.cu[slot];
         cadd = cui.x; trow = __fadd_ru(thr, cui.y);
       }
-      jt_sym = (int)(((tile_m >> 1) + p.bt0) % p.n_tiles_total);
+      jt_sym = p.sym_linear ? (int)p.bt0 : (int)(p.blk_lo + ((tile_m >> 1) - p.blk_lo + p.bt0) % p.blk_len);
       new_chunk();
     }
     int probe_hits = 0;
@@ -912,10 +928,10 @@ tc_kernel(const TcArgs p) {
         // tile are sorted by threshold (tc_sort_tiles_kernel), so that maximum is close to every t_j of its group.
         const int step = (int)p.bt0 + (int)t;
         const int jt = jt_sym;
-        if (++jt_sym == (int)p.n_tiles_total) jt_sym = 0;
+        if (++jt_sym == (int)(p.blk_lo + p.blk_len) && !p.sym_linear) jt_sym = (int)p.blk_lo;
         // the diagonal tile holds both orders of every pair already; for an even tile count the opposite tile is
         // multiplied by both of its pairs: row test only in either case
-        const bool col_on = step > 0 && step * 2 != (int)p.n_tiles_total;
+        const bool col_on = p.sym_linear || (step > 0 && step * 2 != (int)p.blk_len);
         tmem_ld32(taddr, va);
         tmem_ld32(taddr + 32, vb);
         tmem_ld_wait();
@@ -1203,7 +1219,7 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
     st->t8 = a.take<float>((size_t)p.n_tiles * TC_TT_FLOATS);
     st->pool_chunks = tc_pool_chunks(p, n_ref);
     st->pool = a.take<uint4>((size_t)st->pool_chunks * TC_POOL_STRIDE);
-    st->pool_count = a.take<int>(64);                    // [0] chunks handed out, [1] pool exhausted
+    st->pool_count = a.take<int>(64);                    // [0] chunks handed out, [1] chunks taken by the transpose, [2] pool exhausted
   }
 }
 
@@ -1414,33 +1430,98 @@ int tc_filter_chunk(TcState* st, const TcPlan& p, long long row0, long long n_ro
 // The steps are cut into launches (a) at 1/14, 1/7 and 2/7 of T, after which every row has seen a window of 1/7, 2/7
 // and 4/7 of the (pseudo-randomly ordered) references around its own tile -- the same threshold refinement as the
 // one-sided filter -- and (b) so that the reference tiles a launch walks stay L2-resident.
-int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound,
-                  int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+// ---- pieces shared by the two schedules of the symmetric filter ----
+static void tc_sym_args(TcState* st, const TcPlan& p, uint2* cand, int32_t* cand_count, TcArgs& a) {
+  long long n_mtiles;
+  tc_chunk_args(st, p, 0, st->n_ref, a, n_mtiles);
+  a.cand = cand; a.cand_count = cand_count; a.b_tiles = st->b_tiles;
+  a.blk_lo = 0; a.blk_len = p.n_tiles; a.sym_linear = 0; a.t8 = st->t8; a.cu = st->cu;
+  a.pool = st->pool; a.pool_count = st->pool_count; a.pool_chunks = st->pool_chunks; a.pool_fail = st->pool_count + 2;
+}
+static long long tc_sym_max_steps(const TcPlan& p) {
+  static const long long l2_bytes = (long long)tc_env_int("SBK_TC_L2_MB", (int)(TC_L2_CHUNK_BYTES >> 20)) << 20;
+  return std::max<long long>(16, l2_bytes / (long long)p.stage_bytes);
+}
+// one filter launch over query tiles [q_lo, q_lo + q_len) and the transposes of its records
+static int tc_sym_launch(TcState* st, const TcPlan& p, TcArgs& a, long long q_lo, long long q_len, long long blk_tiles,
+                         uint2* cand, int32_t* cand_count, int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+  a.tile_m0 = 2 * q_lo;
+  int rc = tc_launch_cg<TC_FILTER_SYM, 2, 1>(a, 2 * q_len, stream);
+  if (rc) return rc;
+  if (n_launches) ++*n_launches;
+  unsigned long long* dbg = nullptr;
+#ifdef SBK_ENABLE_PROBES
+  static const int sym_debug = tc_env_int("SBK_SYM_DEBUG", 0);
+  if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
+#endif
+  tc_transpose_kernel<<<(unsigned)std::min((st->pool_chunks + 7) / 8, 148 * 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, st->n_ref, p.n_tiles,
+                                                                                blk_tiles, st->tq, cand, cand_count, p.cand_cap, dbg);
+  SBK_LAUNCH_CHECK();
+  SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, 2 * sizeof(int), stream));  // chunks handed out, chunks transposed; [2], the exhaustion flag, stays
+#ifdef SBK_ENABLE_PROBES
+  if (sym_debug) {
+    unsigned long long h[4];
+    SBK_CUDA_CHECK(cudaMemcpyAsync(h, dbg, 32, cudaMemcpyDeviceToHost, stream));
+    SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+    fprintf(stderr, "sym launch: query tiles [%lld,%lld) %s first %lld count %lld: list-segment overflows %llu, group records %llu, pool of %d chunks\n",
+            q_lo, q_lo + q_len, a.sym_linear ? "x tiles" : "circulant steps", a.bt0, a.n_btiles, h[1], h[2], st->pool_chunks);
+  }
+#endif
+  if (n_aux_launches) ++*n_aux_launches;
+  return SBK_OK;
+}
+// threshold refinement of the positions [slot_lo, slot_hi) that have seen the fraction f of the references, then the
+// column thresholds of everything
+static int tc_sym_refine(TcState* st, const TcPlan& p, int k, double f, long long slot_lo, long long slot_hi,
+                         uint2* cand, int32_t* cand_count, double* bound, int* n_aux_launches, cudaStream_t stream) {
+  static const int refine = tc_env_int("SBK_TC_REFINE", 1);
+  const int r = binom_quantile(k, f, 2e-6) + 1;
+  if (!refine || !(f < 1.0) || r > TC_REFINE_MAX / 2 || slot_hi <= slot_lo) return SBK_OK;
+  const long long ns = slot_hi - slot_lo;
+  tc_refine_kernel<<<(unsigned)((ns + 7) / 8), 256, 0, stream>>>(cand + slot_lo * p.cand_cap, cand_count + slot_lo * 4, p.cand_cap, 0, ns, r,
+                                                                st->norms4, st->nrm, st->scale, p.kpad, st->d, st->thr + slot_lo,
+                                                                bound + slot_lo, st->orig + slot_lo);
+  SBK_LAUNCH_CHECK();
+  tc_colthr_kernel<<<(unsigned)p.n_tiles, 256, 0, stream>>>(st->thr, st->cu, st->n_ref, st->t8, st->tq);
+  SBK_LAUNCH_CHECK();
+  if (n_aux_launches) *n_aux_launches += 2;
+  return SBK_OK;
+}
+
+int tc_sym_begin(TcState* st, const TcPlan& p, uint2* cand, int32_t* cand_count, double* bound, int* n_aux_launches,
+                 cudaStream_t stream) {
   if (!st->sym || st->cg != 2) { set_error("tensor kNN: state not prepared for the symmetric filter"); return SBK_ERR_INTERNAL; }
   const long long n = st->n_ref, T = p.n_tiles;
-  TcArgs a; long long n_mtiles;
-  tc_chunk_args(st, p, 0, n, a, n_mtiles);
-  a.cand = cand; a.cand_count = cand_count; a.b_tiles = st->b_tiles;
-  a.n_tiles_total = T; a.t8 = st->t8; a.cu = st->cu;
-  a.pool = st->pool; a.pool_count = st->pool_count; a.pool_chunks = st->pool_chunks; a.pool_fail = st->pool_count + 1;
-  n_mtiles = 2 * T;                                            // every CTA pair exists, padding rows included
   SBK_CUDA_CHECK(cudaMemsetAsync(cand_count, 0, (size_t)n * 4 * sizeof(int32_t), stream));
   SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, 64 * sizeof(int), stream));
   // positions of every tile in descending-threshold order, then the column thresholds of that order
-  {
-    const size_t sm = (size_t)TC_BN * p.kpad * 2;
-    SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    tc_sort_tiles_kernel<<<(unsigned)T, 256, sm, stream>>>(n, p.kpad, st->a_tiles, st->b_tiles, st->thr, bound, st->cu, st->orig, st->rpos);
-    SBK_LAUNCH_CHECK();
-  }
-  const unsigned cgrid = (unsigned)T;
-  tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
+  const size_t sm = (size_t)TC_BN * p.kpad * 2;
+  SBK_CUDA_CHECK(cudaFuncSetAttribute(tc_sort_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  tc_sort_tiles_kernel<<<(unsigned)T, 256, sm, stream>>>(n, p.kpad, st->a_tiles, st->b_tiles, st->thr, bound, st->cu, st->orig, st->rpos);
+  SBK_LAUNCH_CHECK();
+  tc_colthr_kernel<<<(unsigned)T, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
   SBK_LAUNCH_CHECK();
   if (n_aux_launches) *n_aux_launches += 2;
+  return SBK_OK;
+}
+
+int tc_sym_end(TcState* st, cudaStream_t stream) {
+  // a launch that ran out of pool chunks lost group records: the caller redoes the build with the one-sided filter
+  int h_fail = 0;
+  SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fail, st->pool_count + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return h_fail ? TC_SYM_POOL_EXHAUSTED : SBK_OK;
+}
+
+int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound,
+                  int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+  int rc = tc_sym_begin(st, p, cand, cand_count, bound, n_aux_launches, stream);
+  if (rc) return rc;
+  const long long n = st->n_ref, T = p.n_tiles;
+  TcArgs a;
+  tc_sym_args(st, p, cand, cand_count, a);
   const long long n_steps = T / 2 + 1;                         // steps 0 .. floor(T/2)
-  static const long long l2_bytes = (long long)tc_env_int("SBK_TC_L2_MB", (int)(TC_L2_CHUNK_BYTES >> 20)) << 20;
-  const long long max_steps = std::max<long long>(16, l2_bytes / (long long)p.stage_bytes);
-  static const int refine = tc_env_int("SBK_TC_REFINE", 1);
+  const long long max_steps = tc_sym_max_steps(p);
   // launch boundaries: the refinement points, then an even split of whatever is still longer than max_steps
   std::vector<long long> cuts;
   std::vector<char> refine_at;
@@ -1462,49 +1543,64 @@ int tc_filter_sym(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* can
   long long s0 = 0;
   for (size_t li = 0; li < cuts.size(); ++li) {
     a.bt0 = s0; a.n_btiles = cuts[li] - s0;
-    int rc = tc_launch_cg<TC_FILTER_SYM, 2, 1>(a, n_mtiles, stream);
+    rc = tc_sym_launch(st, p, a, 0, T, T, cand, cand_count, n_launches, n_aux_launches, stream);
     if (rc) return rc;
-    if (n_launches) ++*n_launches;
-    unsigned long long* dbg = nullptr;
-#ifdef SBK_ENABLE_PROBES
-    static const int sym_debug = tc_env_int("SBK_SYM_DEBUG", 0);
-    if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
-#endif
-    tc_transpose_kernel<<<(unsigned)((st->pool_chunks + 7) / 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, n, T, st->tq,
-                                                                                  cand, cand_count, p.cand_cap, dbg);
-    SBK_LAUNCH_CHECK();
-    SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, sizeof(int), stream));      // [1], the exhaustion flag, stays
-    SBK_LAUNCH_CHECK();
-#ifdef SBK_ENABLE_PROBES
-    if (sym_debug) {
-      unsigned long long h[4];
-      SBK_CUDA_CHECK(cudaMemcpyAsync(h, dbg, 32, cudaMemcpyDeviceToHost, stream));
-      SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
-      fprintf(stderr, "sym launch %zu steps [%lld,%lld): list-segment overflows %llu, pair records %llu, pool of %d chunks\n",
-              li, s0, cuts[li], h[1], h[2], st->pool_chunks);
-    }
-#endif
-    if (n_aux_launches) ++*n_aux_launches;
     s0 = cuts[li];
-    if (refine && refine_at[li] && s0 < n_steps) {
+    if (refine_at[li] && s0 < n_steps) {
       // rows of tile I have now seen tiles I-s0+1 .. I+s0-1
-      const double f = std::min(1.0, (double)(2 * s0 - 1) * TC_BN / (double)n);
-      const int r = binom_quantile(k, f, 2e-6) + 1;
-      if (r <= TC_REFINE_MAX / 2 && f < 1.0) {
-        tc_refine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(cand, cand_count, p.cand_cap, 0, n, r, st->norms4, st->nrm, st->scale,
-                                                                     p.kpad, st->d, st->thr, bound, st->orig);
-        SBK_LAUNCH_CHECK();
-        tc_colthr_kernel<<<cgrid, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
-        SBK_LAUNCH_CHECK();
-        if (n_aux_launches) *n_aux_launches += 2;
-      }
+      rc = tc_sym_refine(st, p, k, std::min(1.0, (double)(2 * s0 - 1) * TC_BN / (double)n), 0, n, cand, cand_count, bound,
+                         n_aux_launches, stream);
+      if (rc) return rc;
     }
   }
-  // a launch that ran out of pool chunks lost pair records: the caller redoes the build with the one-sided filter
-  int h_fail = 0;
-  SBK_CUDA_CHECK(cudaMemcpyAsync(&h_fail, st->pool_count + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-  SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
-  if (h_fail) return TC_SYM_POOL_EXHAUSTED;
+  return tc_sym_end(st, stream);
+}
+
+// Block-row schedule of the symmetric filter (host-buffer builds): the T tiles are cut into n_blocks blocks; block row r
+// multiplies the pairs (block r, block c >= r) -- its own block circulantly, the later blocks tile by tile -- after
+// which every pair that involves a row of block r has been multiplied: the rows of block r are FINISHED and can be
+// reranked and downloaded while the later block rows are multiplied.  (In the whole-matrix circulant no row is finished
+// before the last launch, and a 3.2 GB download would start when the GPU has nothing left to hide it behind.)
+// Thresholds: block 0 refines after its own block (it has seen 1/n_blocks of the references); at the start of block row
+// r >= 1 all unfinished rows have seen the blocks before r completely and are refined with f = r / n_blocks.
+// (a block is a whole number of waves of CTA pairs, 74 on a B200, so that only the last launch of a block row has a ragged tail)
+long long tc_sym_block_tiles(const TcPlan& p, int n_blocks) {
+  const long long tb = (p.n_tiles + n_blocks - 1) / n_blocks;
+  return tb >= 74 ? (tb + 73) / 74 * 74 : tb;
+}
+
+int tc_sym_block(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound, int n_blocks, int r,
+                 int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+  const long long n = st->n_ref, T = p.n_tiles, tb = tc_sym_block_tiles(p, n_blocks);
+  const long long lo = (long long)r * tb, len = std::min(tb, T - lo);
+  if (len <= 0) return SBK_OK;
+  TcArgs a;
+  tc_sym_args(st, p, cand, cand_count, a);
+  const long long max_steps = tc_sym_max_steps(p);
+  int rc;
+  if (r > 0) {
+    rc = tc_sym_refine(st, p, k, (double)lo / (double)T, lo * TC_BN, n, cand, cand_count, bound, n_aux_launches, stream);
+    if (rc) return rc;
+  }
+  // own block, circulant inside it
+  a.blk_lo = lo; a.blk_len = len; a.sym_linear = 0;
+  const long long n_steps = len / 2 + 1;
+  for (long long s0 = 0; s0 < n_steps; s0 += max_steps) {
+    a.bt0 = s0; a.n_btiles = std::min(max_steps, n_steps - s0);
+    rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream);
+    if (rc) return rc;
+  }
+  if (r == 0 && lo + len < T) {
+    rc = tc_sym_refine(st, p, k, (double)len / (double)T, 0, std::min(n, len * TC_BN), cand, cand_count, bound, n_aux_launches, stream);
+    if (rc) return rc;
+  }
+  // the later blocks, tile by tile (every pair of the launch walks the same tiles)
+  a.sym_linear = 1;
+  for (long long j0 = lo + len; j0 < T; j0 += max_steps) {
+    a.bt0 = j0; a.n_btiles = std::min(max_steps, T - j0);
+    rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream);
+    if (rc) return rc;
+  }
   return SBK_OK;
 }
 

@@ -169,6 +169,43 @@ def test_rerank_warp_and_block_paths_agree():
     assert st['n_retry_rows'] + st['n_fallback_rows'] >= 20 * 400, st
 
 
+def test_symmetric_block_row_build_streams_to_host():
+    """Host-buffer builds of all rows through the symmetric filter run block row by block row: every block of rows is
+    reranked and written straight into the (pinned, mapped) host arrays while the later block rows are multiplied.  Both
+    host forms (the csr_matrix arrays of kneighbors_graph; the f32 / i32 buffers of knn_host), float32 and float64
+    input, a tile count that is not a multiple of the 8 blocks, rows that need the exact fallback -- equal to the
+    device-resident exact path."""
+    import torch
+    from semibin_b200.neighbors import knn, kneighbors_graph, knn_host
+    N, k = 41000, 50
+    X = synth.embeddings(N, seed=41)
+    d0, i0 = knn(torch.from_numpy(X).cuda(), k, algo='exact')
+    g, st = kneighbors_graph(X, k, algo='tensor_symmetric', return_stats=True)
+    assert st['symmetric'] == 1 and st['n_chunks'] == 8, st
+    np.testing.assert_array_equal(g.indices.reshape(N, k), i0.cpu().numpy())
+    np.testing.assert_array_equal(g.data.reshape(N, k), d0.cpu().numpy().astype(np.float64))
+    hd, hi, sth = knn_host(torch.from_numpy(X).pin_memory(), k, algo='tensor_symmetric', return_stats=True)
+    assert sth['symmetric'] == 1
+    np.testing.assert_array_equal(hi.numpy(), i0.cpu().numpy())
+    np.testing.assert_array_equal(hd.numpy(), d0.cpu().numpy())
+    # near-duplicate rows: lists overflow / certificates fail for some rows, which are recomputed and re-sent at the end
+    Xd = X.copy(); Xd[5000:5400] = Xd[0] + 1e-7 * np.arange(400, dtype=np.float32)[:, None]
+    d1, i1 = knn(torch.from_numpy(Xd).cuda(), k, algo='exact')
+    g1, st1 = kneighbors_graph(Xd, k, algo='tensor_symmetric', return_stats=True)
+    np.testing.assert_array_equal(g1.indices.reshape(N, k), i1.cpu().numpy())
+    np.testing.assert_array_equal(g1.data.reshape(N, k), d1.cpu().numpy().astype(np.float64))
+    F = synth.kmer_features(30000, seed=41)                      # float64: distances are downloaded as they are
+    df, jf = knn(torch.from_numpy(F).cuda(), 20, algo='exact')
+    gf, stf = kneighbors_graph(F, 20, algo='tensor_symmetric', return_stats=True)
+    assert stf['symmetric'] == 1
+    np.testing.assert_array_equal(gf.data.reshape(30000, 20), df.cpu().numpy())
+    np.testing.assert_array_equal(gf.indices.reshape(30000, 20), jf.cpu().numpy())
+    # pageable host outputs cannot be written by the device: the call falls back to the chunked copies
+    pd_, pi_ = torch.empty((N, k), dtype=torch.float32), torch.empty((N, k), dtype=torch.int32)
+    knn_host(torch.from_numpy(X).pin_memory(), k, algo='tensor_symmetric', out_dist=pd_, out_idx=pi_)
+    np.testing.assert_array_equal(pi_.numpy(), i0.cpu().numpy())
+
+
 def test_kneighbors_graph_host_arrays_and_devices():
     """The sklearn-signature drop-in: csr_matrix over pinned (float64, int64) arrays written by the device, equal to
     the device-resident call; with two devices in ONE process (skipped on a single-GPU box) the result is bytewise
