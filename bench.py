@@ -368,8 +368,10 @@ def run_ours(args):
                     'd2h_bytes_per_step': int(n * k * 16),
                     'api': "semibin_b200.neighbors.kneighbors_graph(X_numpy, 200, mode='distance', p=2) -> scipy csr_matrix "
                            '(the call at SemiBin/cluster.py:94-99), one process driving all N GPUs (devices=N / SBK_DEVICES): numpy '
-                           'matrix over pinned host memory in, device-widened (float64, int64) row chunks downloaded into the pinned arrays of the '
-                           'csr_matrix while the next chunk is computed',
+                           'matrix over pinned host memory in; one GPU: the symmetric build finishes its rows block row by block row and a '
+                           'zero-copy scatter kernel writes every finished block as (float64, int64) into the pinned arrays of the '
+                           'csr_matrix while later block rows are multiplied; several GPUs: device-widened row chunks downloaded '
+                           'while the next chunk is computed',
                     'host_split_ms': {'alloc_result': g_stats['host_ms']['alloc_result'], 'build': g_stats['host_ms']['build'],
                                       'upload': g_stats.get('upload_ms'),
                                       'per_device': {str(dv): {q: round(v, 2) for q, v in ds.items() if isinstance(v, float)}
