@@ -120,49 +120,48 @@ def recluster_labels(embedding_new, contig_labels, seeds_by_bin, lengths, total_
     return out
 
 
+def _recluster_features(data, embedding, n_sample, is_combined):
+    """cluster.py:184-195: in single-sample / multi-sample mode the embedding is extended by the per-sample mean depths,
+    each divided by its sample's scale (mean depth rounded up to the next hundred) and multiplied by one common integer
+    weight that brings them to the magnitude of the embedding; combined mode re-clusters the embedding alone."""
+    if is_combined:
+        return embedding
+    depth = data.values[:, 136:].astype(np.float32)
+    mean_depth = depth[:, 0:2 * n_sample:2]                      # (mean, variance) pairs per sample: the means
+    mean_depth = mean_depth / (np.ceil(mean_depth.mean(axis=0) / 100) * 100)
+    ratio = np.mean(np.abs(embedding)) / np.mean(mean_depth)
+    weight = 20 * math.ceil(ratio / 10)
+    return np.concatenate((embedding, mean_depth * weight), axis=1)
+
+
 def recluster_bins(logger, data, *, n_sample, embedding, is_combined: bool, contig_labels, minfasta, contig_dict,
                    binned_length, orf_finder, num_process, random_seed, estimate_seeds=None):
     """Same signature and results as SemiBin.cluster.recluster_bins (cluster.py:171-255); `random_seed` is accepted and,
     as in the reference (array init, n_init=1), changes nothing."""
     if estimate_seeds is None:
         from SemiBin.markers import estimate_seeds
-    embedding = np.asarray(embedding)
-    if not is_combined:                                            # :185-195
-        depth = data.values[:, 136:len(data.values[0])].astype(np.float32)
-        mean_index = [2 * temp for temp in range(n_sample)]
-        depth_mean = depth[:, mean_index]
-        abun_scale = np.ceil(depth_mean.mean(axis=0) / 100) * 100
-        depth_mean = depth_mean / abun_scale
-        scaling = np.mean(np.abs(embedding)) / np.mean(depth_mean)
-        base = 10
-        weight = 2 * base * math.ceil(scaling / base)
-        embedding_new = np.concatenate((embedding, depth_mean * weight), axis=1)
-    else:
-        embedding_new = embedding
+    features = _recluster_features(data, np.asarray(embedding), n_sample, is_combined)
     contig_labels = np.asarray(contig_labels)
-    lengths = np.array([len(contig_dict[h]) for h in data.index], dtype=np.int64)
-    total_size = defaultdict(int)
-    for c, ell in zip(contig_labels, lengths):
-        total_size[c] += int(ell)
-    with tempfile.TemporaryDirectory() as tdir:                    # :202-214: seeds from the concatenated bins
+    names = list(data.index)
+    lengths = np.fromiter((len(contig_dict[h]) for h in names), dtype=np.int64, count=len(names))
+    bases = np.bincount(contig_labels, weights=lengths, minlength=int(contig_labels.max()) + 1).astype(np.int64)
+    total_size = defaultdict(int, {b: int(v) for b, v in enumerate(bases)})
+    big_enough = bases[contig_labels] >= minfasta               # :197-205: only bins of at least minfasta bases are searched
+    with tempfile.TemporaryDirectory() as tdir:
         cfasta = os.path.join(tdir, 'concatenated.fna')
-        with open(cfasta, 'wt') as concat_out:
-            for ix, h in enumerate(data.index):
-                bin_ix = contig_labels[ix]
-                if total_size[bin_ix] < minfasta:
-                    continue
-                concat_out.write(f'>bin{bin_ix:06}.{h}\n')
-                concat_out.write(contig_dict[h] + '\n')
+        with open(cfasta, 'wt') as fh:
+            fh.writelines(f'>bin{contig_labels[ix]:06}.{h}\n{contig_dict[h]}\n' for ix, h in enumerate(names) if big_enough[ix])
+        # the ORF finder cannot be bypassed: the contigs were renamed (:213)
         seeds = estimate_seeds(cfasta, binned_length, num_process, multi_mode=True, orf_finder=orf_finder)
-        if not seeds:
-            logger.warning('No bins found in the concatenated fasta file.')
-            return contig_labels
+    if not seeds:
+        logger.warning('No bins found in the concatenated fasta file.')
+        return contig_labels
     name2ix = {name: ix for ix, name in enumerate(data.index)}
     seeds_by_bin = {}
     for b in range(int(contig_labels.max()) + 1):
         seed = seeds.get(f'bin{b:06}', [])
         if len(seed) > 1:
             seeds_by_bin[b] = [name2ix[s] for s in seed]
-    out = recluster_labels(embedding_new, contig_labels, seeds_by_bin, lengths, total_size, minfasta)
+    out = recluster_labels(features, contig_labels, seeds_by_bin, lengths, total_size, minfasta)
     assert out.min() >= 0
     return out
