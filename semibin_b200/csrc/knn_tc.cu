@@ -163,6 +163,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Pure polling wait (no suspend) for the single-warp roles on the tensor pipe's critical path.
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {
+  unsigned long long t0 = 0;
+  for (;;) {
+#pragma unroll 1
+    for (int n = 0; n < 0x10000; ++n) if (mbar_test(bar, parity)) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000ull) { printf("sbk: mbarrier spin timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -910,7 +922,11 @@ tc_kernel(const TcArgs p) {
 #pragma unroll
       for (int h = 0; h < NH; ++h, ++sidx) {
       const int as = (int)(sidx % NS);
-      mbar_wait(&tfull_bar[as], (uint32_t)((sidx / NS) & 1));
+      // the symmetric epilogue polls (no suspend): its warps wait for the MMA most of the time and the wake-up of a
+      // suspended try_wait sits on the accumulator release path (121.8 -> 118.5 ms at 1M; the busier one-sided epilogue
+      // lost 8 ms with polling, and polling in the MMA issuer changed nothing)
+      if (MODE == TC_FILTER_SYM) mbar_spin(&tfull_bar[as], (uint32_t)((sidx / NS) & 1));
+      else mbar_wait(&tfull_bar[as], (uint32_t)((sidx / NS) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * SN + w4 * WC);
       if (MODE == TC_PROBE_NOLD) {
