@@ -1,4 +1,5 @@
-"""Symmetric filter: stats and parity against the one-sided filter at growing sizes (debug aid, run under gpurun)."""
+"""Symmetric against one-sided filter at growing sizes: stage times, candidate counts, fallback rows and bitwise
+equality of the two results (run under gpurun: python scripts/compare_filters.py 200000 1000000)."""
 import sys, time, json
 import numpy as np, torch
 sys.path.insert(0, '.')

@@ -5,6 +5,6 @@ tail -25 gpurun_out/${tag}_pytest.log
 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err; tail -3 gpurun_out/${tag}_bench.err
 python - <<'PY'
 import json
-j=json.loads(open('gpurun_out/blk1_bench.json').read().strip().splitlines()[-1])
+j=json.loads(open('gpurun_out/${tag}_bench.json').read().strip().splitlines()[-1])
 print({k:j[k] for k in ('value','ms_per_step','stages_ms')}, {k:v for k,v in j['e2e'].items() if k!='api'}, j.get('cpu_baseline'))
 PY
