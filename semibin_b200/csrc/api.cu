@@ -24,6 +24,7 @@ void set_error(const char* fmt, ...) {
 static constexpr int KNN_MAX_K = 1023;
 static constexpr long long EXACT_CHUNK = 1 << 18;       // query rows per chunk (exact path)
 static constexpr long long TC_MIN_N = 16384;            // AUTO switches to the tensor path above this
+static constexpr double SYM_ROOMY_LIST_BYTES = 56e9;     // symmetric build: candidate lists may take this much when doubled
 static constexpr int SYM_SINK_BLOCKS = 8;               // block rows of the symmetric build when the result streams to host memory
 
 // Profiling switches exist only in the probe build (-DSBK_ENABLE_PROBES, libsbk_probe.so): the product library
@@ -87,7 +88,15 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     // lists of all rows are then live at once, so the whole call is one filter "chunk"
     // (below ~400k rows its extra launches, record transposes and refinements cost what the halved tensor work saves)
     s.sym = !onesided && n_q == n_ref && s.tcap > 0 && tc_sym_supported(s.plan, n_ref) && (force_sym || s.plan.n_tiles >= TC_SYM_MIN_TILES);
-    if (s.sym) s.chunk = n_q;
+    if (s.sym) {
+      s.chunk = n_q;
+      // Lists of all rows are resident anyway: give every row twice the planned room when that still fits.  Rows of
+      // genomes with thousands of contigs (every cluster mate passes the threshold) then go through the block rerank
+      // instead of overflowing into the FP64 fallback (2 011 rows = 70 ms in the large-genome mix at 1M).
+      const int cap2 = 2 * s.plan.cand_cap;
+      if ((double)n_ref * (double)cap2 * 8.0 <= SYM_ROOMY_LIST_BYTES && cap2 <= 8192) s.plan.cand_cap = cap2;
+      s.cand_stride = s.plan.cand_cap;
+    }
     s.retry_cap = s.tcap ? std::max<long long>(8192, s.chunk / 4) : 0;
   }
   return s;

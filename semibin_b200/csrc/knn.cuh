@@ -59,6 +59,7 @@ struct TcPlan {
   int order_stat;      // r: threshold = r-th smallest group minimum
   int n_groups;        // G
   int cand_cap;        // candidate slots per query row
+  int cand_cap_planned; // what the expected candidate count asks for (the symmetric build may be given more room)
   size_t stage_bytes;  // bytes of one staged reference tile
 };
 static constexpr int TC_BM = 128;   // query rows per CTA

@@ -1187,6 +1187,7 @@ TcPlan tc_make_plan(long long n_ref, int d, int k) {
   double seg = tot / 4.0 + 6.0 * sqrt(tot / 4.0) + 16.0;
   seg = std::min(seg, 2048.0);
   p.cand_cap = 4 * ((int)((seg + 63) / 64) * 64);
+  p.cand_cap_planned = p.cand_cap;
   return p;
 }
 
@@ -1201,7 +1202,7 @@ long long tc_chunk_rows(const TcPlan& p, long long n_ref) {
 // records of the busiest launch (sized for an eighth of the planned list capacity of every row: the first launches run on
 // the loosest thresholds, 3-4x the measured volume at 200k and 1M rows)
 static int tc_pool_chunks(const TcPlan& p, long long n_ref) {
-  const double recs = (double)n_ref * (double)p.cand_cap / 8.0;
+  const double recs = (double)n_ref * (double)p.cand_cap_planned / 8.0;
   const double c = 32.0 * (double)p.n_tiles + recs / TC_POOL_CH + 1024.0;
   return (int)std::min(c, 3.0e6);
 }
