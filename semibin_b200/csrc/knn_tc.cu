@@ -44,6 +44,7 @@
 #include <math.h>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 #include <string.h>
 #include <stdlib.h>
 
@@ -493,16 +494,30 @@ tc_refine_kernel(const uint2* __restrict__ cand, const int32_t* __restrict__ can
       key[u] = tc_f2ord(__uint_as_float(base[(long long)sgm * seg_cap + e].y));
     }
   }
-  // r-th smallest key = the largest v with #(keys < v) < r, built bit by bit
-  uint32_t res = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t t = res | (1u << bit);
-    int cnt = 0;
+  // r-th smallest key = the largest v with #(keys < v) < r, built bit by bit -- only over the bits in which the row's
+  // keys differ at all (they share their leading bits: 32 -> ~20 dependent steps) and only over the key registers the
+  // row fills (lists of 100-300 entries after the first launches, not 512)
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
 #pragma unroll
-    for (int u = 0; u < TC_REFINE_MAX / 32; ++u) cnt += key[u] < t ? 1 : 0;
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (cnt < r_stat) res = t;
-  }
+  for (int u = 0; u < TC_REFINE_MAX / 32; ++u) { kmin = min(kmin, key[u]); if (lane + 32 * u < n) kmax = max(kmax, key[u]); }
+  kmin = __reduce_min_sync(0xffffffffu, kmin); kmax = __reduce_max_sync(0xffffffffu, kmax);
+  const int hb = 31 - __clz(kmin ^ kmax);                    // -1: all keys equal
+  uint32_t res = hb >= 31 ? 0u : (kmin & ~((2u << hb) - 1u));
+  if (hb < 0) res = kmin;
+  auto select = [&](auto nk_tag) {
+    constexpr int NK = decltype(nk_tag)::value;
+    for (int bit = hb; bit >= 0; --bit) {
+      const uint32_t t = res | (1u << bit);
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < NK; ++u) cnt += key[u] < t ? 1 : 0;
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt < r_stat) res = t;
+    }
+  };
+  if (n <= 128) select(std::integral_constant<int, 4>());
+  else if (n <= 256) select(std::integral_constant<int, 8>());
+  else select(std::integral_constant<int, TC_REFINE_MAX / 32>());
   if (lane == 0) {
     const long long grow = slot_row ? (long long)slot_row[slot] : row_lo + slot;
     float thr_new; double bound_new;
