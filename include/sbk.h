@@ -58,7 +58,9 @@ typedef enum sbk_knn_algo {
                                     (q_begin = 0, q_end = n_ref) of at least ~400k rows uses the symmetric self-join
                                     filter: every tile product serves both of its row sets, half the tensor work */
   SBK_KNN_TENSOR_ONESIDED = 3,   /* the same, but never the symmetric filter (row blocks always run one-sided) */
-  SBK_KNN_TENSOR_SYMMETRIC = 4   /* the same, symmetric filter whenever the call covers all rows (any size >= 2048 rows) */
+  SBK_KNN_TENSOR_SYMMETRIC = 4,  /* the same, symmetric filter whenever the call covers all rows (any size >= 2048 rows) */
+  SBK_KNN_TENSOR_SYMMETRIC_STARVED = 5  /* test hook: symmetric filter with a record pool of 48 chunks, so that the
+                                    pool-exhaustion path (the build is redone one-sided) can be exercised */
 } sbk_knn_algo;
 
 /* Filled (when non-NULL) after the call's work is complete; passing a non-NULL

@@ -12,9 +12,9 @@ PROBES = os.environ.get('SBK_LIB_VARIANT', '') == 'probe'
 LIB_PATH = os.path.join(HERE, 'libsbk_probe.so' if PROBES else 'libsbk.so')
 
 SBK_F32, SBK_F64 = 0, 1
-KNN_AUTO, KNN_EXACT, KNN_TENSOR, KNN_TENSOR_ONESIDED, KNN_TENSOR_SYMMETRIC = 0, 1, 2, 3, 4
+KNN_AUTO, KNN_EXACT, KNN_TENSOR, KNN_TENSOR_ONESIDED, KNN_TENSOR_SYMMETRIC, KNN_TENSOR_SYMMETRIC_STARVED = 0, 1, 2, 3, 4, 5
 ALGOS = {'auto': KNN_AUTO, 'exact': KNN_EXACT, 'tensor': KNN_TENSOR, 'tensor_onesided': KNN_TENSOR_ONESIDED,
-         'tensor_symmetric': KNN_TENSOR_SYMMETRIC}
+         'tensor_symmetric': KNN_TENSOR_SYMMETRIC, 'tensor_symmetric_starved': KNN_TENSOR_SYMMETRIC_STARVED}
 MAX_THRESHOLDS = 32
 
 

@@ -67,7 +67,8 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
   KnnShape s; memset(&s, 0, sizeof(s));
   const int k1 = k + 1;
   if (algo == SBK_KNN_AUTO) algo = (n_ref >= TC_MIN_N && (d + 5 + 15) / 16 * 16 <= 176) ? SBK_KNN_TENSOR : SBK_KNN_EXACT;
-  const bool onesided = algo == SBK_KNN_TENSOR_ONESIDED, force_sym = algo == SBK_KNN_TENSOR_SYMMETRIC;
+  const bool starved = algo == SBK_KNN_TENSOR_SYMMETRIC_STARVED;
+  const bool onesided = algo == SBK_KNN_TENSOR_ONESIDED, force_sym = algo == SBK_KNN_TENSOR_SYMMETRIC || starved;
   if (onesided || force_sym) algo = SBK_KNN_TENSOR;
   s.algo = algo;
   if (algo == SBK_KNN_EXACT) {
@@ -90,6 +91,7 @@ static KnnShape knn_shape(int dtype, long long n_ref, int d, long long n_q, int 
     s.sym = !onesided && n_q == n_ref && s.tcap > 0 && tc_sym_supported(s.plan, n_ref) && (force_sym || s.plan.n_tiles >= TC_SYM_MIN_TILES);
     if (s.sym) {
       s.chunk = n_q;
+      if (starved) s.plan.pool_limit = 48;          // test hook: the record pool runs dry in the first launch
       // Lists of all rows are resident anyway: give every row twice the planned room when that still fits.  Rows of
       // genomes with thousands of contigs (every cluster mate passes the threshold) then go through the block rerank
       // instead of overflowing into the FP64 fallback (2 011 rows = 70 ms in the large-genome mix at 1M).

@@ -60,6 +60,7 @@ struct TcPlan {
   int n_groups;        // G
   int cand_cap;        // candidate slots per query row
   int cand_cap_planned; // what the expected candidate count asks for (the symmetric build may be given more room)
+  int pool_limit;      // test hook: at most this many pool chunks (0 = sized for the build); forces the exhaustion fallback
   size_t stage_bytes;  // bytes of one staged reference tile
 };
 static constexpr int TC_BM = 128;   // query rows per CTA

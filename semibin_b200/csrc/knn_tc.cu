@@ -1203,6 +1203,7 @@ TcPlan tc_make_plan(long long n_ref, int d, int k) {
   seg = std::min(seg, 2048.0);
   p.cand_cap = 4 * ((int)((seg + 63) / 64) * 64);
   p.cand_cap_planned = p.cand_cap;
+  p.pool_limit = 0;
   return p;
 }
 
@@ -1250,6 +1251,7 @@ static void tc_carve(Arena& a, const TcPlan& p, long long n_ref, long long chunk
     st->tq = a.take<float4>((size_t)n_b);
     st->t8 = a.take<float>((size_t)p.n_tiles * TC_TT_FLOATS);
     st->pool_chunks = tc_pool_chunks(p, n_ref);
+    if (p.pool_limit > 0) st->pool_chunks = std::min(st->pool_chunks, p.pool_limit);
     st->pool = a.take<uint4>((size_t)st->pool_chunks * TC_POOL_STRIDE);
     st->pool_count = a.take<int>(64);                    // [0] chunks handed out, [1] chunks taken by the transpose, [2] pool exhausted
   }

@@ -156,6 +156,25 @@ def test_live_sklearn_sampled_rows_200k():
     assert i.min() >= 0 and i.max() < N
 
 
+def test_symmetric_pool_exhaustion_falls_back_to_onesided():
+    """A symmetric build whose record pool runs dry (test hook: 48 chunks) has lost group records; the call notices
+    (flag checked after the filter) and redoes the build one-sided -- device-resident and through the host-buffer
+    block-row schedule, where finished blocks had already been written out."""
+    import torch
+    from semibin_b200.neighbors import kneighbors_graph
+    n, k = 30000, 40
+    X = synth.embeddings(n, seed=20290)
+    d0, i0 = _gpu_knn(X, k, 'exact')
+    d1, i1, st = _gpu_knn(X, k, 'tensor_symmetric_starved', return_stats=True)
+    assert st['symmetric'] == 0 and st['algo_used'] == 2, st          # the one-sided rebuild reports itself
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0, d1)
+    g, stg = kneighbors_graph(X, k, algo='tensor_symmetric_starved', return_stats=True)
+    assert stg['symmetric'] == 0, stg
+    np.testing.assert_array_equal(g.indices.reshape(n, k), i0)
+    np.testing.assert_array_equal(g.data.reshape(n, k), d0)
+
+
 def test_default_symmetric_build_450k_vs_live_sklearn():
     """A build of all rows above ~400k rows takes the symmetric filter by default: sampled rows against live sklearn
     (float32 embedding, k = 100), plus the full-size properties.  (The float64 feature graph at that size:
