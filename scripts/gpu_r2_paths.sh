@@ -12,4 +12,4 @@ if [ -f scratch/emb_global_1000000.npy ]; then
 python bench.py --steps 3 --warmup 3 --embedding-file scratch/emb_global_1000000.npy > gpurun_out/${tag}_bench_globalmodel.json 2> gpurun_out/${tag}_bench_globalmodel.err
 fi
 for f in gpurun_out/${tag}_*.json; do echo "== $f"; head -c 2500 $f; echo; done
-tail -3 gpurun_out/${tag}_*.err
+for f in gpurun_out/${tag}_*.err; do tail -n 3 "$f"; done
