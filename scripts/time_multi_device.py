@@ -1,4 +1,5 @@
-"""Timing split of the single-process multi-device kneighbors_graph (debug aid, run under gpurun --gpus 2)."""
+"""Timing split of the single-process multi-device kneighbors_graph: python scripts/time_multi_device.py 1 2 8
+(run under gpurun --gpus N)."""
 import sys, time, json
 import numpy as np, torch
 sys.path.insert(0, '.')
@@ -6,7 +7,8 @@ from semibin_b200.neighbors import kneighbors_graph
 from semibin_b200.synth import embeddings as synth_embeddings
 n, k = 1000000, 200
 X = torch.from_numpy(synth_embeddings(n)).pin_memory().numpy()
-for devs in ([0], [0, 1], [0, 1]):
+counts = [int(a) for a in sys.argv[1:]] or [1, 2]
+for devs in [list(range(c)) for c in counts]:
     for it in range(3):
         t0 = time.perf_counter()
         g, st = kneighbors_graph(X, k, mode='distance', p=2, devices=devs, return_stats=True)
