@@ -98,8 +98,18 @@ def test_c3_edges_200k_sampled_rows_vs_oracle(combined):
     """a5-a10 at 200k contigs x 10 samples, k = 200: the edge list of 512 sampled rows against the restatement fed
     with LIVE SCIKIT-LEARN graphs of those rows (not the GPU's), weights within the derived bound; row maxima equal,
     so the max_node threshold (a function of the row-maximum counts, replayed on the host) is pinned too."""
+    _c3_sampled_rows(200000, combined)
+
+
+def test_c3_edges_1M_sampled_rows_vs_oracle():
+    """The same at the BASELINE size of C3 (1M contigs x 10 samples, KL weights): both kNN graphs come from the
+    symmetric filter here, the 28.6 M-edge list is compared on 512 sampled rows."""
+    _c3_sampled_rows(1000000, False)
+
+
+def _c3_sampled_rows(N, combined):
     from semibin_b200.cluster import build_edge_list, threshold_sequence, pick_threshold
-    N, k, S = 200000, 200, 10
+    k, S = 200, 10
     emb, feat, depth, L = synth.short_read_case(N, n_sample=S, seed=20243)
     F = _combined_features(feat, depth) if combined else feat
     max_node = 0.9
