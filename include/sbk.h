@@ -267,6 +267,23 @@ int sbk_kmeans_batch(const float* X, int64_t ld, int32_t d, const float* weight,
                      int32_t* labels, int32_t* n_iter, double* centers_out,
                      void* workspace, size_t ws_bytes, void* cuda_stream);
 
+/* Symmetric build of the whole kNN graph across the GPUs of one box, one process per GPU (north_star item 4 with the
+ * symmetric filter): GPU `rank` owns the staged positions of tile block `rank`, multiplies its own block, the following
+ * (world-1)/2 blocks and -- for an even world -- half of the opposite block, so that every pair of tiles is multiplied
+ * once across all GPUs.  Candidates it finds for rows of another GPU are stored straight into that GPU's mailbox (peer
+ * memory over NVLink) and merged there; every GPU reranks its own rows and stores each finished row into its own and
+ * every peer's full [n_ref, k] result (out_dist / out_idx, peer_dist / peer_idx: as sbk_knn_peers).
+ *   xchg[r]  : base of rank r's exchange buffer (sbk_knn_sym_shard_xchg_bytes each, same size on every rank, mapped into
+ *              this process: e.g. torch symmetric memory), r = 0 .. world-1, own buffer included
+ *   barrier  : called three times (after the sample thresholds, after every rank's own block, after the last tile pair);
+ *              must return once every rank has called it (the library synchronises its stream first)
+ * Returns SBK_ERR_INVALID when the symmetric filter does not take the build (the caller then shards by row blocks). */
+size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t d, int32_t k, int32_t world);
+int sbk_knn_sym_shard(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld, int32_t k,
+                      int32_t rank, int32_t world, void* const* xchg, void (*barrier)(void*), void* barrier_arg,
+                      void* out_dist, int32_t* out_idx, int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
+                      void* workspace, size_t ws_bytes, sbk_knn_stats* stats, void* cuda_stream);
+
 /* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
  * MMA pipeline as the tensor filter and returns the accumulator values
  *   L[i,j] <= S^2 d2_ij - nrm_i + norms4[i].w      (i < n_q, j < n_ref <= 65536)

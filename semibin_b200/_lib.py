@@ -53,6 +53,11 @@ SIGNATURES = {
     'sbk_knn_peers': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                 C.c_void_p, C.c_size_t, C.c_int, C.POINTER(KnnStats), C.c_void_p]),
+    'sbk_knn_sym_shard_xchg_bytes': (C.c_size_t, [C.c_int, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
+    'sbk_knn_sym_shard': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                    C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t,
+                                    C.POINTER(KnnStats), C.c_void_p]),
     'sbk_knn_stream': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_int,
                                  C.POINTER(KnnStats), C.c_void_p, C.c_void_p]),

@@ -283,11 +283,34 @@ static int sink_rows(const HostSink* sk, int dtype, int k, const void* od, const
   return SBK_OK;
 }
 
+// Sharded symmetric build (sbk_knn_sym_shard): this process is `rank` of `world` GPUs; xchg[r] = base of rank r's exchange
+// buffer (peer memory; same layout everywhere: thresholds of all positions, count_in[8], one outbox per destination rank);
+// barrier() returns once every rank has called it and the device work each rank enqueued before it is complete.
+struct ShardCtx { int rank, world; void* const* xchg; void (*barrier)(void*); void* barrier_arg; };
+static long long shard_mail_cap(const TcPlan& p, long long n_ref, int world) {
+  const long long c = n_ref * (long long)p.cand_cap_planned / (4ll * world * std::max(1, world / 2));
+  return std::max<long long>(c, 1 << 16);
+}
+static size_t shard_thr_bytes(const TcPlan& p) { return align_up((size_t)p.n_tiles * TC_BN * sizeof(float), 256); }
+
+// every rank hands its (refined) thresholds to all ranks and takes theirs: broadcast by peer stores, barrier, local copy
+struct ShardExchange { TcState* tcs; const TcPlan* plan; const ShardCtx* shard; float* const* xthr; long long n_q; cudaStream_t stream; };
+static int shard_exchange_thr(void* arg) {
+  ShardExchange* x = static_cast<ShardExchange*>(arg);
+  int rc = tc_shard_bcast_thr(x->tcs, *x->plan, x->shard->rank, x->shard->world, x->xthr, x->stream);
+  if (rc) return rc;
+  SBK_CUDA_CHECK(cudaStreamSynchronize(x->stream));
+  x->shard->barrier(x->shard->barrier_arg);
+  SBK_CUDA_CHECK(cudaMemcpyAsync(x->tcs->thr, x->xthr[x->shard->rank], (size_t)x->n_q * sizeof(float), cudaMemcpyDeviceToDevice, x->stream));
+  return SBK_OK;
+}
+
 static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,
                     int64_t q_begin, int64_t q_end, int32_t k,
                     void* out_dist, int32_t* out_idx,
                     void* workspace, size_t ws_bytes, int algo,
-                    sbk_knn_stats* stats, cudaStream_t stream, const HostSink* sink, const PeerOut* peers = nullptr) {
+                    sbk_knn_stats* stats, cudaStream_t stream, const HostSink* sink, const PeerOut* peers = nullptr,
+                    const ShardCtx* shard = nullptr) {
   int rc = knn_check(dtype, n_ref, d, q_begin, q_end, k);
   if (rc) return rc;
   if (ld < d) { set_error("knn: ld=%lld < d=%d", (long long)ld, d); return SBK_ERR_INVALID; }
@@ -328,7 +351,80 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       const bool ok_d = !sink->dist || cudaHostGetDevicePointer(&zc_dist, sink->dist, 0) == cudaSuccess;
       if (!ok_i || !ok_d) { cudaGetLastError(); zc_idx = nullptr; zc_dist = nullptr; }    // not mapped: chunked copies at the end
     }
-    if (s.sym && zc_idx) {
+    if (shard && !s.sym) { set_error("knn_sym_shard: the symmetric filter does not take this build (size / k / width)"); return SBK_ERR_INVALID; }
+    if (s.sym && shard) {
+      // ---- one process per GPU, every tile pair multiplied once across all of them ----
+      const int rank = shard->rank, world = shard->world;
+      const long long tb = tc_shard_block_tiles(s.plan, world);
+      const long long slot_lo = std::min<long long>(n_q, (long long)rank * tb * TC_BN), slot_hi = std::min<long long>(n_q, ((long long)rank + 1) * tb * TC_BN);
+      const long long cn = slot_hi - slot_lo;
+      const size_t thr_bytes = shard_thr_bytes(s.plan);
+      const long long mcap = shard_mail_cap(s.plan, n_ref, world);
+      float* xthr[8]; int* xcount[8]; uint4* xmail[8];
+      for (int r = 0; r < world; ++r) {
+        xthr[r] = reinterpret_cast<float*>(shard->xchg[r]);
+        xcount[r] = reinterpret_cast<int*>((char*)shard->xchg[r] + thr_bytes);
+        xmail[r] = reinterpret_cast<uint4*>((char*)shard->xchg[r] + thr_bytes + 256);
+      }
+      // thresholds of the own rows, handed to every rank
+      h = tm.begin(&st.ms_sample);
+      if (cn > 0) {
+        TcState own = tcs; own.thr = tcs.thr + slot_lo;
+        rc = tc_sample_chunk(&own, s.plan, slot_lo, cn, w.bound + slot_lo, stream);
+      }
+      ShardExchange xc; xc.tcs = &tcs; xc.plan = &s.plan; xc.shard = shard; xc.xthr = xthr; xc.n_q = n_q; xc.stream = stream;
+      if (!rc) rc = shard_exchange_thr(&xc);
+      tm.end(h);
+      if (rc) return rc;
+      int nfl = 0, naux = 0;
+      h = tm.begin(&st.ms_filter);
+      rc = tc_sym_begin(&tcs, s.plan, w.cand_pair, w.cand_count, w.bound, &naux, stream);
+      TcMail mail; memset(&mail, 0, sizeof(mail));
+      for (int r = 0; r < world; ++r) mail.out[r] = xmail[rank] + (long long)r * mcap;      // own outbox for rank r (local memory)
+      mail.out_cnt = w.n_fail + 8; mail.cap = (int)mcap; mail.blk_pos = tb * TC_BN; mail.own_lo = slot_lo; mail.own_hi = slot_hi;
+      // (after its own block every rank refines its thresholds; they are exchanged once more so that the blocks of other
+      // ranks are walked against refined column thresholds, and T8 / t are recomputed from them)
+      struct Mid { ShardExchange* xc; TcState* tcs; const TcPlan* plan; cudaStream_t stream; } mid = {&xc, &tcs, &s.plan, stream};
+      auto mid_fn = [](void* a) -> int {
+        Mid* m = static_cast<Mid*>(a);
+        int r2 = shard_exchange_thr(m->xc);
+        return r2 ? r2 : tc_refresh_colthr(m->tcs, *m->plan, m->stream);
+      };
+      if (!rc) rc = tc_sym_shard_filter(&tcs, s.plan, k, rank, world, w.cand_pair, w.cand_count, w.bound, mail, xcount, &nfl, &naux, stream,
+                                        mid_fn, &mid);
+      tm.end(h);
+      if (rc == TC_SYM_POOL_EXHAUSTED) { set_error("knn_sym_shard: group-record pool exhausted"); return SBK_ERR_INTERNAL; }
+      if (rc) return rc;
+      shard->barrier(shard->barrier_arg);              // every mailbox and count is complete (the filter ended with a stream sync)
+      h = tm.begin(&st.ms_filter);
+      uint4* inbox[8];
+      for (int r = 0; r < world; ++r) inbox[r] = xmail[r] + (long long)rank * mcap;          // rank r's outbox for this rank (peer memory)
+      rc = tc_mail_merge(&tcs, s.plan, inbox, xcount[rank], world, (int)mcap, w.cand_pair, w.cand_count, w.n_fail + 16, stream);
+      tm.end(h);
+      if (rc) return rc;
+      st.n_filter_launches += nfl; st.n_launches += 4 + nfl + naux;
+      if (cn > 0) {
+        h = tm.begin(&st.ms_rerank);
+        SBK_CUDA_CHECK(cudaMemsetAsync(w.n_fail + 2, 0, sizeof(int), stream));
+        int32_t* perm = nullptr;
+        rc = launch_row_order(X, dtype, d, ld, q_begin, cn, tcs.centre, w.order_ws, w.order_bytes, &perm, stream, tcs.orig + slot_lo);
+        if (!rc) rc = launch_rerank_warp(X, dtype, d, ld, q_begin, cn, perm, tcs.rpos, w.cand_pair, w.cand_count, (int)s.cand_stride, tcs.thr, w.bound,
+                                         tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, out_dist, out_idx, q_begin, w.fail_rows, w.n_fail, w.retry,
+                                         w.n_fail + 2, (int)s.retry_cap, w.cand_total, stream, peers);
+        if (!rc) rc = launch_rerank(X, dtype, n_ref, d, ld, tcs.orig, q_begin, cn, nullptr, w.cand_pair, s.cand_stride, 4, w.cand_count,
+                                    w.bound, tcs.nrm, tcs.norms4, tcs.scale, tcs.orig, k, out_dist, out_idx, q_begin, w.fail_rows, w.n_fail,
+                                    w.cand_total + 8, stream, w.retry, w.n_fail + 2, (int)s.retry_cap, peers);
+        tm.end(h);
+        st.n_launches += 5;
+        if (rc) return rc;
+      }
+      int h_over = 0;
+      SBK_CUDA_CHECK(cudaMemcpyAsync(&h_over, w.n_fail + 16, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+      if (h_over) { set_error("knn_sym_shard: a mailbox overflowed (more cross-GPU candidates than planned)"); return SBK_ERR_INTERNAL; }
+      st.n_chunks++;
+      blocks_done = true;
+    } else if (s.sym && zc_idx) {
       h = tm.begin(&st.ms_sample);
       rc = tc_sample_chunk(&tcs, s.plan, 0, n_q, w.bound, stream);
       tm.end(h);
@@ -574,6 +670,26 @@ extern "C" int sbk_knn_peers(const void* X, int dtype, int64_t n_ref, int32_t d,
   }
   return knn_impl(X, dtype, n_ref, d, ld, q_begin, q_end, k, out_dist, out_idx, workspace, ws_bytes, algo, stats,
                   (cudaStream_t)cuda_stream, nullptr, &po);
+}
+
+extern "C" size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t d, int32_t k, int32_t world) {
+  if (knn_check(dtype, n_ref, d, 0, n_ref, k) != SBK_OK || world < 2 || world > 8) return 0;
+  KnnShape s = knn_shape(dtype, n_ref, d, n_ref, k, SBK_KNN_TENSOR_SYMMETRIC);
+  if (!s.sym) return 0;
+  return shard_thr_bytes(s.plan) + 256 + (size_t)world * (size_t)shard_mail_cap(s.plan, n_ref, world) * sizeof(uint4);
+}
+
+extern "C" int sbk_knn_sym_shard(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld, int32_t k,
+                                 int32_t rank, int32_t world, void* const* xchg, void (*barrier)(void*), void* barrier_arg,
+                                 void* out_dist, int32_t* out_idx, int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
+                                 void* workspace, size_t ws_bytes, sbk_knn_stats* stats, void* cuda_stream) {
+  if (world < 2 || world > 8 || rank < 0 || rank >= world || !xchg || !barrier) { set_error("knn_sym_shard: bad rank / world / exchange table"); return SBK_ERR_INVALID; }
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && (!peer_dist || !peer_idx))) { set_error("knn_sym_shard: 0..8 peer buffers"); return SBK_ERR_INVALID; }
+  PeerOut po; po.n = n_peers;
+  for (int t = 0; t < n_peers; ++t) { po.dist[t] = peer_dist[t]; po.idx[t] = peer_idx[t]; }
+  ShardCtx sc; sc.rank = rank; sc.world = world; sc.xchg = xchg; sc.barrier = barrier; sc.barrier_arg = barrier_arg;
+  return knn_impl(X, dtype, n_ref, d, ld, 0, n_ref, k, out_dist, out_idx, workspace, ws_bytes, SBK_KNN_TENSOR_SYMMETRIC, stats,
+                  (cudaStream_t)cuda_stream, nullptr, &po, &sc);
 }
 
 extern "C" int sbk_knn_stream(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld,

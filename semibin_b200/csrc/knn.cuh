@@ -92,6 +92,18 @@ __host__ __device__ static inline double tc_pair_upper_slack(const float4& ni, c
   const double G = tc_pair_G(ni, nj, c_acc), J = tc_pair_J(nj, c_acc);
   return 2.02 * G + 2.02 * J + (double)ni.w + 2.4e-7 * ((double)nj.x + (double)nj.y + (double)ni.z + (double)ni.y) + 4e-7;
 }
+// Sharded symmetric build (one process per GPU): GPU g owns the positions of tile block g.  A column hit whose row lives
+// on another GPU goes into this GPU's outbox for that GPU (local memory); after a barrier the owner reads the outboxes
+// addressed to it straight from the senders' memory (coalesced peer loads over NVLink; as 16-byte peer STORES from the
+// transpose kernel the same records cost 65 ms at 1M on two GPUs) and merges them; `cap` = 0 means single-GPU.
+struct TcMail {
+  uint4* out[8];            // out[c]: this rank's outbox for rank c (records (j, i, s bits, -))
+  int* out_cnt;             // [8] local counters of records sent to each rank
+  int cap;                  // records per (source, destination) region
+  long long blk_pos;        // positions per tile block (owner of position p = p / blk_pos)
+  long long own_lo, own_hi; // positions this rank owns
+};
+
 struct TcState {
   __half* a_tiles; __half* b_tiles;
   double* centre; double* colsum; double* scale; double* nrm;
@@ -131,6 +143,21 @@ int tc_sym_begin(TcState* st, const TcPlan& p, uint2* cand, int32_t* cand_count,
 int tc_sym_block(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand_count, double* bound, int n_blocks, int r,
                  int* n_launches, int* n_aux_launches, cudaStream_t stream);
 int tc_sym_end(TcState* st, cudaStream_t stream);
+// ---- sharded symmetric build (rank of world GPUs; see TcMail) ----
+long long tc_shard_block_tiles(const TcPlan& p, int world);
+// own thresholds (positions of the rank's block) into every rank's exchange array
+int tc_shard_bcast_thr(TcState* st, const TcPlan& p, int rank, int world, float* const* xthr, cudaStream_t stream);
+// tile pairs of this rank: own block circulantly, the following (world-1)/2 blocks in full, and for an even world half
+// of the opposite block; row hits and local column hits into the lists, remote column hits into the mailboxes
+int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,
+                        const TcMail& mail, int* const* peer_count_in, int* n_launches, int* n_aux_launches, cudaStream_t stream,
+                        int (*mid_exchange)(void*) = nullptr, void* mid_arg = nullptr);
+// t, T8 of every position from the current thresholds (after thresholds of other ranks arrived)
+int tc_refresh_colthr(TcState* st, const TcPlan& p, cudaStream_t stream);
+// records other ranks hold for this one (boxes[src]: the outbox of rank src for this rank, in src's memory; count_in[src])
+// into the lists
+int tc_mail_merge(TcState* st, const TcPlan& p, uint4* const* boxes, const int* count_in, int world, int cap,
+                  uint2* cand, int32_t* cand_count, int* overflow_flag, cudaStream_t stream);
 // Sample pass for query rows [row0, row0+n_rows): per-row thresholds (st->thr)
 // and certificate bounds bound[slot].
 int tc_sample_chunk(TcState* st, const TcPlan& p, long long row0, long long n_rows, double* bound,

@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(256)
 tc_transpose_kernel(const uint4* __restrict__ pool, int* __restrict__ pool_count, int pool_chunks,
                     long long n, long long n_tiles, long long blk_tiles, const float4* __restrict__ tq,
                     uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
-                    unsigned long long* __restrict__ dbg) {
+                    unsigned long long* __restrict__ dbg, const TcMail mail) {
   const int lane = threadIdx.x & 31;
   const int n_chunks = min(*pool_count, pool_chunks);
   const int seg_cap = cand_cap >> 2;
@@ -654,9 +654,23 @@ tc_transpose_kernel(const uint4* __restrict__ pool, int* __restrict__ pool_count
       if (col_on) {
         const float4 qj = tq[j];                               // padding positions: t = -inf
         if (sv <= qj.z) {
-          const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
-          if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, qj.y)));
-          else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+          if (mail.cap == 0 || (j >= mail.own_lo && j < mail.own_hi)) {
+            const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
+            if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, qj.y)));
+            else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+          } else {                                              // the row lives on another GPU: into its mailbox (peer store)
+            // one counter per destination: the lanes that are here together and send to the same rank take their slots with
+            // ONE atomic (54 M single increments of one address cost 30 ms at 1M on two GPUs)
+            const int dst = (int)(j / mail.blk_pos);
+            const unsigned am = __activemask();
+            const unsigned grp = __match_any_sync(am, dst);
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&mail.out_cnt[dst], __popc(grp));
+            base = __shfl_sync(grp, base, leader);
+            const int at = base + __popc(grp & ((1u << lane) - 1u));
+            if (at < mail.cap) mail.out[dst][at] = make_uint4((uint32_t)j, (uint32_t)i, __float_as_uint(sv), 0u);
+          }
         }
       }
     }
@@ -1478,7 +1492,10 @@ static long long tc_sym_max_steps(const TcPlan& p) {
 }
 // one filter launch over query tiles [q_lo, q_lo + q_len) and the transposes of its records
 static int tc_sym_launch(TcState* st, const TcPlan& p, TcArgs& a, long long q_lo, long long q_len, long long blk_tiles,
-                         uint2* cand, int32_t* cand_count, int* n_launches, int* n_aux_launches, cudaStream_t stream) {
+                         uint2* cand, int32_t* cand_count, int* n_launches, int* n_aux_launches, cudaStream_t stream,
+                         const TcMail* mail = nullptr) {
+  TcMail mv; memset(&mv, 0, sizeof(mv));
+  if (mail) mv = *mail;
   a.tile_m0 = 2 * q_lo;
   int rc = tc_launch_cg<TC_FILTER_SYM, 2, 1>(a, 2 * q_len, stream);
   if (rc) return rc;
@@ -1489,7 +1506,7 @@ static int tc_sym_launch(TcState* st, const TcPlan& p, TcArgs& a, long long q_lo
   if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
 #endif
   tc_transpose_kernel<<<(unsigned)std::min((st->pool_chunks + 7) / 8, 148 * 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, st->n_ref, p.n_tiles,
-                                                                                blk_tiles, st->tq, cand, cand_count, p.cand_cap, dbg);
+                                                                                blk_tiles, st->tq, cand, cand_count, p.cand_cap, dbg, mv);
   SBK_LAUNCH_CHECK();
   SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, 2 * sizeof(int), stream));  // chunks handed out, chunks transposed; [2], the exhaustion flag, stays
 #ifdef SBK_ENABLE_PROBES
@@ -1536,6 +1553,12 @@ int tc_sym_begin(TcState* st, const TcPlan& p, uint2* cand, int32_t* cand_count,
   tc_colthr_kernel<<<(unsigned)T, 256, 0, stream>>>(st->thr, st->cu, n, st->t8, st->tq);
   SBK_LAUNCH_CHECK();
   if (n_aux_launches) *n_aux_launches += 2;
+  return SBK_OK;
+}
+
+int tc_refresh_colthr(TcState* st, const TcPlan& p, cudaStream_t stream) {
+  tc_colthr_kernel<<<(unsigned)p.n_tiles, 256, 0, stream>>>(st->thr, st->cu, st->n_ref, st->t8, st->tq);
+  SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
 
@@ -1635,6 +1658,152 @@ int tc_sym_block(TcState* st, const TcPlan& p, int k, uint2* cand, int32_t* cand
     rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream);
     if (rc) return rc;
   }
+  return SBK_OK;
+}
+
+// ---------------------------------------------------------------------------
+// sharded symmetric build
+// ---------------------------------------------------------------------------
+long long tc_shard_block_tiles(const TcPlan& p, int world) { return (p.n_tiles + world - 1) / world; }
+
+__global__ void tc_bcast_thr_kernel(const float* __restrict__ thr, long long lo, long long hi, int world, TcMail ptrs) {
+  // ptrs.out[r] reused as the float exchange array of rank r
+  const long long s = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= hi) return;
+  const float v = thr[s];
+  for (int r = 0; r < world; ++r) reinterpret_cast<float*>(ptrs.out[r])[s] = v;
+}
+
+int tc_shard_bcast_thr(TcState* st, const TcPlan& p, int rank, int world, float* const* xthr, cudaStream_t stream) {
+  const long long tb = tc_shard_block_tiles(p, world);
+  const long long lo = std::min<long long>(st->n_ref, (long long)rank * tb * TC_BN), hi = std::min<long long>(st->n_ref, ((long long)rank + 1) * tb * TC_BN);
+  if (hi <= lo) return SBK_OK;
+  TcMail ptrs; memset(&ptrs, 0, sizeof(ptrs));
+  for (int r = 0; r < world; ++r) ptrs.out[r] = reinterpret_cast<uint4*>(xthr[r]);
+  tc_bcast_thr_kernel<<<(unsigned)((hi - lo + 255) / 256), 256, 0, stream>>>(st->thr, lo, hi, world, ptrs);
+  SBK_LAUNCH_CHECK();
+  return SBK_OK;
+}
+
+__global__ void tc_mail_counts_kernel(const int* __restrict__ out_cnt, int rank, int world, TcMail ptrs) {
+  // ptrs.out[r] reused as the int count_in array of rank r: count_in[source] = records this source sent
+  const int r = threadIdx.x;
+  if (r < world) reinterpret_cast<int*>(ptrs.out[r])[rank] = out_cnt[r];
+}
+
+int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,
+                        const TcMail& mail, int* const* peer_count_in, int* n_launches, int* n_aux_launches, cudaStream_t stream,
+                        int (*mid_exchange)(void*), void* mid_arg) {
+  if (!st->sym || st->cg != 2) { set_error("tensor kNN: state not prepared for the symmetric filter"); return SBK_ERR_INTERNAL; }
+  const long long n = st->n_ref, T = p.n_tiles, tb = tc_shard_block_tiles(p, world);
+  const long long lo = (long long)rank * tb, len = std::min(tb, T - lo);
+  SBK_CUDA_CHECK(cudaMemsetAsync(mail.out_cnt, 0, 8 * sizeof(int), stream));
+  int rc = SBK_OK;
+  if (len > 0) {
+    TcArgs a;
+    tc_sym_args(st, p, cand, cand_count, a);
+    const long long max_steps = tc_sym_max_steps(p);
+    // own block, circulant inside it, with the refinement points of the single-GPU schedule: after 1/14, 1/7 and 2/7 of
+    // the block the own rows have seen a window of 1/7, 2/7, 4/7 of their block = (2s - 1) / T of all references (what
+    // other ranks find for them waits in their outboxes and does not disturb the count)
+    a.blk_lo = lo; a.blk_len = len; a.sym_linear = 0;
+    const long long n_steps = len / 2 + 1;
+    std::vector<long long> cuts; std::vector<char> refine_at;
+    {
+      const long long marks[3] = {(len + 13) / 14, (len + 6) / 7, (2 * len + 6) / 7};
+      long long prev = 0;
+      auto add_range = [&](long long end, bool is_mark) {
+        if (end <= prev) return;
+        const long long l2 = end - prev, parts = (l2 + max_steps - 1) / max_steps;
+        for (long long q = 1; q <= parts; ++q) { cuts.push_back(prev + l2 * q / parts); refine_at.push_back(is_mark && q == parts); }
+        prev = end;
+      };
+      for (int m = 0; m < 3; ++m) if (marks[m] < n_steps) add_range(marks[m], true);
+      add_range(n_steps, false);
+    }
+    long long s0 = 0;
+    for (size_t li = 0; li < cuts.size(); ++li) {
+      a.bt0 = s0; a.n_btiles = cuts[li] - s0;
+      rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream, &mail);
+      if (rc) return rc;
+      s0 = cuts[li];
+      if (refine_at[li] && s0 < n_steps) {
+        rc = tc_sym_refine(st, p, k, std::min(1.0, (double)(2 * s0 - 1) / (double)T), lo * TC_BN, std::min(n, (lo + len) * TC_BN),
+                           cand, cand_count, bound, n_aux_launches, stream);
+        if (rc) return rc;
+      }
+    }
+    // the own rows have now seen their whole block
+    rc = tc_sym_refine(st, p, k, (double)len / (double)T, lo * TC_BN, std::min(n, (lo + len) * TC_BN), cand, cand_count, bound,
+                       n_aux_launches, stream);
+    if (rc) return rc;
+  }
+  // refined thresholds of every rank before the blocks of other ranks are walked (every rank calls this, rows or not)
+  if (mid_exchange) { rc = mid_exchange(mid_arg); if (rc) return rc; }
+  if (len > 0) {
+    TcArgs a;
+    tc_sym_args(st, p, cand, cand_count, a);
+    const long long max_steps = tc_sym_max_steps(p);
+    a.blk_lo = lo; a.blk_len = len;
+    a.sym_linear = 1;
+    auto linear = [&](long long q_lo, long long q_len, long long j_lo, long long j_len) -> int {
+      for (long long j0 = j_lo; j0 < j_lo + j_len; j0 += max_steps) {
+        a.bt0 = j0; a.n_btiles = std::min(max_steps, j_lo + j_len - j0);
+        int r2 = tc_sym_launch(st, p, a, q_lo, q_len, tb, cand, cand_count, n_launches, n_aux_launches, stream, &mail);
+        if (r2) return r2;
+      }
+      return SBK_OK;
+    };
+    const int h_full = (world - 1) / 2;
+    for (int s = 1; s <= h_full; ++s) {
+      const long long c = (rank + s) % world, clo = c * tb, clen = std::min(tb, T - clo);
+      if (clen > 0) { rc = linear(lo, len, clo, clen); if (rc) return rc; }
+    }
+    if ((world & 1) == 0) {
+      // the opposite block pair is shared: the lower rank takes its rows x the first half of the other block's tiles, the
+      // upper rank the second half of ITS tiles (as rows) x all tiles of the lower block
+      const long long c = (rank + world / 2) % world, clo = c * tb, clen = std::max<long long>(0, std::min(tb, T - clo));
+      if (rank < world / 2) { if (clen / 2 > 0) { rc = linear(lo, len, clo, clen / 2); if (rc) return rc; } }
+      else { const long long h = len / 2; if (len - h > 0 && clen > 0) { rc = linear(lo + h, len - h, clo, clen); if (rc) return rc; } }
+    }
+  }
+  // how many records went to every rank (into their count_in[this rank])
+  TcMail ptrs; memset(&ptrs, 0, sizeof(ptrs));
+  for (int r = 0; r < world; ++r) ptrs.out[r] = reinterpret_cast<uint4*>(peer_count_in[r]);
+  tc_mail_counts_kernel<<<1, 32, 0, stream>>>(mail.out_cnt, rank, world, ptrs);
+  SBK_LAUNCH_CHECK();
+  return tc_sym_end(st, stream);
+}
+
+__global__ void __launch_bounds__(256)
+tc_mail_merge_kernel(const TcMail boxes, const int* __restrict__ count_in, int world, int cap,
+                     const float4* __restrict__ tq, uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
+                     int* __restrict__ overflow_flag) {
+  const int seg_cap = cand_cap >> 2;
+  for (int src = 0; src < world; ++src) {
+    const int cnt = count_in[src];
+    if (cnt > cap) { if (blockIdx.x == 0 && threadIdx.x == 0) *overflow_flag = 1; }
+    const uint4* box = boxes.out[src];                           // in the SOURCE rank's memory: coalesced peer loads
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < min(cnt, cap); e += (long long)gridDim.x * blockDim.x) {
+      const uint4 rec = box[e];
+      const long long j = rec.x;
+      const float sv = __uint_as_float(rec.z);
+      const float4 qj = tq[j];
+      if (sv <= qj.z) {                                          // this rank's (refined) threshold
+        const int ts = (int)(e & 3);
+        const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
+        if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2(rec.y, __float_as_uint(__fsub_rd(sv, qj.y)));
+      }
+    }
+  }
+}
+
+int tc_mail_merge(TcState* st, const TcPlan& p, uint4* const* boxes, const int* count_in, int world, int cap,
+                  uint2* cand, int32_t* cand_count, int* overflow_flag, cudaStream_t stream) {
+  TcMail b; memset(&b, 0, sizeof(b));
+  for (int r = 0; r < world; ++r) b.out[r] = boxes[r];
+  tc_mail_merge_kernel<<<148 * 8, 256, 0, stream>>>(b, count_in, world, cap, st->tq, cand, cand_count, p.cand_cap, overflow_flag);
+  SBK_LAUNCH_CHECK();
   return SBK_OK;
 }
 

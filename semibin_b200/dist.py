@@ -130,6 +130,72 @@ def knn_sharded_p2p(X, n_neighbors, bufs, *, algo='auto', return_stats=False):
     return bufs.dist, bufs.idx
 
 
+class SymShard:
+    """Exchange buffers of the sharded symmetric build (`sbk_knn_sym_shard`): per rank the thresholds of all positions,
+    the record counts and one mailbox region per source rank, allocated as torch symmetric memory so that every rank
+    can store into every other rank's buffer over NVLink.  Raises ValueError when the symmetric filter does not take a
+    build of this shape (the caller then shards by row blocks)."""
+
+    def __init__(self, n, d, k, dtype, device, group=None):
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        lib = _lib.load()
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = world_info(group)
+        self.shape = (n, d, k, dtype)
+        code = _lib.SBK_F32 if dtype == torch.float32 else _lib.SBK_F64
+        nbytes = lib.sbk_knn_sym_shard_xchg_bytes(code, n, d, k, self.world)
+        if nbytes == 0:
+            raise ValueError('the symmetric filter does not take this build on %d GPUs' % self.world)
+        self.buf = symm.empty((int(nbytes),), dtype=torch.uint8, device=device)
+        self._handle = symm.rendezvous(self.buf, self.group)
+        self.xchg = (C.c_void_p * self.world)(*[int(self._handle.buffer_ptrs[r]) for r in range(self.world)])
+
+
+def knn_sharded_sym(X, n_neighbors, bufs, shard, *, return_stats=False):
+    """The whole kNN graph on all GPUs of the group with every tile pair multiplied ONCE across them (symmetric filter;
+    `knn_sharded_p2p` multiplies every pair twice: once for either row's owner).  Every rank owns a block of staged
+    positions, sends the candidates it finds for other ranks' rows into their mailboxes (shard: SymShard), reranks its
+    own rows and stores them into every rank's full result (bufs: PeerResult).  Returns (bufs.dist, bufs.idx), complete
+    on every rank."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from .neighbors import _workspace
+    lib = _lib.load()
+    n, d = X.shape
+    k = int(n_neighbors)
+    if (n, d, k, X.dtype) != shard.shape:
+        raise ValueError('SymShard was made for another problem shape')
+    dtype = _lib.SBK_F32 if X.dtype == torch.float32 else _lib.SBK_F64
+    ws_bytes = lib.sbk_knn_workspace_bytes(dtype, n, d, n, k, _lib.KNN_TENSOR_SYMMETRIC)
+    if ws_bytes == 0:
+        raise ValueError(_lib.last_error())
+    ws = _workspace(ws_bytes, X.device)
+    st = _lib.KnnStats()
+    group = bufs.group
+
+    @C.CFUNCTYPE(None, C.c_void_p)
+    def barrier(_arg):
+        dist.barrier(group=group)
+
+    rc = lib.sbk_knn_sym_shard(_lib.ptr(X), dtype, n, d, X.stride(0), k, shard.rank, shard.world, shard.xchg,
+                               C.cast(barrier, C.c_void_p), None, _lib.ptr(bufs.dist), _lib.ptr(bufs.idx),
+                               bufs.n_peers, bufs.peer_dist, bufs.peer_idx, _lib.ptr(ws), ws.numel(), C.byref(st),
+                               _lib.stream_ptr(X.device))
+    _lib.check(rc)
+    # the call returns with this rank's stream drained; once every rank has got here every full buffer is complete and
+    # nobody reads its mailboxes any more
+    dist.barrier(group=group)
+    if return_stats:
+        return bufs.dist, bufs.idx, st.as_dict()
+    return bufs.dist, bufs.idx
+
+
 def allreduce_counts(counts, group=None):
     """Sum of the per-threshold row counts over ranks (cluster.py:122)."""
     dist = _dist()
