@@ -230,18 +230,30 @@ def run_ours(args):
     # N > 1: the rerank kernels store every finished row into every rank's full result buffer (P2P over NVLink,
     # symmetric memory), the gather rides on the compute kernel; --gather nccl (or a box without peer mapping)
     # falls back to two all-gathers after the kernels
-    peer_bufs, gather_mode = None, 'none'
+    peer_bufs, gather_mode, sym_shard = None, 'none', None
+    sharding = f'row-block x{world}, references replicated'
     if world > 1:
         gather_mode = 'nccl all_gather_into_tensor x2'
-        if args.gather == 'p2p':
+        if args.gather in ('p2p', 'sym'):
             try:
                 peer_bufs = sdist.PeerResult(n, k, torch.float32, X.device)
                 gather_mode = 'p2p stores from the rerank kernels into symmetric-memory result buffers + barrier'
             except Exception as e:      # noqa: BLE001  (reported in the JSON line)
                 gather_mode = f'nccl all_gather_into_tensor x2 (symmetric memory unavailable: {type(e).__name__}: {e})'[:300]
+        # --gather sym (default): the tile pairs are split over the ranks so that each is multiplied once in the whole
+        # job (sbk_knn_sym_shard); candidates for other ranks' rows travel through NVLink mailboxes.  A shape the
+        # symmetric filter does not take falls back to row blocks (every pair multiplied twice, no exchange).
+        if peer_bufs is not None and args.gather == 'sym' and args.algo in ('auto', 'tensor', 'tensor_symmetric'):
+            try:
+                sym_shard = sdist.SymShard(n, X.shape[1], k, torch.float32, X.device)
+                sharding = f'symmetric tile pairs x{world} (each pair multiplied once), candidate mailboxes over NVLink'
+            except ValueError as e:
+                sharding += f' (symmetric sharding not taken: {e})'
 
     def step(collect=None):
-        if peer_bufs is not None:
+        if sym_shard is not None:
+            d, i, st = sdist.knn_sharded_sym(X, k, peer_bufs, sym_shard, return_stats=True)
+        elif peer_bufs is not None:
             d, i, st = sdist.knn_sharded_p2p(X, k, peer_bufs, algo=args.algo, return_stats=True)
         else:
             d, i, st = knn(X, k, q_begin=lo, q_end=hi, algo=args.algo, return_stats=True, out=(dev_d, dev_i))
@@ -330,7 +342,7 @@ def run_ours(args):
         # the symmetric self-join filter multiplies every unordered pair of 256-row tiles once: T * (T // 2 + 1) tile
         # products instead of T * T; `achieved` counts the flops the kernel executes (true D), never the one-sided 2 N^2 D
         T = (n + 255) // 256
-        flops = 2.0 * 256 * 256 * D_EMB * T * (T // 2 + 1)
+        flops = 2.0 * 256 * 256 * D_EMB * T * (T // 2 + 1) / world     # N > 1: the tile pairs are split over the ranks
     else:
         flops = flops_onesided
     roofline = None
@@ -358,7 +370,7 @@ def run_ours(args):
             'config': {'workload': f'kNN graph, N={n} contigs x D={D_EMB} float32 embedding, k={k} (BASELINE configs[2] shape / metric quote)',
                        'n': n, 'd': D_EMB, 'k': k, 'algo': args.algo,
                        'embedding': (f'file {os.path.basename(args.embedding_file)}' if args.embedding_file else
-                                     f'synthetic Gaussian mixture, lognormal genome sizes (mean {args.genome_size} contigs)'), 'parallelism': f'row-block x{world}, references replicated', 'gather': gather_mode,
+                                     f'synthetic Gaussian mixture, lognormal genome sizes (mean {args.genome_size} contigs)'), 'parallelism': sharding, 'gather': gather_mode,
                        'l2': 'inputs (400 MB embedding + 224 MB staged operands + candidate lists) exceed the 126 MB L2'},
             'clocks': sampler.summary(),
             'e2e': {'value': n / (e2e_ms * 1e-3), 'unit': 'contigs/s', 'ms_per_step': e2e_ms,
@@ -429,7 +441,7 @@ def main():
     ap.add_argument('--neighbors', dest='k', type=int, default=K_DEFAULT)
     ap.add_argument('--algo', default='auto')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl'])
+    ap.add_argument('--gather', default='sym', choices=['sym', 'p2p', 'nccl'])
     ap.add_argument('--embedding-file', default=None, help='.npy float32 [N, 100] matrix instead of the synthetic mixture (realism runs)')
     ap.add_argument('--genome-size', type=int, default=200, help='mean contigs per synthetic genome (lognormal, sigma 1)')
     args = ap.parse_args()

@@ -275,14 +275,22 @@ int sbk_kmeans_batch(const float* X, int64_t ld, int32_t d, const float* weight,
  * every peer's full [n_ref, k] result (out_dist / out_idx, peer_dist / peer_idx: as sbk_knn_peers).
  *   xchg[r]  : base of rank r's exchange buffer (sbk_knn_sym_shard_xchg_bytes each, same size on every rank, mapped into
  *              this process: e.g. torch symmetric memory), r = 0 .. world-1, own buffer included
- *   barrier  : called three times (after the sample thresholds, after every rank's own block, after the last tile pair);
- *              must return once every rank has called it (the library synchronises its stream first)
- * Returns SBK_ERR_INVALID when the symmetric filter does not take the build (the caller then shards by row blocks). */
+ *   barrier  : barrier(barrier_arg, failed) is called three times (after the sample thresholds, after every rank's own
+ *              block, after the last tile pair); it must return once every rank has called it, with a non-zero value when
+ *              any rank passed failed != 0 (the library synchronises its stream first).  The vote makes all ranks leave
+ *              a failed build together.
+ * Returns SBK_ERR_INVALID when the symmetric filter does not take the build, SBK_ERR_INTERNAL when a record pool or a
+ * mailbox was too small on this or (voted) another rank; a mailbox overflow is only known to the receiving rank at the
+ * end, so the caller votes once more after the call.  In all these cases the caller shards by row blocks instead. */
 size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t d, int32_t k, int32_t world);
 int sbk_knn_sym_shard(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld, int32_t k,
-                      int32_t rank, int32_t world, void* const* xchg, void (*barrier)(void*), void* barrier_arg,
+                      int32_t rank, int32_t world, void* const* xchg, int (*barrier)(void*, int), void* barrier_arg,
                       void* out_dist, int32_t* out_idx, int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
                       void* workspace, size_t ws_bytes, sbk_knn_stats* stats, void* cuda_stream);
+
+/* Debug / test hook: fixes the capacity (records) of every mailbox of the sharded symmetric build, 0 = planned size.
+ * Set it identically on every rank BEFORE sbk_knn_sym_shard_xchg_bytes; a small value forces the overflow vote. */
+void sbk_debug_shard_mail_cap(int64_t records);
 
 /* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
  * MMA pipeline as the tensor filter and returns the accumulator values

@@ -12,6 +12,7 @@ PROBES = os.environ.get('SBK_LIB_VARIANT', '') == 'probe'
 LIB_PATH = os.path.join(HERE, 'libsbk_probe.so' if PROBES else 'libsbk.so')
 
 SBK_F32, SBK_F64 = 0, 1
+SBK_OK, SBK_ERR_INVALID, SBK_ERR_WORKSPACE, SBK_ERR_CUDA, SBK_ERR_INTERNAL = 0, -1, -2, -3, -4
 KNN_AUTO, KNN_EXACT, KNN_TENSOR, KNN_TENSOR_ONESIDED, KNN_TENSOR_SYMMETRIC, KNN_TENSOR_SYMMETRIC_STARVED = 0, 1, 2, 3, 4, 5
 ALGOS = {'auto': KNN_AUTO, 'exact': KNN_EXACT, 'tensor': KNN_TENSOR, 'tensor_onesided': KNN_TENSOR_ONESIDED,
          'tensor_symmetric': KNN_TENSOR_SYMMETRIC, 'tensor_symmetric_starved': KNN_TENSOR_SYMMETRIC_STARVED}
@@ -84,6 +85,7 @@ SIGNATURES = {
     'sbk_kmeans_batch': (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
                                    C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
+    'sbk_debug_shard_mail_cap': (None, [C.c_int64]),
     'sbk_debug_tc_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_debug_tc_scores': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

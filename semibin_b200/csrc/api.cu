@@ -286,21 +286,35 @@ static int sink_rows(const HostSink* sk, int dtype, int k, const void* od, const
 // Sharded symmetric build (sbk_knn_sym_shard): this process is `rank` of `world` GPUs; xchg[r] = base of rank r's exchange
 // buffer (peer memory; same layout everywhere: thresholds of all positions, count_in[8], one outbox per destination rank);
 // barrier() returns once every rank has called it and the device work each rank enqueued before it is complete.
-struct ShardCtx { int rank, world; void* const* xchg; void (*barrier)(void*); void* barrier_arg; };
+// It also carries an error vote: every rank passes "I failed" and gets "somebody failed", so that all ranks leave the
+// build together (a rank that returned alone would leave the others waiting in the next barrier).
+struct ShardCtx { int rank, world; void* const* xchg; int (*barrier)(void*, int); void* barrier_arg; };
+static int shard_vote(const ShardCtx* sc, int rc) {
+  const int any = sc->barrier(sc->barrier_arg, rc != SBK_OK);
+  if (rc) return rc;
+  if (any) { set_error("knn_sym_shard: another rank failed, the build was abandoned on all ranks"); return SBK_ERR_INTERNAL; }
+  return SBK_OK;
+}
+static long long g_debug_mail_cap = 0;             // test hook (sbk_debug_shard_mail_cap): forces the overflow path
 static long long shard_mail_cap(const TcPlan& p, long long n_ref, int world) {
-  const long long c = n_ref * (long long)p.cand_cap_planned / (4ll * world * std::max(1, world / 2));
+  if (g_debug_mail_cap > 0) return g_debug_mail_cap;
+  // one outbox holds what ONE rank finds for the rows of ONE other rank: at most one block pair, walked in one direction.
+  // Sized as if every row of the build were at its planned list capacity (the positions are shuffled, so the blocks are
+  // statistically alike): ~2.4x the synthetic load at 1M.  An overflow is detected by the receiver and fails the build
+  // on all ranks (the host side then shards by row blocks).
+  const long long c = n_ref * (long long)p.cand_cap_planned / ((long long)world * world);
   return std::max<long long>(c, 1 << 16);
 }
 static size_t shard_thr_bytes(const TcPlan& p) { return align_up((size_t)p.n_tiles * TC_BN * sizeof(float), 256); }
 
 // every rank hands its (refined) thresholds to all ranks and takes theirs: broadcast by peer stores, barrier, local copy
 struct ShardExchange { TcState* tcs; const TcPlan* plan; const ShardCtx* shard; float* const* xthr; long long n_q; cudaStream_t stream; };
-static int shard_exchange_thr(void* arg) {
+static int shard_exchange_thr(void* arg, int rc) {
   ShardExchange* x = static_cast<ShardExchange*>(arg);
-  int rc = tc_shard_bcast_thr(x->tcs, *x->plan, x->shard->rank, x->shard->world, x->xthr, x->stream);
+  if (!rc) rc = tc_shard_bcast_thr(x->tcs, *x->plan, x->shard->rank, x->shard->world, x->xthr, x->stream);
+  if (!rc && cudaStreamSynchronize(x->stream) != cudaSuccess) { set_error("knn_sym_shard: stream synchronize failed"); rc = SBK_ERR_CUDA; }
+  rc = shard_vote(x->shard, rc);
   if (rc) return rc;
-  SBK_CUDA_CHECK(cudaStreamSynchronize(x->stream));
-  x->shard->barrier(x->shard->barrier_arg);
   SBK_CUDA_CHECK(cudaMemcpyAsync(x->tcs->thr, x->xthr[x->shard->rank], (size_t)x->n_q * sizeof(float), cudaMemcpyDeviceToDevice, x->stream));
   return SBK_OK;
 }
@@ -367,40 +381,52 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
         xmail[r] = reinterpret_cast<uint4*>((char*)shard->xchg[r] + thr_bytes + 256);
       }
       // thresholds of the own rows, handed to every rank
+      tc_trace("start", stream);
       h = tm.begin(&st.ms_sample);
       if (cn > 0) {
         TcState own = tcs; own.thr = tcs.thr + slot_lo;
         rc = tc_sample_chunk(&own, s.plan, slot_lo, cn, w.bound + slot_lo, stream);
       }
       ShardExchange xc; xc.tcs = &tcs; xc.plan = &s.plan; xc.shard = shard; xc.xthr = xthr; xc.n_q = n_q; xc.stream = stream;
-      if (!rc) rc = shard_exchange_thr(&xc);
+      tc_trace("sample", stream);
+      rc = shard_exchange_thr(&xc, rc);
       tm.end(h);
       if (rc) return rc;
+      tc_trace("xchg1", stream);
       int nfl = 0, naux = 0;
       h = tm.begin(&st.ms_filter);
       rc = tc_sym_begin(&tcs, s.plan, w.cand_pair, w.cand_count, w.bound, &naux, stream);
+      tc_trace("begin", stream);
       TcMail mail; memset(&mail, 0, sizeof(mail));
       for (int r = 0; r < world; ++r) mail.out[r] = xmail[rank] + (long long)r * mcap;      // own outbox for rank r (local memory)
       mail.out_cnt = w.n_fail + 8; mail.cap = (int)mcap; mail.blk_pos = tb * TC_BN; mail.own_lo = slot_lo; mail.own_hi = slot_hi;
       // (after its own block every rank refines its thresholds; they are exchanged once more so that the blocks of other
       // ranks are walked against refined column thresholds, and T8 / t are recomputed from them)
-      struct Mid { ShardExchange* xc; TcState* tcs; const TcPlan* plan; cudaStream_t stream; } mid = {&xc, &tcs, &s.plan, stream};
-      auto mid_fn = [](void* a) -> int {
+      struct Mid { ShardExchange* xc; TcState* tcs; const TcPlan* plan; cudaStream_t stream; bool left; } mid = {&xc, &tcs, &s.plan, stream, false};
+      auto mid_fn = [](void* a, int err) -> int {
         Mid* m = static_cast<Mid*>(a);
-        int r2 = shard_exchange_thr(m->xc);
+        tc_trace("own_done", m->stream);
+        int r2 = shard_exchange_thr(m->xc, err);
+        tc_trace("xchg2", m->stream);
+        m->left = (r2 != SBK_OK);          // the vote failed: every rank leaves here
         return r2 ? r2 : tc_refresh_colthr(m->tcs, *m->plan, m->stream);
       };
-      if (!rc) rc = tc_sym_shard_filter(&tcs, s.plan, k, rank, world, w.cand_pair, w.cand_count, w.bound, mail, xcount, &nfl, &naux, stream,
+      if (rc) rc = mid_fn(&mid, rc);          // keeps the barrier count of the other ranks
+      else rc = tc_sym_shard_filter(&tcs, s.plan, k, rank, world, w.cand_pair, w.cand_count, w.bound, mail, xcount, &nfl, &naux, stream,
                                         mid_fn, &mid);
       tm.end(h);
-      if (rc == TC_SYM_POOL_EXHAUSTED) { set_error("knn_sym_shard: group-record pool exhausted"); return SBK_ERR_INTERNAL; }
+      if (rc == TC_SYM_POOL_EXHAUSTED) { set_error("knn_sym_shard: group-record pool exhausted"); rc = SBK_ERR_INTERNAL; }
+      if (mid.left) return rc;                         // agreed at the mid-pass vote: every rank has left already
+      tc_trace("filter_end", stream);
+      rc = shard_vote(shard, rc);                      // every mailbox and count is complete (the filter ended with a stream sync)
       if (rc) return rc;
-      shard->barrier(shard->barrier_arg);              // every mailbox and count is complete (the filter ended with a stream sync)
       h = tm.begin(&st.ms_filter);
       uint4* inbox[8];
       for (int r = 0; r < world; ++r) inbox[r] = xmail[r] + (long long)rank * mcap;          // rank r's outbox for this rank (peer memory)
+      tc_trace("vote3", stream);
       rc = tc_mail_merge(&tcs, s.plan, inbox, xcount[rank], world, (int)mcap, w.cand_pair, w.cand_count, w.n_fail + 16, stream);
       tm.end(h);
+      tc_trace("merge", stream);
       if (rc) return rc;
       st.n_filter_launches += nfl; st.n_launches += 4 + nfl + naux;
       if (cn > 0) {
@@ -421,6 +447,8 @@ static int knn_impl(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t 
       int h_over = 0;
       SBK_CUDA_CHECK(cudaMemcpyAsync(&h_over, w.n_fail + 16, sizeof(int), cudaMemcpyDeviceToHost, stream));
       SBK_CUDA_CHECK(cudaStreamSynchronize(stream));
+      tc_trace("rerank", stream);
+      tc_trace_dump(rank);
       if (h_over) { set_error("knn_sym_shard: a mailbox overflowed (more cross-GPU candidates than planned)"); return SBK_ERR_INTERNAL; }
       st.n_chunks++;
       blocks_done = true;
@@ -672,6 +700,8 @@ extern "C" int sbk_knn_peers(const void* X, int dtype, int64_t n_ref, int32_t d,
                   (cudaStream_t)cuda_stream, nullptr, &po);
 }
 
+extern "C" void sbk_debug_shard_mail_cap(int64_t records) { g_debug_mail_cap = records; }
+
 extern "C" size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t d, int32_t k, int32_t world) {
   if (knn_check(dtype, n_ref, d, 0, n_ref, k) != SBK_OK || world < 2 || world > 8) return 0;
   KnnShape s = knn_shape(dtype, n_ref, d, n_ref, k, SBK_KNN_TENSOR_SYMMETRIC);
@@ -680,7 +710,7 @@ extern "C" size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t
 }
 
 extern "C" int sbk_knn_sym_shard(const void* X, int dtype, int64_t n_ref, int32_t d, int64_t ld, int32_t k,
-                                 int32_t rank, int32_t world, void* const* xchg, void (*barrier)(void*), void* barrier_arg,
+                                 int32_t rank, int32_t world, void* const* xchg, int (*barrier)(void*, int), void* barrier_arg,
                                  void* out_dist, int32_t* out_idx, int32_t n_peers, void* const* peer_dist, int32_t* const* peer_idx,
                                  void* workspace, size_t ws_bytes, sbk_knn_stats* stats, void* cuda_stream) {
   if (world < 2 || world > 8 || rank < 0 || rank >= world || !xchg || !barrier) { set_error("knn_sym_shard: bad rank / world / exchange table"); return SBK_ERR_INVALID; }

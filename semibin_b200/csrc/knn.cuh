@@ -149,9 +149,11 @@ long long tc_shard_block_tiles(const TcPlan& p, int world);
 int tc_shard_bcast_thr(TcState* st, const TcPlan& p, int rank, int world, float* const* xthr, cudaStream_t stream);
 // tile pairs of this rank: own block circulantly, the following (world-1)/2 blocks in full, and for an even world half
 // of the opposite block; row hits and local column hits into the lists, remote column hits into the mailboxes
+void tc_trace(const char* what, cudaStream_t stream);
+void tc_trace_dump(int rank);
 int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,
                         const TcMail& mail, int* const* peer_count_in, int* n_launches, int* n_aux_launches, cudaStream_t stream,
-                        int (*mid_exchange)(void*) = nullptr, void* mid_arg = nullptr);
+                        int (*mid_exchange)(void*, int) = nullptr, void* mid_arg = nullptr);
 // t, T8 of every position from the current thresholds (after thresholds of other ranks arrived)
 int tc_refresh_colthr(TcState* st, const TcPlan& p, cudaStream_t stream);
 // records other ranks hold for this one (boxes[src]: the outbox of rank src for this rank, in src's memory; count_in[src])

@@ -44,6 +44,8 @@
 #include <math.h>
 #include <algorithm>
 #include <vector>
+#include <string>
+#include <time.h>
 #include <type_traits>
 #include <string.h>
 #include <stdlib.h>
@@ -608,7 +610,8 @@ tc_sort_tiles_kernel(long long n, int kpad, __half* __restrict__ a_tiles, __half
 // appended to one of the row's four segments with an atomic counter; a count beyond the segment capacity is the
 // overflow mark the rerank already understands.  One warp per chunk, one record per lane and turn (eight lanes per
 // record with coalesced reads measured 15 % slower: the kernel is bound by the scattered 8-byte candidate stores).
-__global__ void __launch_bounds__(256)
+template <bool MAIL>
+__global__ void __launch_bounds__(256, MAIL ? 3 : 6)
 tc_transpose_kernel(const uint4* __restrict__ pool, int* __restrict__ pool_count, int pool_chunks,
                     long long n, long long n_tiles, long long blk_tiles, const float4* __restrict__ tq,
                     uint2* __restrict__ cand, int32_t* __restrict__ cand_count, int cand_cap,
@@ -626,52 +629,84 @@ tc_transpose_kernel(const uint4* __restrict__ pool, int* __restrict__ pool_count
   const uint4* src = pool + (long long)ch * TC_POOL_STRIDE;
   const int cnt = min((int)src[0].x, TC_POOL_CH);
   if (dbg && lane == 0) atomicAdd(&dbg[2], (unsigned long long)cnt);
-  for (int e = lane; e < cnt; e += 32) {
-    const uint4 hd = src[1 + 3 * e], q0 = src[2 + 3 * e], q1 = src[3 + 3 * e];
-    const long long i = hd.x, j0 = hd.y;
-    const float v[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
-                        __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
-    const float4 qi = tq[i];                                   // (c_i, u_i, t_i)
-    // pairs of one tile block are multiplied circulantly inside the block: its diagonal tiles, and the opposite tiles of an
-    // even block length, hold both orders of their pairs themselves and were row-tested only
-    const long long ti = i / TC_BN, tj = j0 / TC_BN;
-    bool col_on = true;
-    if (ti / blk_tiles == tj / blk_tiles) {
-      const long long len = min(blk_tiles, n_tiles - (ti / blk_tiles) * blk_tiles);
-      long long dt = tj - ti; if (dt < 0) dt = -dt;
-      col_on = !(dt == 0 || dt * 2 == len);
-    }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float sv = __fadd_rd(v[c], qi.x);
-      const long long j = j0 + c;
-      const int ts = (e + c) & 3;
-      if (sv <= qi.z) {
-        const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
-        if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv, qi.y)));
-        else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+  // every turn takes 32 records, one per lane (all lanes stay in the loop: the mailbox part below is warp-collective)
+  for (int e0 = 0; e0 < cnt; e0 += 32) {
+    const int e = e0 + lane;
+    const bool valid = e < cnt;
+    long long i = 0, j0 = 0;
+    bool remote = false;
+    unsigned colm = 0;                                           // columns of a remote owner that passed their test
+    float sv[8];
+    if (valid) {
+      const uint4 hd = src[1 + 3 * e], q0 = src[2 + 3 * e], q1 = src[3 + 3 * e];
+      i = hd.x; j0 = hd.y;
+      const float v[8] = {__uint_as_float(q0.x), __uint_as_float(q0.y), __uint_as_float(q0.z), __uint_as_float(q0.w),
+                          __uint_as_float(q1.x), __uint_as_float(q1.y), __uint_as_float(q1.z), __uint_as_float(q1.w)};
+      const float4 qi = tq[i];                                   // (c_i, u_i, t_i)
+      // pairs of one tile block are multiplied circulantly inside the block: its diagonal tiles, and the opposite tiles of
+      // an even block length, hold both orders of their pairs themselves and were row-tested only
+      const long long ti = i / TC_BN, tj = j0 / TC_BN;
+      bool col_on = true;
+      if (ti / blk_tiles == tj / blk_tiles) {
+        const long long len = min(blk_tiles, n_tiles - (ti / blk_tiles) * blk_tiles);
+        long long dt = tj - ti; if (dt < 0) dt = -dt;
+        col_on = !(dt == 0 || dt * 2 == len);
       }
-      if (col_on) {
-        const float4 qj = tq[j];                               // padding positions: t = -inf
-        if (sv <= qj.z) {
-          if (mail.cap == 0 || (j >= mail.own_lo && j < mail.own_hi)) {
-            const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
-            if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv, qj.y)));
-            else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
-          } else {                                              // the row lives on another GPU: into its mailbox (peer store)
-            // one counter per destination: the lanes that are here together and send to the same rank take their slots with
-            // ONE atomic (54 M single increments of one address cost 30 ms at 1M on two GPUs)
-            const int dst = (int)(j / mail.blk_pos);
-            const unsigned am = __activemask();
-            const unsigned grp = __match_any_sync(am, dst);
-            const int leader = __ffs(grp) - 1;
-            int base = 0;
-            if (lane == leader) base = atomicAdd(&mail.out_cnt[dst], __popc(grp));
-            base = __shfl_sync(grp, base, leader);
-            const int at = base + __popc(grp & ((1u << lane) - 1u));
-            if (at < mail.cap) mail.out[dst][at] = make_uint4((uint32_t)j, (uint32_t)i, __float_as_uint(sv), 0u);
+      // the eight columns of a record are consecutive positions of one tile: one owner
+      remote = MAIL && !(j0 >= mail.own_lo && j0 < mail.own_hi);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        sv[c] = __fadd_rd(v[c], qi.x);
+        const long long j = j0 + c;
+        const int ts = (e + c) & 3;
+        if (sv[c] <= qi.z) {
+          const int at = atomicAdd(&cand_count[i * 4 + ts], 1);
+          if (at < seg_cap) cand[i * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)j, __float_as_uint(__fsub_rd(sv[c], qi.y)));
+          else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+        }
+        if (col_on) {
+          const float4 qj = tq[j];                               // padding positions: t = -inf
+          if (sv[c] <= qj.z) {
+            if (MAIL && remote) colm |= 1u << c;
+            else {
+              const int at = atomicAdd(&cand_count[j * 4 + ts], 1);
+              if (at < seg_cap) cand[j * (long long)cand_cap + (long long)ts * seg_cap + at] = make_uint2((uint32_t)i, __float_as_uint(__fsub_rd(sv[c], qj.y)));
+              else if (dbg && at == seg_cap) atomicAdd(&dbg[1], 1ull);
+            }
           }
         }
+      }
+    }
+    if (MAIL) {
+      // columns that live on another GPU: into the outbox of their owner.  The lanes that send to the same rank take their
+      // slots with ONE atomic per turn (single increments of one address: 30 ms for the 54 M records of 1M on two GPUs)
+      const int rcnt = remote ? __popc(colm) : 0;
+      const int dst = (int)(j0 / mail.blk_pos);
+      unsigned pending = __ballot_sync(0xffffffffu, rcnt > 0);
+      while (pending) {
+        const int lead = __ffs(pending) - 1;
+        const int d0 = __shfl_sync(0xffffffffu, dst, lead);
+        const bool mine = rcnt > 0 && dst == d0;
+        const unsigned grp = __ballot_sync(0xffffffffu, mine);
+        const int mv = mine ? rcnt : 0;
+        int incl = mv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int base = 0;
+        if (lane == lead) base = atomicAdd(&mail.out_cnt[d0], total);
+        base = __shfl_sync(0xffffffffu, base, lead);
+        if (mine) {
+          int at = base + incl - mv;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (colm >> c & 1u) {
+              if (at < mail.cap) mail.out[d0][at] = make_uint4((uint32_t)(j0 + c), (uint32_t)i, __float_as_uint(sv[c]), 0u);
+              ++at;
+            }
+          }
+        }
+        pending &= ~grp;
       }
     }
   }
@@ -1490,6 +1525,32 @@ static long long tc_sym_max_steps(const TcPlan& p) {
   static const long long l2_bytes = (long long)tc_env_int("SBK_TC_L2_MB", (int)(TC_L2_CHUNK_BYTES >> 20)) << 20;
   return std::max<long long>(16, l2_bytes / (long long)p.stage_bytes);
 }
+// SBK_SHARD_TRACE=1: device and host time between named points of the sharded build, printed per rank (development aid)
+struct TcTraceMark { const char* what; cudaEvent_t ev; double host_ms; };
+static std::vector<TcTraceMark> g_trace_marks;
+void tc_trace(const char* what, cudaStream_t stream) {
+  static const int on = tc_env_int("SBK_SHARD_TRACE", 0);
+  if (!on) return;
+  TcTraceMark m; m.what = what;
+  cudaEventCreate(&m.ev); cudaEventRecord(m.ev, stream);
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  m.host_ms = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  g_trace_marks.push_back(m);
+}
+void tc_trace_dump(int rank) {
+  if (g_trace_marks.empty()) return;
+  cudaDeviceSynchronize();
+  std::string line = "shard trace rank " + std::to_string(rank) + ":";
+  for (size_t i = 1; i < g_trace_marks.size(); ++i) {
+    float ms = 0.f; cudaEventElapsedTime(&ms, g_trace_marks[i - 1].ev, g_trace_marks[i].ev);
+    char buf[128]; snprintf(buf, sizeof(buf), " %s %.2f(h%.2f)", g_trace_marks[i].what, ms, g_trace_marks[i].host_ms - g_trace_marks[i - 1].host_ms);
+    line += buf;
+  }
+  fprintf(stderr, "%s\n", line.c_str());
+  for (auto& m : g_trace_marks) cudaEventDestroy(m.ev);
+  g_trace_marks.clear();
+}
+
 // one filter launch over query tiles [q_lo, q_lo + q_len) and the transposes of its records
 static int tc_sym_launch(TcState* st, const TcPlan& p, TcArgs& a, long long q_lo, long long q_len, long long blk_tiles,
                          uint2* cand, int32_t* cand_count, int* n_launches, int* n_aux_launches, cudaStream_t stream,
@@ -1499,16 +1560,21 @@ static int tc_sym_launch(TcState* st, const TcPlan& p, TcArgs& a, long long q_lo
   a.tile_m0 = 2 * q_lo;
   int rc = tc_launch_cg<TC_FILTER_SYM, 2, 1>(a, 2 * q_len, stream);
   if (rc) return rc;
+  tc_trace(a.sym_linear ? "lin" : "circ", stream);
   if (n_launches) ++*n_launches;
   unsigned long long* dbg = nullptr;
 #ifdef SBK_ENABLE_PROBES
   static const int sym_debug = tc_env_int("SBK_SYM_DEBUG", 0);
   if (sym_debug) { dbg = reinterpret_cast<unsigned long long*>(st->maxabs) + 4; SBK_CUDA_CHECK(cudaMemsetAsync(dbg, 0, 32, stream)); }
 #endif
-  tc_transpose_kernel<<<(unsigned)std::min((st->pool_chunks + 7) / 8, 148 * 8), 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, st->n_ref, p.n_tiles,
-                                                                                blk_tiles, st->tq, cand, cand_count, p.cand_cap, dbg, mv);
+  const unsigned tr_grid = (unsigned)std::min((st->pool_chunks + 7) / 8, 148 * 8);
+  if (mail) tc_transpose_kernel<true><<<tr_grid, 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, st->n_ref, p.n_tiles, blk_tiles, st->tq, cand,
+                                                                   cand_count, p.cand_cap, dbg, mv);
+  else tc_transpose_kernel<false><<<tr_grid, 256, 0, stream>>>(st->pool, st->pool_count, st->pool_chunks, st->n_ref, p.n_tiles, blk_tiles, st->tq, cand,
+                                                               cand_count, p.cand_cap, dbg, mv);
   SBK_LAUNCH_CHECK();
   SBK_CUDA_CHECK(cudaMemsetAsync(st->pool_count, 0, 2 * sizeof(int), stream));  // chunks handed out, chunks transposed; [2], the exhaustion flag, stays
+  tc_trace("tr", stream);
 #ifdef SBK_ENABLE_PROBES
   if (sym_debug) {
     unsigned long long h[4];
@@ -1536,6 +1602,7 @@ static int tc_sym_refine(TcState* st, const TcPlan& p, int k, double f, long lon
   tc_colthr_kernel<<<(unsigned)p.n_tiles, 256, 0, stream>>>(st->thr, st->cu, st->n_ref, st->t8, st->tq);
   SBK_LAUNCH_CHECK();
   if (n_aux_launches) *n_aux_launches += 2;
+  tc_trace("refine", stream);
   return SBK_OK;
 }
 
@@ -1693,13 +1760,14 @@ __global__ void tc_mail_counts_kernel(const int* __restrict__ out_cnt, int rank,
 
 int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,
                         const TcMail& mail, int* const* peer_count_in, int* n_launches, int* n_aux_launches, cudaStream_t stream,
-                        int (*mid_exchange)(void*), void* mid_arg) {
+                        int (*mid_exchange)(void*, int), void* mid_arg) {
   if (!st->sym || st->cg != 2) { set_error("tensor kNN: state not prepared for the symmetric filter"); return SBK_ERR_INTERNAL; }
   const long long n = st->n_ref, T = p.n_tiles, tb = tc_shard_block_tiles(p, world);
   const long long lo = (long long)rank * tb, len = std::min(tb, T - lo);
   SBK_CUDA_CHECK(cudaMemsetAsync(mail.out_cnt, 0, 8 * sizeof(int), stream));
   int rc = SBK_OK;
-  if (len > 0) {
+  // (an error in the own block is carried into the mid-pass exchange, whose barrier every rank has to reach)
+  auto own_block = [&]() -> int {
     TcArgs a;
     tc_sym_args(st, p, cand, cand_count, a);
     const long long max_steps = tc_sym_max_steps(p);
@@ -1724,7 +1792,7 @@ int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world
     long long s0 = 0;
     for (size_t li = 0; li < cuts.size(); ++li) {
       a.bt0 = s0; a.n_btiles = cuts[li] - s0;
-      rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream, &mail);
+      int rc = tc_sym_launch(st, p, a, lo, len, tb, cand, cand_count, n_launches, n_aux_launches, stream, &mail);
       if (rc) return rc;
       s0 = cuts[li];
       if (refine_at[li] && s0 < n_steps) {
@@ -1734,12 +1802,13 @@ int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world
       }
     }
     // the own rows have now seen their whole block
-    rc = tc_sym_refine(st, p, k, (double)len / (double)T, lo * TC_BN, std::min(n, (lo + len) * TC_BN), cand, cand_count, bound,
-                       n_aux_launches, stream);
-    if (rc) return rc;
-  }
+    return tc_sym_refine(st, p, k, (double)len / (double)T, lo * TC_BN, std::min(n, (lo + len) * TC_BN), cand, cand_count, bound,
+                         n_aux_launches, stream);
+  };
+  if (len > 0) rc = own_block();
   // refined thresholds of every rank before the blocks of other ranks are walked (every rank calls this, rows or not)
-  if (mid_exchange) { rc = mid_exchange(mid_arg); if (rc) return rc; }
+  if (mid_exchange) rc = mid_exchange(mid_arg, rc);
+  if (rc) return rc;
   if (len > 0) {
     TcArgs a;
     tc_sym_args(st, p, cand, cand_count, a);

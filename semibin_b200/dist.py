@@ -179,18 +179,32 @@ def knn_sharded_sym(X, n_neighbors, bufs, shard, *, return_stats=False):
     st = _lib.KnnStats()
     group = bufs.group
 
-    @C.CFUNCTYPE(None, C.c_void_p)
-    def barrier(_arg):
-        dist.barrier(group=group)
+    flag = torch.zeros(1, dtype=torch.int32, device=X.device)
+
+    def vote(failed):
+        # barrier + "did anybody fail": one small MAX all-reduce, read back
+        flag.fill_(1 if failed else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        return int(flag.item())
+
+    @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int)
+    def barrier(_arg, failed):
+        return vote(failed)
 
     rc = lib.sbk_knn_sym_shard(_lib.ptr(X), dtype, n, d, X.stride(0), k, shard.rank, shard.world, shard.xchg,
                                C.cast(barrier, C.c_void_p), None, _lib.ptr(bufs.dist), _lib.ptr(bufs.idx),
                                bufs.n_peers, bufs.peer_dist, bufs.peer_idx, _lib.ptr(ws), ws.numel(), C.byref(st),
                                _lib.stream_ptr(X.device))
-    _lib.check(rc)
     # the call returns with this rank's stream drained; once every rank has got here every full buffer is complete and
-    # nobody reads its mailboxes any more
-    dist.barrier(group=group)
+    # nobody reads its mailboxes any more.  The same vote tells every rank whether the build held everywhere (a pool or
+    # mailbox that was too small fails it on all ranks together): if not, all ranks shard by row blocks instead.
+    if rc not in (_lib.SBK_OK, _lib.SBK_ERR_INTERNAL):
+        _lib.check(rc)
+    why = _lib.last_error() if rc else ''
+    if vote(rc != _lib.SBK_OK):
+        out = knn_sharded_p2p(X, k, bufs, algo='tensor_onesided', return_stats=True)
+        out[2]['sym_shard_fallback'] = why or 'another rank failed'
+        return out if return_stats else out[:2]
     if return_stats:
         return bufs.dist, bufs.idx, st.as_dict()
     return bufs.dist, bufs.idx

@@ -1,0 +1,52 @@
+"""Sharded symmetric build (`sbk_knn_sym_shard`, semibin_b200.dist.knn_sharded_sym): one process per GPU under torchrun,
+NCCL + symmetric memory.  Needs at least two GPUs (skipped on a one-GPU box; scripts/gpu_two_gpus.sh runs it)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(world, *script_args, port=29533):
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
+           '--master-port', str(port), os.path.join(ROOT, 'scripts', 'shard_sym_check.py'), *script_args]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
+
+
+def _world():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip('needs two GPUs')
+    return 4 if n >= 4 else 2
+
+
+def test_sharded_symmetric_build_equals_exact_and_row_blocks():
+    """41k x k=50 (every rank: circulant own block, full and split block pairs, mailboxes): bitwise the exact path's and
+    the row-block build's result on every rank; 450k x k=200 against the row-block build."""
+    world = _world()
+    rows = _torchrun(world, '--iters', '1', '41000', '450000')
+    assert len(rows) == 2 * world
+    for r in rows:
+        assert r['sym_equals_rowblock'], r
+        assert r['sym']['symmetric'] == 1 and 'sym_shard_fallback' not in r['sym'], r
+        assert r['sym']['n_fallback_rows'] == 0, r
+        if r['n'] == 41000:
+            assert r['sym_equals_exact'], r
+
+
+def test_sharded_symmetric_build_mailbox_overflow_votes_for_row_blocks():
+    """Mailboxes of 1024 records: the receiving ranks see the overflow, the vote sends all ranks to the row-block build
+    and the result is still the exact one."""
+    world = _world()
+    rows = _torchrun(world, '--starve', '--iters', '1', '41000', port=29534)
+    assert len(rows) == world
+    for r in rows:
+        assert 'sym_shard_fallback' in r['sym'], r
+        assert r['sym_equals_rowblock'] and r['sym_equals_exact'], r
