@@ -74,7 +74,7 @@ class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU while the timed region runs: the `nvidia-smi -lms 200`
     line of B200_PROFILING.md as a child process (an in-process NVML poller can hold driver locks the CUDA
     launches of this process need; a 50 ms pynvml thread cost an occasional 100+ ms stall in one step)."""
-    FIELDS = ('clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,'
+    FIELDS = ('timestamp,clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,'
               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
               'clocks_event_reasons.sw_power_cap')
 
@@ -84,6 +84,13 @@ class ClockSampler:
         self.stop_flag = False
         self.err = None
         self.lines = []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         import subprocess
@@ -109,24 +116,33 @@ class ClockSampler:
                 pass
 
     def summary(self):
-        samples, reasons, max_mhz = [], set(), None
+        import datetime
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows, max_mhz = [], None
         for ln in self.lines:
             f = [x.strip() for x in ln.split(',')]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                samples.append((float(f[0]), float(f[2])))
-                max_mhz = float(f[1])
+                ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(f[1]), float(f[3]), [nm for nm, v in zip(names, f[4:8]) if v.lower().startswith('active')]))
+                max_mhz = float(f[2])
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith('active'):
-                    reasons.add(nm)
+        # the child is started before the warm-up steps (its start-up takes longer than a short timed region); the samples
+        # of the timed steps count, and when the timed region is shorter than the sampling period, those of the warm-up
+        # steps right before it (same kernels, same load)
+        window = 'timed steps'
+        inside = [r for r in rows if self.t_begin is None or (self.t_begin <= r[0] <= (self.t_end or r[0]))]
+        if not inside and rows:
+            inside = [r for r in rows if r[2] >= 50] or rows[-2:]
+            window = 'warm-up + timed steps (no sample fell inside the timed region)'
+        samples = [(m, u) for _, m, u, _ in inside]
+        reasons = {nm for r in inside for nm in r[3]}
         loaded = [m for m, u in samples if u >= 50] or [m for m, _ in samples]
         med = float(np.median(loaded)) if loaded else None
-        out = {'sm_mhz': med, 'sm_max_mhz': max_mhz, 'reasons': sorted(reasons), 'samples': len(samples),
-               'how': 'nvidia-smi -lms 200 child process during the timed steps'}
+        out = {'sm_mhz': med, 'sm_max_mhz': max_mhz, 'reasons': sorted(reasons), 'samples': len(samples), 'window': window,
+               'how': 'nvidia-smi -lms 200 child process started before the warm-up'}
         if self.err:
             out['error'] = self.err
         return out
@@ -279,11 +295,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier(group=cpu_group)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark_begin()
     stats = []
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step_evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -294,6 +311,7 @@ def run_ours(args):
         step_evs[s_i + 1].record()
     ev1.record()
     barrier()
+    sampler.mark_end()
     sampler.join()
     ms_total = ev0.elapsed_time(ev1)
     ms_each = [step_evs[j].elapsed_time(step_evs[j + 1]) for j in range(args.steps)]
