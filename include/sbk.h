@@ -292,6 +292,13 @@ int sbk_knn_sym_shard(const void* X, int dtype, int64_t n_ref, int32_t d, int64_
  * Set it identically on every rank BEFORE sbk_knn_sym_shard_xchg_bytes; a small value forces the overflow vote. */
 void sbk_debug_shard_mail_cap(int64_t records);
 
+/* Debug / test hook, host only: the tile products sbk_knn_sym_shard launches on `rank` of `world` for a build of n_tiles
+ * 256-row tiles.  Writes five int64 per step into out (at most max_steps steps): kind, q_lo, q_len, j_lo, j_len --
+ * kind 0: the block of query tiles [q_lo, q_lo + q_len) against itself, circulant (tile I x tile q_lo + (I - q_lo + s) mod
+ * q_len for s = 0 .. q_len / 2); kind 1: query tiles [q_lo, q_lo + q_len) x reference tiles [j_lo, j_lo + j_len).
+ * Returns the number of steps (< 0: error).  Over all ranks every ordered pair of tiles is tested exactly once. */
+int sbk_debug_sym_shard_schedule(int64_t n_tiles, int32_t world, int32_t rank, int64_t* out, int32_t max_steps);
+
 /* Debug / test hook: raw tcgen05 tile product.  Runs the same FP16 operand staging and
  * MMA pipeline as the tensor filter and returns the accumulator values
  *   L[i,j] <= S^2 d2_ij - nrm_i + norms4[i].w      (i < n_q, j < n_ref <= 65536)

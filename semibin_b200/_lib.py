@@ -86,6 +86,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_size_t, C.c_void_p]),
     'sbk_debug_shard_mail_cap': (None, [C.c_int64]),
+    'sbk_debug_sym_shard_schedule': (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     'sbk_debug_tc_workspace_bytes': (C.c_size_t, [C.c_int64, C.c_int32]),
     'sbk_debug_tc_scores': (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

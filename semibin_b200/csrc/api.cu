@@ -702,6 +702,17 @@ extern "C" int sbk_knn_peers(const void* X, int dtype, int64_t n_ref, int32_t d,
 
 extern "C" void sbk_debug_shard_mail_cap(int64_t records) { g_debug_mail_cap = records; }
 
+// host only (no device needed): the tile products sbk_knn_sym_shard launches on `rank`, five int64 per step
+extern "C" int sbk_debug_sym_shard_schedule(int64_t n_tiles, int32_t world, int32_t rank, int64_t* out, int32_t max_steps) {
+  if (n_tiles < 1 || world < 1 || world > 8 || rank < 0 || rank >= world) { set_error("sym_shard_schedule: bad arguments"); return SBK_ERR_INVALID; }
+  const std::vector<TcShardStep> steps = tc_shard_schedule(n_tiles, world, rank);
+  for (size_t i = 0; i < steps.size() && (int)i < max_steps && out; ++i) {
+    out[5 * i + 0] = steps[i].kind; out[5 * i + 1] = steps[i].q_lo; out[5 * i + 2] = steps[i].q_len;
+    out[5 * i + 3] = steps[i].j_lo; out[5 * i + 4] = steps[i].j_len;
+  }
+  return (int)steps.size();
+}
+
 extern "C" size_t sbk_knn_sym_shard_xchg_bytes(int dtype, int64_t n_ref, int32_t d, int32_t k, int32_t world) {
   if (knn_check(dtype, n_ref, d, 0, n_ref, k) != SBK_OK || world < 2 || world > 8) return 0;
   KnnShape s = knn_shape(dtype, n_ref, d, n_ref, k, SBK_KNN_TENSOR_SYMMETRIC);

@@ -1,6 +1,7 @@
 // knn.cuh -- internal launch interfaces of the kNN pipeline stages.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace sbk {
 
@@ -149,6 +150,8 @@ long long tc_shard_block_tiles(const TcPlan& p, int world);
 int tc_shard_bcast_thr(TcState* st, const TcPlan& p, int rank, int world, float* const* xthr, cudaStream_t stream);
 // tile pairs of this rank: own block circulantly, the following (world-1)/2 blocks in full, and for an even world half
 // of the opposite block; row hits and local column hits into the lists, remote column hits into the mailboxes
+struct TcShardStep { int kind; long long q_lo, q_len, j_lo, j_len; };
+std::vector<TcShardStep> tc_shard_schedule(long long n_tiles, int world, int rank);
 void tc_trace(const char* what, cudaStream_t stream);
 void tc_trace_dump(int rank);
 int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,

@@ -1758,6 +1758,33 @@ __global__ void tc_mail_counts_kernel(const int* __restrict__ out_cnt, int rank,
   if (r < world) reinterpret_cast<int*>(ptrs.out[r])[rank] = out_cnt[r];
 }
 
+// The tile products of one rank of the sharded symmetric build, as tile ranges.  kind 0: the own block [q_lo, q_lo + q_len),
+// circulant inside itself (steps 0 .. q_len / 2; j_lo / j_len repeat the block); kind 1: query tiles [q_lo, q_lo + q_len)
+// against every tile of [j_lo, j_lo + j_len).  Over all ranks every ordered pair of tiles is tested exactly once: a
+// product (I, J) tests the rows of I against J and -- except on the diagonal and the opposite tiles of an even-length
+// circulant block, which hold both orders themselves -- the rows of J against I (tests/test_host_logic.py walks this
+// list for every world size through sbk_debug_sym_shard_schedule; tc_sym_shard_filter launches exactly this list).
+std::vector<TcShardStep> tc_shard_schedule(long long T, int world, int rank) {
+  std::vector<TcShardStep> steps;
+  const long long tb = (T + world - 1) / world;
+  const long long lo = (long long)rank * tb, len = std::min(tb, T - lo);
+  if (len <= 0) return steps;
+  steps.push_back({0, lo, len, lo, len});
+  const int h_full = (world - 1) / 2;
+  for (int s = 1; s <= h_full; ++s) {
+    const long long c = (rank + s) % world, clo = c * tb, clen = std::min(tb, T - clo);
+    if (clen > 0) steps.push_back({1, lo, len, clo, clen});
+  }
+  if ((world & 1) == 0) {
+    // the opposite block pair is shared: the lower rank takes its rows x the first half of the other block's tiles, the
+    // upper rank the second half of ITS tiles (as rows) x all tiles of the lower block
+    const long long c = (rank + world / 2) % world, clo = c * tb, clen = std::max<long long>(0, std::min(tb, T - clo));
+    if (rank < world / 2) { if (clen / 2 > 0) steps.push_back({1, lo, len, clo, clen / 2}); }
+    else { const long long h = len / 2; if (len - h > 0 && clen > 0) steps.push_back({1, lo + h, len - h, clo, clen}); }
+  }
+  return steps;
+}
+
 int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world, uint2* cand, int32_t* cand_count, double* bound,
                         const TcMail& mail, int* const* peer_count_in, int* n_launches, int* n_aux_launches, cudaStream_t stream,
                         int (*mid_exchange)(void*, int), void* mid_arg) {
@@ -1823,17 +1850,10 @@ int tc_sym_shard_filter(TcState* st, const TcPlan& p, int k, int rank, int world
       }
       return SBK_OK;
     };
-    const int h_full = (world - 1) / 2;
-    for (int s = 1; s <= h_full; ++s) {
-      const long long c = (rank + s) % world, clo = c * tb, clen = std::min(tb, T - clo);
-      if (clen > 0) { rc = linear(lo, len, clo, clen); if (rc) return rc; }
-    }
-    if ((world & 1) == 0) {
-      // the opposite block pair is shared: the lower rank takes its rows x the first half of the other block's tiles, the
-      // upper rank the second half of ITS tiles (as rows) x all tiles of the lower block
-      const long long c = (rank + world / 2) % world, clo = c * tb, clen = std::max<long long>(0, std::min(tb, T - clo));
-      if (rank < world / 2) { if (clen / 2 > 0) { rc = linear(lo, len, clo, clen / 2); if (rc) return rc; } }
-      else { const long long h = len / 2; if (len - h > 0 && clen > 0) { rc = linear(lo + h, len - h, clo, clen); if (rc) return rc; } }
+    for (const TcShardStep& sp : tc_shard_schedule(T, world, rank)) {
+      if (sp.kind != 1) continue;                    // (kind 0, the own block, ran before the exchange)
+      rc = linear(sp.q_lo, sp.q_len, sp.j_lo, sp.j_len);
+      if (rc) return rc;
     }
   }
   // how many records went to every rank (into their count_in[this rank])

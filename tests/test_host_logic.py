@@ -149,3 +149,40 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--contigs', '3000',
                           '--neighbors', '20', '--steps', '1', '--warmup', '1'], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+@pytest.mark.parametrize('world', [1, 2, 3, 4, 5, 6, 7, 8])
+def test_sym_shard_schedule_tests_every_ordered_tile_pair_once(world):
+    """The tile products `sbk_knn_sym_shard` launches (sbk_debug_sym_shard_schedule returns the very list the launcher
+    walks; host only): over all ranks every ORDERED pair of tiles must be tested exactly once -- a product (I, J) tests
+    the rows of I against J and, unless the circulant own block holds both orders of the pair itself (diagonal, opposite
+    tiles of an even block), the rows of J against I.  Tile counts: fewer tiles than ranks allow blocks for, ragged last
+    blocks, odd and even block lengths, the BASELINE size (3907 tiles)."""
+    import ctypes as C
+    from semibin_b200 import _lib
+    lib = _lib.load()
+    for T in (8, 12, 13, 37, 161, 1000, 3907):
+        seen = np.zeros((T, T), dtype=np.uint8)
+        n_products = 0
+        for rank in range(world):
+            buf = np.zeros(5 * 16, dtype=np.int64)
+            ns = lib.sbk_debug_sym_shard_schedule(T, world, rank, buf.ctypes.data_as(C.c_void_p), 16)
+            assert 0 <= ns <= 16
+            for kind, q_lo, q_len, j_lo, j_len in buf[:5 * ns].reshape(ns, 5):
+                if kind == 0:
+                    assert (j_lo, j_len) == (q_lo, q_len)
+                    I = np.arange(q_lo, q_lo + q_len)
+                    for s in range(q_len // 2 + 1):
+                        J = q_lo + (I - q_lo + s) % q_len
+                        seen[I, J] += 1
+                        if not (s == 0 or 2 * s == q_len):
+                            seen[J, I] += 1
+                        n_products += q_len
+                else:
+                    assert j_lo + j_len <= q_lo or q_lo + q_len <= j_lo      # never its own block
+                    seen[q_lo:q_lo + q_len, j_lo:j_lo + j_len] += 1
+                    seen[j_lo:j_lo + j_len, q_lo:q_lo + q_len] += 1
+                    n_products += q_len * j_len
+        assert seen.min() == 1 and seen.max() == 1, (T, world, int(seen.min()), int(seen.max()))
+        assert n_products <= T * (T // 2 + 1) + world * T               # half the one-sided T * T products
+    assert lib.sbk_debug_sym_shard_schedule(8, 9, 0, None, 0) < 0
