@@ -186,3 +186,33 @@ def test_sym_shard_schedule_tests_every_ordered_tile_pair_once(world):
         assert seen.min() == 1 and seen.max() == 1, (T, world, int(seen.min()), int(seen.max()))
         assert n_products <= T * (T // 2 + 1) + world * T               # half the one-sided T * T products
     assert lib.sbk_debug_sym_shard_schedule(8, 9, 0, None, 0) < 0
+
+
+def test_bench_clock_sampler_window():
+    """bench.py's clock summary: samples inside the timed region count; a timed region shorter than the sampling period
+    (8 GPUs: 5 steps of 27 ms) falls back to the loaded samples of the warm-up steps and says so."""
+    import datetime
+    import importlib.util
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_for_test', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        spec.loader.exec_module(bench)
+    finally:
+        sys.argv = argv
+    now = time.time()
+    fmt = lambda t: datetime.datetime.fromtimestamp(t).strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]
+    s = bench.ClockSampler(0)
+    s.lines = [f'{fmt(now - 1.0)}, 1800, 1965, 100, Not Active, Not Active, Not Active, Active',
+               f'{fmt(now - 0.5)}, 1900, 1965, 10, Not Active, Not Active, Not Active, Not Active',
+               f'{fmt(now + 0.1)}, 1950, 1965, 99, Not Active, Not Active, Not Active, Not Active',
+               'garbage line']
+    s.t_begin, s.t_end = now, now + 0.2
+    out = s.summary()
+    assert out['samples'] == 1 and out['sm_mhz'] == 1950.0 and out['reasons'] == [] and out['window'] == 'timed steps'
+    s.t_begin, s.t_end = now + 0.12, now + 0.2
+    out = s.summary()
+    assert out['samples'] == 2 and out['sm_mhz'] == 1875.0 and out['reasons'] == ['sw_power_cap']
+    assert out['window'].startswith('warm-up') and out['sm_max_mhz'] == 1965.0
