@@ -216,3 +216,76 @@ def test_bench_clock_sampler_window():
     out = s.summary()
     assert out['samples'] == 2 and out['sm_mhz'] == 1875.0 and out['reasons'] == ['sw_power_cap']
     assert out['window'].startswith('warm-up') and out['sm_max_mhz'] == 1965.0
+
+
+class _FakeShardLib:
+    """Stands in for libsbk in the world-2 gloo test of `knn_sharded_sym`'s control flow: calls the barrier callback three
+    times like sbk_knn_sym_shard (failing rank: reports the failure at `fail_at`, everybody leaves at the first vote that
+    says so), or fails only at the end (a mailbox overflow is seen by the receiver alone)."""
+
+    def __init__(self, rank, fail_rank, fail_at):
+        self.rank, self.fail_rank, self.fail_at = rank, fail_rank, fail_at
+        self.votes = 0
+
+    def sbk_knn_workspace_bytes(self, *a):
+        return 64
+
+    def sbk_last_error(self):
+        return b'fake: mailbox overflowed'
+
+    def sbk_knn_sym_shard(self, X, dtype, n, d, ld, k, rank, world, xchg, barrier, barrier_arg, *rest):
+        import ctypes as C
+        vote = C.cast(barrier, C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int))
+        for phase in range(3):
+            mine = int(self.rank == self.fail_rank and self.fail_at == phase)
+            self.votes += 1
+            if vote(None, mine):
+                return -4
+        return -4 if (self.rank == self.fail_rank and self.fail_at == 3) else 0
+
+
+def _shard_vote_worker(rank, world, port, tmp):
+    import types
+    import torch
+    import torch.distributed as dist
+    from semibin_b200 import _lib, neighbors
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    X = torch.zeros((64, 8), dtype=torch.float32)
+    bufs = types.SimpleNamespace(group=dist.group.WORLD, dist=torch.zeros(1), idx=torch.zeros(1, dtype=torch.int32), n_peers=0,
+                                 peer_dist=None, peer_idx=None)
+    shard = types.SimpleNamespace(shape=(64, 8, 5, torch.float32), rank=rank, world=world, xchg=None)
+    fell_back = []
+    sd.knn_sharded_p2p = lambda X, k, bufs, algo='auto', return_stats=False: (fell_back.append(algo) or (bufs.dist, bufs.idx, {}))
+    _lib.stream_ptr = lambda dev: None
+    neighbors._workspace = lambda nbytes, dev: torch.zeros(int(nbytes), dtype=torch.uint8)
+    rows = []
+    for fail_rank, fail_at in ((-1, -1), (1, 0), (0, 1), (1, 2), (0, 3)):
+        fake = _FakeShardLib(rank, fail_rank, fail_at)
+        _lib.load = lambda fake=fake: fake
+        fell_back.clear()
+        _, _, st = sd.knn_sharded_sym(X, 5, bufs, shard, return_stats=True)
+        rows.append((fake.votes, list(fell_back), st.get('sym_shard_fallback')))
+    import json
+    with open(os.path.join(tmp, f'vote{rank}.json'), 'w') as fh:
+        json.dump(rows, fh)
+    dist.destroy_process_group()
+
+
+def test_sharded_symmetric_vote_gloo_world2(tmp_path):
+    """Host side of the sharded symmetric build on two gloo ranks with a fake library: whichever rank fails and wherever,
+    BOTH ranks leave the build at the same vote and both redo it by row blocks; a build that held everywhere is kept."""
+    import json
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_shard_vote_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = [json.load(open(tmp_path / f'vote{r}.json')) for r in range(2)]
+    expect_votes = [3, 1, 2, 3, 3]            # votes called until everybody has left
+    for r in range(2):
+        for case, (votes, fell_back, why) in enumerate(got[r]):
+            assert votes == expect_votes[case], (r, case, votes)
+            if case == 0:
+                assert fell_back == [] and why is None
+            else:
+                assert fell_back == ['tensor_onesided'] and why, (r, case, fell_back, why)
